@@ -1,0 +1,624 @@
+// api.cu — the extern "C" surface of libabsb200.so (include/absb200.h) for the index half of the
+// path: library/device queries, the synthetic generator, IndexFlatIP and IndexIVFFlat.
+// The encoder entry points live in encoder.cu.
+//
+// Every function is a thin shell: validate, pick the stream, stage host buffers, call the C++
+// object, translate exceptions into error codes.  No exception crosses the boundary.
+#include <mutex>
+
+#include "common.cuh"
+#include "ivf.cuh"
+
+namespace absb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+
+DeviceProps device_props(int device) {
+  static std::mutex mu;
+  static std::vector<DeviceProps> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  int count = 0;
+  ABSB_CUDA(cudaGetDeviceCount(&count));
+  ABSB_CHECK(device >= 0 && device < count, ABSB_ERR_INVALID, "device %d out of range (count=%d)", device, count);
+  if ((int)cache.size() < count) cache.resize(count);
+  DeviceProps& p = cache[device];
+  if (p.sm_count == 0) {
+    int v = 0;
+    ABSB_CUDA(cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, device));
+    ABSB_CUDA(cudaDeviceGetAttribute(&p.cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    ABSB_CUDA(cudaDeviceGetAttribute(&p.cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+    ABSB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    p.smem_optin = (size_t)v;
+  }
+  return p;
+}
+
+// The library carries sm_100a code only: anything else cannot run it, and there is no fallback.
+static void require_sm100(int device) {
+  const DeviceProps p = device_props(device);
+  ABSB_CHECK(p.cc_major == 10, ABSB_ERR_UNSUPPORTED,
+             "device %d is sm_%d%d; libabsb200 is built for sm_100a (B200) only and has no fallback",
+             device, p.cc_major, p.cc_minor);
+}
+
+namespace {
+
+// Stages a host array into a device workspace on st (async; caller syncs before reusing `src`).
+template <typename T>
+T* stage_in(DBuf<T>& ws, const T* src, size_t n, cudaStream_t st) {
+  ws.reserve(std::max<size_t>(n, 1));
+  if (n) ABSB_CUDA(cudaMemcpyAsync(ws.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+  return ws.p;
+}
+
+template <typename T>
+void fetch_out(T* dst, const T* src_dev, size_t n, cudaStream_t st) {
+  if (n) ABSB_CUDA(cudaMemcpyAsync(dst, src_dev, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+}
+
+}  // namespace
+}  // namespace absb
+
+using namespace absb;
+
+struct absb_ivf_s {
+  IvfIndex ix;
+  absb_ivf_s(int d, int nlist, int device) : ix(d, nlist, device) {}
+};
+struct absb_flat_s {
+  FlatIndex ix;
+  absb_flat_s(int d, int device) : ix(d, device) {}
+};
+
+#define NEED(p) ABSB_CHECK((p) != nullptr, ABSB_ERR_INVALID, "null argument: " #p)
+
+extern "C" {
+
+// ------------------------------------------------------------------ library -----------------
+int absb_version(void) { return 100; }
+
+const char* absb_last_error(void) { return g_last_error.c_str(); }
+
+int absb_device_count(int* count) {
+  ABSB_API_BEGIN
+  NEED(count);
+  ABSB_CUDA(cudaGetDeviceCount(count));
+  ABSB_API_END
+}
+
+int absb_device_info(int device, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor) {
+  ABSB_API_BEGIN
+  const DeviceProps p = device_props(device);
+  if (name && name_len > 0) {
+    cudaDeviceProp prop;
+    ABSB_CUDA(cudaGetDeviceProperties(&prop, device));
+    snprintf(name, (size_t)name_len, "%s", prop.name);
+  }
+  if (sm_count) *sm_count = p.sm_count;
+  if (cc_major) *cc_major = p.cc_major;
+  if (cc_minor) *cc_minor = p.cc_minor;
+  ABSB_API_END
+}
+
+// ------------------------------------------------------------------ synthetic ---------------
+int absb_synth_fill_dev(int kind, uint64_t seed, int64_t row0, int64_t n, int d, int nlist,
+                        int64_t corpus_rows, float* out_dev, void* stream) {
+  ABSB_API_BEGIN
+  ABSB_CHECK(n == 0 || out_dev, ABSB_ERR_INVALID, "null output");
+  synth_fill(kind, seed, row0, n, d, nlist, corpus_rows, out_dev, (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_synth_cluster_dev(uint64_t seed, int64_t row0, int64_t n, int nlist, int64_t* out_dev,
+                           void* stream) {
+  ABSB_API_BEGIN
+  ABSB_CHECK(n == 0 || out_dev, ABSB_ERR_INVALID, "null output");
+  ABSB_CHECK(nlist > 0, ABSB_ERR_INVALID, "nlist=%d", nlist);
+  synth_cluster(seed, row0, n, nlist, reinterpret_cast<long long*>(out_dev), (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+// ------------------------------------------------------------------ IndexFlatIP -------------
+int absb_flat_create(int d, int metric, int device, absb_flat_t* out) {
+  ABSB_API_BEGIN
+  NEED(out);
+  ABSB_CHECK(metric == ABSB_METRIC_INNER_PRODUCT, ABSB_ERR_UNSUPPORTED,
+             "only METRIC_INNER_PRODUCT is on the abstracts-search path (metric=%d)", metric);
+  require_sm100(device);
+  *out = new absb_flat_s(d, device);
+  ABSB_API_END
+}
+
+int absb_flat_destroy(absb_flat_t h) {
+  ABSB_API_BEGIN
+  delete h;
+  ABSB_API_END
+}
+
+int absb_flat_reset(absb_flat_t h) {
+  ABSB_API_BEGIN
+  NEED(h);
+  DeviceGuard g(h->ix.device);
+  ABSB_CUDA(cudaStreamSynchronize(h->ix.own_stream));
+  h->ix.xb.release();
+  h->ix.ntotal = 0;
+  ABSB_API_END
+}
+
+int absb_flat_ntotal(absb_flat_t h, int64_t* ntotal) {
+  ABSB_API_BEGIN
+  NEED(h); NEED(ntotal);
+  *ntotal = h->ix.ntotal;
+  ABSB_API_END
+}
+
+int absb_flat_add_dev(absb_flat_t h, int64_t n, const float* x_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || x_dev), ABSB_ERR_INVALID, "bad add arguments");
+  DeviceGuard g(h->ix.device);
+  h->ix.add_dev(n, x_dev, (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_flat_add(absb_flat_t h, int64_t n, const float* x) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || x), ABSB_ERR_INVALID, "bad add arguments");
+  FlatIndex& ix = h->ix;
+  DeviceGuard g(ix.device);
+  cudaStream_t st = ix.own_stream;
+  const int64_t step = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)ix.d * 4));
+  for (int64_t r0 = 0; r0 < n; r0 += step) {
+    const int64_t nr = std::min(step, n - r0);
+    const float* xd = stage_in(ix.ws_x, x + r0 * ix.d, (size_t)nr * ix.d, st);
+    ix.add_dev(nr, xd, st);
+    ABSB_CUDA(cudaStreamSynchronize(st));
+  }
+  ABSB_API_END
+}
+
+int absb_flat_search_dev(absb_flat_t h, int64_t n, const float* q_dev, int k, float* D_dev,
+                         int64_t* I_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || (q_dev && D_dev && I_dev)), ABSB_ERR_INVALID, "bad search arguments");
+  DeviceGuard g(h->ix.device);
+  h->ix.search_dev(n, q_dev, k, D_dev, reinterpret_cast<long long*>(I_dev), (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_flat_search(absb_flat_t h, int64_t n, const float* q, int k, float* D, int64_t* I) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || (q && D && I)), ABSB_ERR_INVALID, "bad search arguments");
+  ABSB_CHECK(k >= 1 && k <= ABSB_MAX_K, ABSB_ERR_INVALID, "k=%d outside [1,%d]", k, ABSB_MAX_K);
+  FlatIndex& ix = h->ix;
+  DeviceGuard g(ix.device);
+  cudaStream_t st = ix.own_stream;
+  const int64_t step = 8192;
+  ix.ws_D.reserve((size_t)std::min(step, std::max<int64_t>(n, 1)) * k);
+  ix.ws_I.reserve((size_t)std::min(step, std::max<int64_t>(n, 1)) * k);
+  for (int64_t r0 = 0; r0 < n; r0 += step) {
+    const int64_t nr = std::min(step, n - r0);
+    const float* qd = stage_in(ix.ws_x, q + r0 * ix.d, (size_t)nr * ix.d, st);
+    ix.search_dev(nr, qd, k, ix.ws_D.p, ix.ws_I.p, st);
+    fetch_out(D + r0 * k, ix.ws_D.p, (size_t)nr * k, st);
+    fetch_out(reinterpret_cast<long long*>(I) + r0 * k, ix.ws_I.p, (size_t)nr * k, st);
+    ABSB_CUDA(cudaStreamSynchronize(st));
+  }
+  ABSB_API_END
+}
+
+int absb_flat_reconstruct(absb_flat_t h, int64_t i0, int64_t n, float* x) {
+  ABSB_API_BEGIN
+  NEED(h);
+  FlatIndex& ix = h->ix;
+  ABSB_CHECK(i0 >= 0 && n >= 0 && i0 + n <= ix.ntotal && (n == 0 || x), ABSB_ERR_INVALID,
+             "reconstruct range [%lld,%lld) outside [0,%lld)", (long long)i0, (long long)(i0 + n), (long long)ix.ntotal);
+  DeviceGuard g(ix.device);
+  ABSB_CUDA(cudaStreamSynchronize(ix.own_stream));
+  if (n) ABSB_CUDA(cudaMemcpy(x, ix.xb.p + (size_t)i0 * ix.d, sizeof(float) * (size_t)n * ix.d, cudaMemcpyDeviceToHost));
+  ABSB_API_END
+}
+
+// ------------------------------------------------------------------ IndexIVFFlat ------------
+int absb_ivf_create(int d, int nlist, int metric, int device, absb_ivf_t* out) {
+  ABSB_API_BEGIN
+  NEED(out);
+  ABSB_CHECK(metric == ABSB_METRIC_INNER_PRODUCT, ABSB_ERR_UNSUPPORTED,
+             "only METRIC_INNER_PRODUCT is on the abstracts-search path (metric=%d)", metric);
+  require_sm100(device);
+  *out = new absb_ivf_s(d, nlist, device);
+  ABSB_API_END
+}
+
+int absb_ivf_destroy(absb_ivf_t h) {
+  ABSB_API_BEGIN
+  delete h;
+  ABSB_API_END
+}
+
+int absb_ivf_reset(absb_ivf_t h) {
+  ABSB_API_BEGIN
+  NEED(h);
+  h->ix.reset();
+  ABSB_API_END
+}
+
+int absb_ivf_ntotal(absb_ivf_t h, int64_t* ntotal) {
+  ABSB_API_BEGIN
+  NEED(h); NEED(ntotal);
+  *ntotal = h->ix.ntotal;
+  ABSB_API_END
+}
+
+int absb_ivf_is_trained(absb_ivf_t h, int* trained) {
+  ABSB_API_BEGIN
+  NEED(h); NEED(trained);
+  *trained = h->ix.trained ? 1 : 0;
+  ABSB_API_END
+}
+
+int absb_ivf_set_clustering(absb_ivf_t h, int niter, int max_points_per_centroid,
+                            int min_points_per_centroid, int64_t seed) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(niter >= 0 && max_points_per_centroid >= 1, ABSB_ERR_INVALID, "bad clustering parameters");
+  h->ix.cp.niter = niter;
+  h->ix.cp.max_points_per_centroid = max_points_per_centroid;
+  h->ix.cp.min_points_per_centroid = min_points_per_centroid;
+  h->ix.cp.seed = seed;
+  ABSB_API_END
+}
+
+int absb_ivf_train(absb_ivf_t h, int64_t n, const float* x) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || x), ABSB_ERR_INVALID, "bad train arguments");
+  DeviceGuard g(h->ix.device);
+  h->ix.train_host(n, x);
+  ABSB_API_END
+}
+
+int absb_ivf_train_dev(absb_ivf_t h, int64_t n, const float* x_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || x_dev), ABSB_ERR_INVALID, "bad train arguments");
+  DeviceGuard g(h->ix.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  h->ix.train_dev(n, x_dev, st);
+  ABSB_CUDA(cudaStreamSynchronize(st));
+  ABSB_API_END
+}
+
+int absb_ivf_set_centroids(absb_ivf_t h, const float* centroids) {
+  ABSB_API_BEGIN
+  NEED(h); NEED(centroids);
+  IvfIndex& ix = h->ix;
+  DeviceGuard g(ix.device);
+  ABSB_CUDA(cudaStreamSynchronize(ix.own_stream));
+  ABSB_CUDA(cudaMemcpy(ix.centroids.p, centroids, sizeof(float) * (size_t)ix.nlist * ix.d, cudaMemcpyHostToDevice));
+  ix.trained = true;
+  ix.c3_dirty = true;
+  ABSB_API_END
+}
+
+int absb_ivf_get_centroids(absb_ivf_t h, float* centroids) {
+  ABSB_API_BEGIN
+  NEED(h); NEED(centroids);
+  IvfIndex& ix = h->ix;
+  ABSB_CHECK(ix.trained, ABSB_ERR_STATE, "index is not trained");
+  DeviceGuard g(ix.device);
+  ABSB_CUDA(cudaStreamSynchronize(ix.own_stream));
+  ABSB_CUDA(cudaMemcpy(centroids, ix.centroids.p, sizeof(float) * (size_t)ix.nlist * ix.d, cudaMemcpyDeviceToHost));
+  ABSB_API_END
+}
+
+int absb_ivf_set_centroids_dev(absb_ivf_t h, const float* centroids_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(h); NEED(centroids_dev);
+  DeviceGuard g(h->ix.device);
+  h->ix.set_centroids_dev(centroids_dev, (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_ivf_add_dev(absb_ivf_t h, int64_t n, const float* x_dev, const int64_t* ids_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || x_dev), ABSB_ERR_INVALID, "bad add arguments");
+  DeviceGuard g(h->ix.device);
+  h->ix.add_dev(n, x_dev, reinterpret_cast<const long long*>(ids_dev), (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_ivf_add_preassigned_dev(absb_ivf_t h, int64_t n, const float* x_dev, const int64_t* ids_dev,
+                                 const int64_t* list_ids_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || (x_dev && list_ids_dev)), ABSB_ERR_INVALID, "bad add arguments");
+  DeviceGuard g(h->ix.device);
+  const int64_t step = (int64_t)1 << 22;
+  for (int64_t r0 = 0; r0 < n; r0 += step) {
+    const int64_t nr = std::min(step, n - r0);
+    h->ix.add_core_dev(nr, x_dev + r0 * h->ix.d,
+                       ids_dev ? reinterpret_cast<const long long*>(ids_dev) + r0 : nullptr,
+                       reinterpret_cast<const long long*>(list_ids_dev) + r0, (cudaStream_t)stream);
+  }
+  ABSB_API_END
+}
+
+static void ivf_add_host(IvfIndex& ix, int64_t n, const float* x, const int64_t* ids, const int64_t* list_ids) {
+  ABSB_CHECK(n >= 0 && (n == 0 || x), ABSB_ERR_INVALID, "bad add arguments");
+  ABSB_CHECK(ix.trained, ABSB_ERR_STATE, "index is not trained");
+  DeviceGuard g(ix.device);
+  cudaStream_t st = ix.own_stream;
+  const int64_t step = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)ix.d * 4));
+  for (int64_t r0 = 0; r0 < n; r0 += step) {
+    const int64_t nr = std::min(step, n - r0);
+    const float* xd = stage_in(ix.ws_x, x + r0 * ix.d, (size_t)nr * ix.d, st);
+    const long long* idd = nullptr;
+    if (ids) idd = stage_in(ix.ws_ids, reinterpret_cast<const long long*>(ids) + r0, (size_t)nr, st);
+    if (list_ids) {
+      ix.ws_list_ids.reserve((size_t)nr);
+      ABSB_CUDA(cudaMemcpyAsync(ix.ws_list_ids.p, list_ids + r0, sizeof(long long) * nr, cudaMemcpyHostToDevice, st));
+      ix.add_core_dev(nr, xd, idd, ix.ws_list_ids.p, st);
+    } else {
+      ix.add_dev(nr, xd, idd, st);
+    }
+    ABSB_CUDA(cudaStreamSynchronize(st));
+  }
+}
+
+int absb_ivf_add(absb_ivf_t h, int64_t n, const float* x, const int64_t* ids) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ivf_add_host(h->ix, n, x, ids, nullptr);
+  ABSB_API_END
+}
+
+int absb_ivf_add_preassigned(absb_ivf_t h, int64_t n, const float* x, const int64_t* ids,
+                             const int64_t* list_ids) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n == 0 || list_ids, ABSB_ERR_INVALID, "null list_ids");
+  ivf_add_host(h->ix, n, x, ids, list_ids);
+  ABSB_API_END
+}
+
+int absb_ivf_compact(absb_ivf_t h) {
+  ABSB_API_BEGIN
+  NEED(h);
+  fail(ABSB_ERR_UNSUPPORTED, "compact is not implemented yet");
+  ABSB_API_END
+}
+
+int absb_ivf_coarse_dev(absb_ivf_t h, int64_t n, const float* q_dev, int nprobe, float* Dc_dev,
+                        int64_t* Ic_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || (q_dev && Dc_dev && Ic_dev)), ABSB_ERR_INVALID, "bad coarse arguments");
+  ABSB_CHECK(nprobe >= 1 && nprobe <= h->ix.nlist, ABSB_ERR_INVALID, "nprobe=%d outside [1,nlist]", nprobe);
+  DeviceGuard g(h->ix.device);
+  h->ix.coarse_dev(n, q_dev, nprobe, Dc_dev, reinterpret_cast<long long*>(Ic_dev), true, (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_ivf_coarse(absb_ivf_t h, int64_t n, const float* q, int nprobe, float* Dc, int64_t* Ic) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || (q && Dc && Ic)), ABSB_ERR_INVALID, "bad coarse arguments");
+  IvfIndex& ix = h->ix;
+  ABSB_CHECK(nprobe >= 1 && nprobe <= ix.nlist && nprobe <= ABSB_MAX_K, ABSB_ERR_INVALID,
+             "nprobe=%d outside [1,min(nlist,%d)]", nprobe, ABSB_MAX_K);
+  DeviceGuard g(ix.device);
+  cudaStream_t st = ix.own_stream;
+  const int64_t step = 4096;
+  ix.ws_D.reserve((size_t)step * nprobe);
+  ix.ws_I.reserve((size_t)step * nprobe);
+  for (int64_t r0 = 0; r0 < n; r0 += step) {
+    const int64_t nr = std::min(step, n - r0);
+    const float* qd = stage_in(ix.ws_x, q + r0 * ix.d, (size_t)nr * ix.d, st);
+    ix.coarse_dev(nr, qd, nprobe, ix.ws_D.p, ix.ws_I.p, true, st);
+    fetch_out(Dc + r0 * nprobe, ix.ws_D.p, (size_t)nr * nprobe, st);
+    fetch_out(reinterpret_cast<long long*>(Ic) + r0 * nprobe, ix.ws_I.p, (size_t)nr * nprobe, st);
+    ABSB_CUDA(cudaStreamSynchronize(st));
+  }
+  ABSB_API_END
+}
+
+int absb_ivf_assign(absb_ivf_t h, int64_t n, const float* x, int64_t* list_ids) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || (x && list_ids)), ABSB_ERR_INVALID, "bad assign arguments");
+  IvfIndex& ix = h->ix;
+  DeviceGuard g(ix.device);
+  cudaStream_t st = ix.own_stream;
+  const int64_t step = 16384;
+  ix.ws_I.reserve((size_t)step);
+  for (int64_t r0 = 0; r0 < n; r0 += step) {
+    const int64_t nr = std::min(step, n - r0);
+    const float* xd = stage_in(ix.ws_x, x + r0 * ix.d, (size_t)nr * ix.d, st);
+    ix.assign_dev(nr, xd, ix.ws_I.p, st);
+    fetch_out(reinterpret_cast<long long*>(list_ids) + r0, ix.ws_I.p, (size_t)nr, st);
+    ABSB_CUDA(cudaStreamSynchronize(st));
+  }
+  ABSB_API_END
+}
+
+int absb_ivf_search_dev(absb_ivf_t h, int64_t n, const float* q_dev, int k, int nprobe, float* D_dev,
+                        int64_t* I_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || (q_dev && D_dev && I_dev)), ABSB_ERR_INVALID, "bad search arguments");
+  DeviceGuard g(h->ix.device);
+  h->ix.reset_stats();
+  h->ix.search_dev(n, q_dev, k, nprobe, D_dev, reinterpret_cast<long long*>(I_dev), (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_ivf_search_preassigned_dev(absb_ivf_t h, int64_t n, const float* q_dev, int k, int nprobe,
+                                    const int64_t* coarse_ids_dev, float* D_dev, int64_t* I_dev,
+                                    void* stream) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n >= 0 && (n == 0 || (q_dev && D_dev && I_dev && coarse_ids_dev)), ABSB_ERR_INVALID, "bad search arguments");
+  DeviceGuard g(h->ix.device);
+  IvfIndex& ix = h->ix;
+  ix.reset_stats();
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t q0 = 0; q0 < n; q0 += kMaxPlanQueries) {
+    const int64_t nb = std::min<int64_t>(kMaxPlanQueries, n - q0);
+    ix.search_preassigned_dev(nb, q_dev + q0 * ix.d, k, nprobe,
+                              reinterpret_cast<const long long*>(coarse_ids_dev) + q0 * nprobe,
+                              D_dev + q0 * k, reinterpret_cast<long long*>(I_dev) + q0 * k, st);
+  }
+  ABSB_API_END
+}
+
+static void ivf_search_host(IvfIndex& ix, int64_t n, const float* q, int k, int nprobe,
+                            const int64_t* coarse, float* D, int64_t* I) {
+  ABSB_CHECK(n >= 0 && (n == 0 || (q && D && I)), ABSB_ERR_INVALID, "bad search arguments");
+  ABSB_CHECK(k >= 1 && k <= ABSB_MAX_K, ABSB_ERR_INVALID, "k=%d outside [1,%d]", k, ABSB_MAX_K);
+  ABSB_CHECK(nprobe >= 1, ABSB_ERR_INVALID, "nprobe=%d", nprobe);
+  ABSB_CHECK(ix.trained, ABSB_ERR_STATE, "index is not trained");
+  DeviceGuard g(ix.device);
+  cudaStream_t st = ix.own_stream;
+  ix.reset_stats();
+  const int64_t step = 4096;
+  ix.ws_D.reserve((size_t)std::min(step, std::max<int64_t>(n, 1)) * k);
+  ix.ws_I.reserve((size_t)std::min(step, std::max<int64_t>(n, 1)) * k);
+  for (int64_t r0 = 0; r0 < n; r0 += step) {
+    const int64_t nr = std::min(step, n - r0);
+    const float* qd = stage_in(ix.ws_x, q + r0 * ix.d, (size_t)nr * ix.d, st);
+    if (coarse) {
+      const long long* cd = stage_in(ix.ws_ids, reinterpret_cast<const long long*>(coarse) + r0 * nprobe,
+                                     (size_t)nr * nprobe, st);
+      for (int64_t q0 = 0; q0 < nr; q0 += kMaxPlanQueries) {
+        const int64_t nb = std::min<int64_t>(kMaxPlanQueries, nr - q0);
+        ix.search_preassigned_dev(nb, qd + q0 * ix.d, k, nprobe, cd + q0 * nprobe, ix.ws_D.p + q0 * k,
+                                  ix.ws_I.p + q0 * k, st);
+      }
+    } else {
+      ix.search_dev(nr, qd, k, nprobe, ix.ws_D.p, ix.ws_I.p, st);
+    }
+    fetch_out(D + r0 * k, ix.ws_D.p, (size_t)nr * k, st);
+    fetch_out(reinterpret_cast<long long*>(I) + r0 * k, ix.ws_I.p, (size_t)nr * k, st);
+    ABSB_CUDA(cudaStreamSynchronize(st));
+  }
+}
+
+int absb_ivf_search(absb_ivf_t h, int64_t n, const float* q, int k, int nprobe, float* D, int64_t* I) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ivf_search_host(h->ix, n, q, k, nprobe, nullptr, D, I);
+  ABSB_API_END
+}
+
+int absb_ivf_search_preassigned(absb_ivf_t h, int64_t n, const float* q, int k, int nprobe,
+                                const int64_t* coarse_ids, float* D, int64_t* I) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(n == 0 || coarse_ids, ABSB_ERR_INVALID, "null coarse_ids");
+  ivf_search_host(h->ix, n, q, k, nprobe, coarse_ids, D, I);
+  ABSB_API_END
+}
+
+int absb_ivf_list_sizes(absb_ivf_t h, int64_t* sizes) {
+  ABSB_API_BEGIN
+  NEED(h); NEED(sizes);
+  std::copy(h->ix.h_list_size.begin(), h->ix.h_list_size.end(), sizes);
+  ABSB_API_END
+}
+
+int absb_ivf_get_list(absb_ivf_t h, int64_t list_no, float* codes, int64_t* ids) {
+  ABSB_API_BEGIN
+  NEED(h);
+  IvfIndex& ix = h->ix;
+  ABSB_CHECK(list_no >= 0 && list_no < ix.nlist, ABSB_ERR_INVALID, "list %lld outside [0,%d)", (long long)list_no, ix.nlist);
+  DeviceGuard g(ix.device);
+  ix.get_list(list_no, codes, reinterpret_cast<long long*>(ids));
+  ABSB_API_END
+}
+
+int absb_ivf_set_shard(absb_ivf_t h, int rank, int world) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(world >= 1 && rank >= 0 && rank < world, ABSB_ERR_INVALID, "shard rank=%d world=%d", rank, world);
+  ABSB_CHECK(h->ix.rows_seen == 0, ABSB_ERR_STATE, "set_shard must precede the first add");
+  h->ix.shard_rank = rank;
+  h->ix.shard_world = world;
+  ABSB_API_END
+}
+
+int absb_merge_shards_dev(int device, int world, int64_t n, int k, const float* D_all_dev,
+                          const int64_t* I_all_dev, int64_t rank_stride_bytes, float* D_dev,
+                          int64_t* I_dev, void* stream) {
+  ABSB_API_BEGIN
+  ABSB_CHECK(world >= 1 && n >= 0 && k >= 1 && k <= ABSB_MAX_K, ABSB_ERR_INVALID, "bad merge arguments");
+  ABSB_CHECK(n == 0 || (D_all_dev && I_all_dev && D_dev && I_dev), ABSB_ERR_INVALID, "null argument");
+  DeviceGuard g(device);
+  const int64_t ds = rank_stride_bytes ? rank_stride_bytes : n * k * (int64_t)sizeof(float);
+  const int64_t is = rank_stride_bytes ? rank_stride_bytes : n * k * (int64_t)sizeof(long long);
+  merge_shards(world, n, k, D_all_dev, reinterpret_cast<const long long*>(I_all_dev), ds, is, D_dev,
+               reinterpret_cast<long long*>(I_dev), (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int scan_ctas_per_sm) {
+  ABSB_API_BEGIN
+  NEED(h);
+  if (scan_chunk > 0) h->ix.scan_chunk = scan_chunk;
+  if (coarse_impl >= 0) {
+    ABSB_CHECK(coarse_impl <= 1, ABSB_ERR_INVALID, "coarse_impl=%d", coarse_impl);
+    h->ix.coarse_impl = coarse_impl;
+  }
+  if (scan_ctas_per_sm >= 0) h->ix.scan_ctas_per_sm = scan_ctas_per_sm;
+  ABSB_API_END
+}
+
+int absb_ivf_last_stats(absb_ivf_t h, int64_t* vectors_scanned, int64_t* bytes_scanned,
+                        int64_t* work_items, int64_t* launches) {
+  ABSB_API_BEGIN
+  NEED(h);
+  IvfIndex& ix = h->ix;
+  DeviceGuard g(ix.device);
+  ABSB_CUDA(cudaDeviceSynchronize());
+  ix.fold_stats();
+  if (vectors_scanned) *vectors_scanned = ix.stats.vectors;
+  if (bytes_scanned) *bytes_scanned = ix.stats.bytes;
+  if (work_items) *work_items = ix.stats.items;
+  if (launches) *launches = ix.stats.launches;
+  ABSB_API_END
+}
+
+int absb_ivf_time_scan(absb_ivf_t h, int iters, void* stream, float* ms_mean) {
+  ABSB_API_BEGIN
+  NEED(h); NEED(ms_mean);
+  IvfIndex& ix = h->ix;
+  ABSB_CHECK(ix.have_last_scan, ABSB_ERR_STATE, "no search has run on this handle yet");
+  ABSB_CHECK(iters >= 1, ABSB_ERR_INVALID, "iters=%d", iters);
+  DeviceGuard g(ix.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  ABSB_CUDA(cudaEventCreate(&e0));
+  ABSB_CUDA(cudaEventCreate(&e1));
+  float total = 0.f;
+  for (int i = 0; i < iters; ++i) {
+    ABSB_CUDA(cudaMemsetAsync(ix.last_scan.queue_counter, 0, sizeof(int), st));
+    ABSB_CUDA(cudaEventRecord(e0, st));
+    launch_scan(ix.last_scan, st);
+    ABSB_CUDA(cudaEventRecord(e1, st));
+    ABSB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    ABSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    total += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_mean = total / iters;
+  ABSB_API_END
+}
+
+}  // extern "C"

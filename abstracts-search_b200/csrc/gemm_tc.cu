@@ -1,0 +1,425 @@
+// gemm_tc.cu — bf16 x bf16 -> fp32 GEMM on the 5th-generation tensor cores (tcgen05), the one
+// dense contraction on the abstracts-search path:
+//   * every Linear of the stella/Qwen2 encoder behind SentenceTransformer.encode()
+//     (/root/reference/Makefile:65, README.md:28,60 — SURVEY §2c E3/E6/E7/E8), with the bias,
+//     SwiGLU and residual-add epilogues fused;
+//   * the IVF coarse quantiser  <q, centroid>  (faiss quantizer.search under Index.search/add,
+//     /root/reference/Makefile:25,32) as a split-bf16 GEMM that keeps fp32-faithful scores.
+//
+// C[M,N] = A[M,K] * B[N,K]^T, both operands K-major (row-major activations, nn.Linear weights).
+//
+// Kernel anatomy (persistent, one CTA per SM, 256 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor 128x64 (A) and BNx64 (B) bf16 boxes, SWIZZLE_128B,
+//            into a 4-stage shared-memory ring, completion on `full` mbarriers;
+//   warp 1   MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//            (M=128, N=BN, K=16) x4 per stage into a TMEM accumulator, tcgen05.commit releases the
+//            stage (`empty`) and finally signals `tmem_full`;
+//   warp 2   allocates / frees the 2 x BN TMEM columns (double-buffered accumulator);
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused epilogue, direct global
+//            stores (each thread owns one output row: 64-128 contiguous bytes per store burst),
+//            then release the accumulator (`tmem_empty`) so the next tile's MMAs overlap.
+#include <mutex>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "tc.cuh"
+
+namespace absb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // bf16 elements = 128 bytes = one swizzle span
+constexpr int kStages = 4;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOff = kStages * kStageBytes;
+  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr
+  static constexpr int kTotal = kBarOff + (2 * kStages + 4) * 8 + 16;
+  static constexpr int kDyn = kTotal + 1024;  // slack for manual 1024-byte alignment
+};
+
+struct KernelParams {
+  int M, N, K;
+  int tiles_m, tiles_n;
+  int num_kb;  // k-blocks per tile over all segments
+  int seg_kb;  // k-blocks per segment
+  int a_off[kMaxGemmSegs];
+  int b_off[kMaxGemmSegs];
+  void* out;
+  int64_t ldc;
+  const float* bias;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+
+template <int BN, int EPI>
+__global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   const KernelParams p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      tc::mbar_init(full_bar + i, 1);
+      tc::mbar_init(empty_bar + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(tmem_full + i, 1);
+      tc::mbar_init(tmem_empty + i, 4);  // one arrive per epilogue warp
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_slot, 2 * BN);
+    tc::tmem_relinquish();
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // consecutive tiles share the B (weight) tile row-block: m fastest
+        const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int seg = kb / p.seg_kb, within = kb - seg * p.seg_kb;
+          tc::mbar_wait(empty_bar + stage, phase ^ 1);
+          tc::mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          tc::tma_load_2d(sa, &tmA, full_bar + stage, p.a_off[seg] + within * BK, tm * BM);
+          tc::tma_load_2d(sa + L::kABytes, &tmB, full_bar + stage, p.b_off[seg] + within * BK, tn * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        tc::mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        tc::tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          tc::mbar_wait(full_bar + stage, phase);
+          tc::tcgen05_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + stage * L::kStageBytes);
+          const uint64_t da = tc::make_kmajor_sw128_desc(sa);
+          const uint64_t db = tc::make_kmajor_sw128_desc(sa + L::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
+            tc::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc::umma_commit(empty_bar + stage);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc::umma_commit(tmem_full + acc);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+      const int row = tm * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      tc::mbar_wait(tmem_full + acc, acc_phase);
+      tc::tcgen05_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+
+      if constexpr (EPI == EPI_SWIGLU_BF16) {
+        // tile columns [0, BN/2) are gate rows, [BN/2, BN) the matching up rows
+        constexpr int H = BN / 2;
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+        const int ocol0 = tn * H;
+        const int ncols = p.N / 2;
+#pragma unroll 1
+        for (int c = 0; c < H; c += 32) {
+          uint32_t g[32], u[32];
+          tc::tmem_ld_32x32(t_base + c, g);
+          tc::tmem_ld_32x32(t_base + H + c, u);
+          tc::tmem_ld_wait();
+          if (row_ok && ocol0 + c < ncols) {
+            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * p.ldc + ocol0 + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float g0 = __uint_as_float(g[j * 8 + e * 2]), g1 = __uint_as_float(g[j * 8 + e * 2 + 1]);
+                const float u0 = __uint_as_float(u[j * 8 + e * 2]), u1 = __uint_as_float(u[j * 8 + e * 2 + 1]);
+                w[e] = pack_bf16x2(silu(g0) * u0, silu(g1) * u1);
+              }
+              dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      } else {
+        const int col0 = tn * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(t_base + c, v);
+          tc::tmem_ld_wait();
+          const int col = col0 + c;
+          if (row_ok && col < p.N) {
+            if constexpr (EPI == EPI_BF16_BIAS) {
+              __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+              uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * p.ldc + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+                if (p.bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col + j * 8));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + j * 8 + 4));
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                dst[j] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                    pack_bf16x2(f[6], f[7]));
+              }
+            } else {
+              float* out = reinterpret_cast<float*>(p.out);
+              float4* dst = reinterpret_cast<float4*>(out + (size_t)row * p.ldc + col);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 f = make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]),
+                                       __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
+                if constexpr (EPI == EPI_F32_ADD) {
+                  const float4 o = dst[j];
+                  f.x += o.x; f.y += o.y; f.z += o.z; f.w += o.w;
+                } else if (p.bias) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j * 4));
+                  f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
+                }
+                dst[j] = f;
+              }
+            }
+          }
+        }
+      }
+      // accumulator drained: hand it back to the MMA warp
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tcgen05_fence_after();
+    tc::tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------ tensor maps -------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  ABSB_CHECK(fn != nullptr, ABSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  return fn;
+}
+
+// bf16 matrix [rows, cols] with row stride ld (elements); box = box_rows x 64 elements, 128B swizzle
+CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  ABSB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, ABSB_ERR_INVALID,
+             "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (ld=%lld)", (long long)ld);
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ABSB_CHECK(r == CUDA_SUCCESS, ABSB_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return m;
+}
+
+template <int BN, int EPI>
+void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p, int sms, cudaStream_t st) {
+  auto kern = gemm_bf16_tc_kernel<BN, EPI>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    ABSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::kDyn));
+    configured = true;
+  }
+  const int grid = std::min(p.tiles_m * p.tiles_n, sms);
+  kern<<<grid, kThreads, SmemLayout<BN>::kDyn, st>>>(tmA, tmB, p);
+  ABSB_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
+                  int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st) {
+  if (M == 0 || N == 0) return;
+  ABSB_CHECK(K > 0 && K % 8 == 0, ABSB_ERR_INVALID, "tcgen05 GEMM needs K %% 8 == 0 (K=%d)", K);
+  ABSB_CHECK(N % 32 == 0, ABSB_ERR_INVALID, "tcgen05 GEMM needs N %% 32 == 0 (N=%d)", N);
+  ABSB_CHECK(epi != EPI_SWIGLU_BF16 || N % 256 == 0, ABSB_ERR_INVALID, "SwiGLU epilogue needs N %% 256 == 0 (N=%d)", N);
+  constexpr int BN = 256;
+  KernelParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.tiles_m = (int)ceil_div(M, BM);
+  p.tiles_n = (int)ceil_div(N, BN);
+  int64_t a_cols = K, b_cols = K;
+  if (segs && segs->nseg > 0) {
+    ABSB_CHECK(segs->nseg <= kMaxGemmSegs, ABSB_ERR_INVALID, "too many GEMM segments");
+    p.seg_kb = (int)ceil_div(K, BK);
+    p.num_kb = p.seg_kb * segs->nseg;
+    for (int i = 0; i < segs->nseg; ++i) {
+      p.a_off[i] = segs->a_off[i];
+      p.b_off[i] = segs->b_off[i];
+      ABSB_CHECK(segs->a_off[i] % 8 == 0 && segs->b_off[i] % 8 == 0, ABSB_ERR_INVALID, "segment offsets must be multiples of 8");
+    }
+    a_cols = segs->a_cols;
+    b_cols = segs->b_cols;
+    // a segment may not read into its neighbour: K must fill whole k-blocks
+    ABSB_CHECK(K % BK == 0, ABSB_ERR_INVALID, "segmented GEMM needs K %% 64 == 0");
+  } else {
+    p.seg_kb = (int)ceil_div(K, BK);
+    p.num_kb = p.seg_kb;
+    p.a_off[0] = p.b_off[0] = 0;
+  }
+  p.out = out;
+  p.ldc = ldc;
+  p.bias = bias;
+  const CUtensorMap tmA = make_tmap(A, M, a_cols, lda, BM);
+  const CUtensorMap tmB = make_tmap(B, N, b_cols, ldb, BN);
+  switch (epi) {
+    case EPI_BF16_BIAS: launch<BN, EPI_BF16_BIAS>(tmA, tmB, p, sms, st); break;
+    case EPI_F32_BIAS: launch<BN, EPI_F32_BIAS>(tmA, tmB, p, sms, st); break;
+    case EPI_F32_ADD: launch<BN, EPI_F32_ADD>(tmA, tmB, p, sms, st); break;
+    case EPI_SWIGLU_BF16: launch<BN, EPI_SWIGLU_BF16>(tmA, tmB, p, sms, st); break;
+    default: fail(ABSB_ERR_INVALID, "unknown epilogue %d", epi);
+  }
+}
+
+// ------------------------------------------------------------------ split-bf16 fp32 GEMM ----
+// x = hi + mid + lo with three bf16 terms (8 + 8 + 8 significant bits): the six products below
+// carry every term down to 2^-24 relative, accumulated in fp32 inside TMEM, smallest first.
+namespace {
+__global__ void split3_kernel(int64_t rows, int K, const float* __restrict__ x, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = rows * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / K;
+    const int c = (int)(i - r * K);
+    const float v = x[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+    __nv_bfloat16* o = out + r * 3 * K;
+    o[c] = h;
+    o[K + c] = m;
+    o[2 * K + c] = l;
+  }
+}
+}  // namespace
+
+void split3_bf16(int64_t rows, int K, const float* x, void* out, cudaStream_t st) {
+  if (rows == 0) return;
+  const int64_t total = rows * K;
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 32);
+  split3_kernel<<<blocks, 256, 0, st>>>(rows, K, x, reinterpret_cast<__nv_bfloat16*>(out));
+  ABSB_CUDA(cudaGetLastError());
+}
+
+void gemm_split3_f32(int M, int N, int K, const void* A3, const void* B3, float* S, int64_t lds, int sms,
+                     cudaStream_t st) {
+  GemmSegs segs{};
+  // (a part, b part): 0 = hi, 1 = mid, 2 = lo; smallest contributions first
+  const int pa[6] = {1, 0, 2, 0, 1, 0};
+  const int pb[6] = {1, 2, 0, 1, 0, 0};
+  segs.nseg = 6;
+  for (int i = 0; i < 6; ++i) {
+    segs.a_off[i] = pa[i] * K;
+    segs.b_off[i] = pb[i] * K;
+  }
+  segs.a_cols = segs.b_cols = 3 * (int64_t)K;
+  gemm_bf16_tc(EPI_F32_BIAS, M, N, K, A3, 3 * (int64_t)K, B3, 3 * (int64_t)K, S, lds, nullptr, &segs, sms, st);
+}
+
+}  // namespace absb
+
+extern "C" int absb_gemm_bf16_dev(int device, int M, int N, int K, const void* A_dev, const void* B_dev, float* C_dev,
+                                  void* stream) {
+  ABSB_API_BEGIN
+  using namespace absb;
+  ABSB_CHECK(M >= 0 && N >= 0 && K > 0 && A_dev && B_dev && C_dev, ABSB_ERR_INVALID, "bad GEMM arguments");
+  DeviceGuard g(device);
+  const DeviceProps pr = device_props(device);
+  ABSB_CHECK(pr.cc_major == 10, ABSB_ERR_UNSUPPORTED, "tcgen05 GEMM needs an sm_100 device");
+  gemm_bf16_tc(EPI_F32_BIAS, M, N, K, A_dev, K, B_dev, K, C_dev, N, nullptr, nullptr, pr.sm_count, (cudaStream_t)stream);
+  ABSB_API_END
+}

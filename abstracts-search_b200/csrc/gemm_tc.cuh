@@ -1,0 +1,38 @@
+// gemm_tc.cuh — host interface of the tcgen05 GEMM (gemm_tc.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace absb {
+
+enum GemmEpilogue {
+  EPI_BF16_BIAS = 0,    // out bf16 [M,N]   = acc (+ bias[N])
+  EPI_F32_BIAS = 1,     // out f32  [M,N]   = acc (+ bias[N])
+  EPI_F32_ADD = 2,      // out f32  [M,N]  += acc                      (residual stream)
+  EPI_SWIGLU_BF16 = 3,  // out bf16 [M,N/2] = silu(gate) * up, weight rows interleaved per 256-row
+                        //                    tile: [128 gate rows | 128 up rows]
+};
+
+constexpr int kMaxGemmSegs = 8;
+
+// K-segment table: the reduction runs over nseg segments of length K; segment s reads A columns
+// [a_off[s], a_off[s]+K) and B columns [b_off[s], b_off[s]+K).  Used by the split-bf16 GEMM.
+struct GemmSegs {
+  int nseg = 0;
+  int a_off[kMaxGemmSegs] = {0};
+  int b_off[kMaxGemmSegs] = {0};
+  int64_t a_cols = 0, b_cols = 0;  // full row length of A and B
+};
+
+// C[M,N] = A[M,K] * B[N,K]^T; A, B bf16 with row pitches lda, ldb (elements).
+void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
+                  int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st);
+
+// fp32 [rows,K] -> bf16 [rows, 3K] = [hi | mid | lo]
+void split3_bf16(int64_t rows, int K, const float* x, void* out, cudaStream_t st);
+// S[M,N] (fp32, pitch lds) = A * B^T from split operands A3 [M,3K], B3 [N,3K]
+void gemm_split3_f32(int M, int N, int K, const void* A3, const void* B3, float* S, int64_t lds, int sms,
+                     cudaStream_t st);
+
+}  // namespace absb

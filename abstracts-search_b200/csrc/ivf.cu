@@ -1,0 +1,739 @@
+// ivf.cu — IndexIVFFlat / IndexFlatIP host logic on top of the kernels.
+//
+// Mirrors what faiss does behind Index.train / Index.add / Index.search for
+// index_factory(d, "IVF<nlist>,Flat", METRIC_INNER_PRODUCT) — the calls made by
+// `sidecar-search index train|fill|tune` (/root/reference/Makefile:38-39, 24-25, 31-32) and app.py
+// (/root/reference/README.md:16,28).  See SURVEY.md §8(a) a4–a8 for the semantics followed here.
+#include "ivf.cuh"
+
+#include <cub/cub.cuh>
+
+#include "gemm_tc.cuh"
+#include <numeric>
+#include <random>
+
+namespace absb {
+
+// =========================================================================================
+// small kernels
+// =========================================================================================
+namespace {
+
+__global__ void make_keys_kernel(int64_t n, const long long* __restrict__ list_ids, int nlist,
+                                 int rank, int world, unsigned* __restrict__ keys,
+                                 int* __restrict__ vals, unsigned* __restrict__ hist /* [nlist+1] */) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const long long l = list_ids[i];
+    unsigned key = (unsigned)nlist;  // dropped rows sort last
+    if (l >= 0 && l < nlist && (world == 1 || (int)(l % world) == rank)) key = (unsigned)l;
+    keys[i] = key;
+    vals[i] = (int)i;
+    atomicAdd(&hist[key], 1u);
+  }
+}
+
+// per-list bookkeeping for one add(): new sizes, number of fresh pages
+__global__ void list_growth_kernel(int nlist, int P, const long long* __restrict__ old_size,
+                                   const unsigned* __restrict__ hist, long long* __restrict__ new_size,
+                                   int* __restrict__ fresh_pages, long long* __restrict__ total_pages_per_list) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nlist) return;
+  const long long os = old_size[l], ns = os + hist[l];
+  new_size[l] = ns;
+  const long long op = (os + P - 1) / P, np = (ns + P - 1) / P;
+  fresh_pages[l] = (int)(np - op);
+  total_pages_per_list[l] = np;
+}
+
+__global__ void build_page_table_kernel(int nlist, int P, const long long* __restrict__ old_size,
+                                        const long long* __restrict__ old_off,
+                                        const int* __restrict__ old_pages,
+                                        const long long* __restrict__ new_off,
+                                        const int* __restrict__ fresh_off /* exclusive scan */,
+                                        const int* __restrict__ fresh_pages, long long first_fresh_page,
+                                        int* __restrict__ new_pages) {
+  const int l = blockIdx.x;
+  const long long op = (old_size[l] + P - 1) / P;
+  const long long nb = new_off[l];
+  for (long long j = threadIdx.x; j < op; j += blockDim.x) new_pages[nb + j] = old_pages[old_off[l] + j];
+  const int f = fresh_pages[l];
+  for (int j = threadIdx.x; j < f; j += blockDim.x)
+    new_pages[nb + op + j] = (int)(first_fresh_page + fresh_off[l] + j);
+}
+
+// One warp per kept row (in list-sorted, insertion-stable order): copy the vector + id to its slot.
+__global__ void scatter_rows_kernel(int64_t n_kept, int d4, int P, int slab_shift,
+                                    const unsigned* __restrict__ keys_sorted,
+                                    const int* __restrict__ perm, const unsigned* __restrict__ call_off,
+                                    const long long* __restrict__ old_size,
+                                    const long long* __restrict__ pt_off, const int* __restrict__ pt_pages,
+                                    float* const* __restrict__ code_slabs,
+                                    long long* const* __restrict__ id_slabs,
+                                    const float* __restrict__ x, const long long* __restrict__ ids,
+                                    long long id0) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = wid; p < n_kept; p += nw) {
+    const unsigned l = keys_sorted[p];
+    const int row = perm[p];
+    const long long pos = old_size[l] + (long long)(p - call_off[l]);
+    const long long page = pt_pages[pt_off[l] + pos / P];
+    const int slot = (int)(pos % P);
+    const int slab = (int)(page >> slab_shift);
+    const long long in_slab = page & ((1ll << slab_shift) - 1);
+    float4* dst = reinterpret_cast<float4*>(code_slabs[slab]) + ((size_t)in_slab * P + slot) * d4;
+    const float4* src = reinterpret_cast<const float4*>(x) + (size_t)row * d4;
+    for (int j = lane; j < d4; j += 32) dst[j] = __ldcs(src + j);
+    if (lane == 0) id_slabs[slab][(size_t)in_slab * P + slot] = ids ? ids[row] : id0 + row;
+  }
+}
+
+__global__ void gather_rows_kernel(int64_t n, int d4, const int* __restrict__ rows,
+                                   const float* __restrict__ x, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = wid; p < n; p += nw) {
+    const float4* src = reinterpret_cast<const float4*>(x) + (size_t)rows[p] * d4;
+    float4* dst = reinterpret_cast<float4*>(out) + (size_t)p * d4;
+    for (int j = lane; j < d4; j += 32) dst[j] = src[j];
+  }
+}
+
+// Clustering::compute_centroids: members of centroid c are rows perm[off[c] .. off[c+1]) in
+// ascending row order; fp32 running sum in that order, then multiply by 1/count.
+__global__ void centroid_mean_kernel(int d, const unsigned* __restrict__ off,
+                                     const int* __restrict__ perm, const float* __restrict__ x,
+                                     float* __restrict__ centroids, float* __restrict__ hassign) {
+  const int c = blockIdx.x;
+  const unsigned b = off[c], e = off[c + 1];
+  if (threadIdx.x == 0) hassign[c] = (float)(e - b);
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    float acc = 0.f;
+    for (unsigned i = b; i < e; ++i) acc += x[(size_t)perm[i] * d + j];
+    if (e > b) acc *= 1.f / (float)(e - b);
+    centroids[(size_t)c * d + j] = acc;
+  }
+}
+
+__global__ void copy_list_kernel(ListTable lt, long long l, float* __restrict__ codes,
+                                 long long* __restrict__ ids) {
+  const long long size = lt.list_size[l];
+  const int P = lt.page_vecs;
+  const int d = lt.d;
+  for (long long v = blockIdx.x; v < size; v += gridDim.x) {
+    const long long page = lt.pt_pages[lt.pt_off[l] + v / P];
+    const int slot = (int)(v % P);
+    const int slab = (int)(page >> lt.slab_shift);
+    const long long in_slab = page & ((1ll << lt.slab_shift) - 1);
+    const float* src = lt.code_slabs[slab] + ((size_t)in_slab * P + slot) * d;
+    if (codes)
+      for (int j = threadIdx.x; j < d; j += blockDim.x) codes[(size_t)v * d + j] = src[j];
+    if (ids && threadIdx.x == 0) ids[v] = lt.id_slabs[slab][(size_t)in_slab * P + slot];
+  }
+}
+
+int grid_for(int64_t work, int threads, int sms) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, threads), (int64_t)sms * 16));
+}
+
+}  // namespace
+
+// =========================================================================================
+// PagePool
+// =========================================================================================
+void PagePool::configure(int d_, int page_vecs_) {
+  d = d_;
+  page_vecs = page_vecs_;
+  // slabs of ~256 MB of codes
+  const size_t page_bytes = (size_t)page_vecs * d * sizeof(float);
+  slab_shift = 0;
+  while (((size_t)1 << (slab_shift + 1)) * page_bytes <= ((size_t)256 << 20)) ++slab_shift;
+}
+
+void PagePool::ensure_pages(int64_t total_pages, cudaStream_t st) {
+  const int64_t per_slab = (int64_t)1 << slab_shift;
+  const size_t need = (size_t)ceil_div(total_pages, per_slab);
+  if (need <= code_slabs.size()) return;
+  while (code_slabs.size() < need) {
+    float* c = nullptr;
+    long long* i = nullptr;
+    ABSB_CUDA(cudaMalloc(&c, (size_t)per_slab * page_vecs * d * sizeof(float)));
+    cudaError_t e = cudaMalloc(&i, (size_t)per_slab * page_vecs * sizeof(long long));
+    if (e != cudaSuccess) {
+      cudaFree(c);
+      ABSB_CUDA(e);
+    }
+    code_slabs.push_back(c);
+    id_slabs.push_back(i);
+  }
+  if (code_slabs.size() > table_cap) {
+    // the old tables may still be referenced by in-flight kernels on st: sync before freeing
+    ABSB_CUDA(cudaStreamSynchronize(st));
+    table_cap = std::max<size_t>(64, code_slabs.size() * 2);
+    d_code_slabs.alloc_exact(table_cap);
+    d_id_slabs.alloc_exact(table_cap);
+  }
+  ABSB_CUDA(cudaMemcpyAsync(d_code_slabs.p, code_slabs.data(), code_slabs.size() * sizeof(float*),
+                            cudaMemcpyHostToDevice, st));
+  ABSB_CUDA(cudaMemcpyAsync(d_id_slabs.p, id_slabs.data(), id_slabs.size() * sizeof(long long*),
+                            cudaMemcpyHostToDevice, st));
+  ABSB_CUDA(cudaStreamSynchronize(st));  // host vectors may reallocate later
+}
+
+void PagePool::release() {
+  for (auto p : code_slabs) cudaFree(p);
+  for (auto p : id_slabs) cudaFree(p);
+  code_slabs.clear();
+  id_slabs.clear();
+  pages_used = 0;
+}
+
+// =========================================================================================
+// scores GEMM dispatch
+// =========================================================================================
+// impl 0: exact-fp32 FFMA GEMM.  impl 1: split-bf16 tcgen05 GEMM (hi/mid/lo terms, fp32 accumulate in
+// TMEM) — fp32-faithful scores at tensor-core speed; needs d % 64 == 0 and nlist % 32 == 0, other
+// shapes take the FFMA kernel.
+void IvfIndex::coarse_scores(int M, const float* q, float* S, cudaStream_t st) {
+  if (coarse_impl == 1 && d % 64 == 0 && nlist % 32 == 0) {
+    if (c3_dirty) {
+      centroids3.reserve((size_t)nlist * 3 * d);
+      split3_bf16(nlist, d, centroids.p, centroids3.p, st);
+      c3_dirty = false;
+    }
+    ws_q3.reserve((size_t)M * 3 * d);
+    split3_bf16(M, d, q, ws_q3.p, st);
+    gemm_split3_f32(M, nlist, d, ws_q3.p, centroids3.p, S, nlist, props.sm_count, st);
+    stats.launches += 2;
+  } else {
+    gemm_nt_f32(M, nlist, d, q, d, centroids.p, d, S, nlist, st);
+    stats.launches += 1;
+  }
+}
+
+// =========================================================================================
+// IvfIndex
+// =========================================================================================
+IvfIndex::IvfIndex(int d_, int nlist_, int device_) : d(d_), nlist(nlist_), device(device_) {
+  ABSB_CHECK(d > 0 && d % 4 == 0, ABSB_ERR_UNSUPPORTED, "d must be a positive multiple of 4 (d=%d)", d);
+  ABSB_CHECK(nlist > 0 && nlist < (1 << 30), ABSB_ERR_INVALID, "nlist=%d", nlist);
+  props = device_props(device);
+  DeviceGuard g(device);
+  ABSB_CUDA(cudaStreamCreate(&own_stream));
+  centroids.alloc_exact((size_t)nlist * d);
+  list_size.alloc_exact(nlist);
+  pt_off.alloc_exact(nlist + 1);
+  ws_counters.alloc_exact(2);
+  ws_stats.alloc_exact(2);
+  ABSB_CUDA(cudaMemsetAsync(list_size.p, 0, sizeof(long long) * nlist, own_stream));
+  ABSB_CUDA(cudaMemsetAsync(pt_off.p, 0, sizeof(long long) * (nlist + 1), own_stream));
+  ABSB_CUDA(cudaStreamSynchronize(own_stream));
+  h_list_size.assign(nlist, 0);
+  // ~64 KB pages
+  int P = (int)std::max<size_t>(1, (64 * 1024) / ((size_t)d * sizeof(float)));
+  int p2 = 1;
+  while (p2 * 2 <= P) p2 *= 2;
+  pool.configure(d, p2);
+}
+
+IvfIndex::~IvfIndex() {
+  cudaSetDevice(device);
+  if (own_stream) {
+    cudaStreamSynchronize(own_stream);
+    cudaStreamDestroy(own_stream);
+  }
+}
+
+ListTable IvfIndex::table() const {
+  ListTable lt;
+  lt.nlist = nlist;
+  lt.d = d;
+  lt.page_vecs = pool.page_vecs;
+  lt.slab_shift = pool.slab_shift;
+  lt.list_size = list_size.p;
+  lt.pt_off = pt_off.p;
+  lt.pt_pages = pt_pages.p;
+  lt.code_slabs = pool.d_code_slabs.p;
+  lt.id_slabs = pool.d_id_slabs.p;
+  return lt;
+}
+
+void IvfIndex::reset() {
+  DeviceGuard g(device);
+  ABSB_CUDA(cudaStreamSynchronize(own_stream));
+  pool.release();
+  pt_pages.release();
+  pt_total_pages = 0;
+  ABSB_CUDA(cudaMemset(list_size.p, 0, sizeof(long long) * nlist));
+  ABSB_CUDA(cudaMemset(pt_off.p, 0, sizeof(long long) * (nlist + 1)));
+  h_list_size.assign(nlist, 0);
+  h_pages_prefix_desc.clear();
+  ntotal = 0;
+  rows_seen = 0;
+  have_last_scan = false;
+}
+
+void IvfIndex::set_centroids_dev(const float* c, cudaStream_t st) {
+  ABSB_CUDA(cudaMemcpyAsync(centroids.p, c, sizeof(float) * (size_t)nlist * d, cudaMemcpyDeviceToDevice, st));
+  trained = true;
+  c3_dirty = true;
+}
+
+// ---------------------------------------------------------------- coarse / assign ---------
+void IvfIndex::coarse_dev(int64_t nq, const float* q, int nprobe, float* Dc, long long* Ic,
+                          bool finalize, cudaStream_t st) {
+  ABSB_CHECK(trained, ABSB_ERR_STATE, "index is not trained");
+  ABSB_CHECK(nprobe >= 1 && nprobe <= ABSB_MAX_K, ABSB_ERR_INVALID, "nprobe=%d outside [1,%d]", nprobe, ABSB_MAX_K);
+  // chunk rows so the score matrix stays <= 1 GiB
+  const int64_t rows_max = std::max<int64_t>(128, ((int64_t)1 << 28) / nlist);
+  for (int64_t r0 = 0; r0 < nq; r0 += rows_max) {
+    const int64_t nr = std::min(rows_max, nq - r0);
+    ws_scores.reserve((size_t)std::min(rows_max, nq) * nlist);
+    coarse_scores((int)nr, q + r0 * d, ws_scores.p, st);
+    select_rows(ws_scores.p, nlist, nr, nlist, 0, nprobe, Dc + r0 * nprobe, Ic + r0 * nprobe, nprobe,
+                finalize, st);
+    stats.launches += 1;
+  }
+}
+
+void IvfIndex::assign_dev(int64_t n, const float* x, long long* list_ids, cudaStream_t st) {
+  ws_coarse_s.reserve((size_t)std::min<int64_t>(n, (int64_t)1 << 22));
+  // Dc is scratch: process in slices that fit ws_coarse_s
+  const int64_t slice = (int64_t)1 << 22;
+  for (int64_t r0 = 0; r0 < n; r0 += slice) {
+    const int64_t nr = std::min(slice, n - r0);
+    coarse_dev(nr, x + r0 * d, 1, ws_coarse_s.p, list_ids + r0, true, st);
+  }
+}
+
+// ---------------------------------------------------------------- add ----------------------
+void IvfIndex::refresh_host_sizes(cudaStream_t st) {
+  ABSB_CUDA(cudaMemcpyAsync(h_list_size.data(), list_size.p, sizeof(long long) * nlist,
+                            cudaMemcpyDeviceToHost, st));
+  ABSB_CUDA(cudaStreamSynchronize(st));
+  std::vector<int64_t> pages(nlist);
+  const int P = pool.page_vecs;
+  for (int l = 0; l < nlist; ++l) pages[l] = (h_list_size[l] + P - 1) / P;
+  std::sort(pages.begin(), pages.end(), std::greater<int64_t>());
+  h_pages_prefix_desc.assign(nlist + 1, 0);
+  for (int l = 0; l < nlist; ++l) h_pages_prefix_desc[l + 1] = h_pages_prefix_desc[l] + pages[l];
+}
+
+int64_t IvfIndex::items_bound_per_query(int nprobe) const {
+  if (h_pages_prefix_desc.empty()) return 0;
+  return h_pages_prefix_desc[std::min(nprobe, nlist)];
+}
+
+void IvfIndex::add_core_dev(int64_t n, const float* x, const long long* ids,
+                            const long long* list_ids, cudaStream_t st) {
+  ABSB_CHECK(trained, ABSB_ERR_STATE, "index is not trained");
+  if (n == 0) return;
+  ABSB_CHECK(n < ((int64_t)1 << 31), ABSB_ERR_INVALID, "add chunk too large");
+  const int P = pool.page_vecs;
+  const int sms = props.sm_count;
+
+  // scratch carved out of one buffer: keys, keys_sorted, vals, perm, hist, call_off, fresh, ...
+  DBuf<unsigned> keys, keys_sorted, hist, call_off;
+  DBuf<int> vals, perm, fresh_pages, fresh_off;
+  DBuf<long long> new_size, pages_per_list, new_off;
+  keys.alloc_exact(n); keys_sorted.alloc_exact(n); vals.alloc_exact(n); perm.alloc_exact(n);
+  hist.alloc_exact(nlist + 2); call_off.alloc_exact(nlist + 2);
+  fresh_pages.alloc_exact(nlist + 1); fresh_off.alloc_exact(nlist + 1);
+  new_size.alloc_exact(nlist); pages_per_list.alloc_exact(nlist + 1); new_off.alloc_exact(nlist + 1);
+
+  ABSB_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned) * (nlist + 2), st));
+  make_keys_kernel<<<grid_for(n, 256, sms), 256, 0, st>>>(n, list_ids, nlist, shard_rank, shard_world,
+                                                          keys.p, vals.p, hist.p);
+  ABSB_CUDA(cudaGetLastError());
+
+  int bits = 1;
+  while ((1ll << bits) < (long long)nlist + 1) ++bits;
+  size_t tmp_bytes = 0, t2 = 0;
+  ABSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, vals.p, perm.p,
+                                            (int)n, 0, bits, st));
+  ABSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t2, hist.p, call_off.p, nlist + 2, st));
+  tmp_bytes = std::max(tmp_bytes, t2);
+  ABSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t2, pages_per_list.p, new_off.p, nlist + 1, st));
+  tmp_bytes = std::max(tmp_bytes, t2);
+  ws_cub.reserve(tmp_bytes + 16);
+  size_t tb = ws_cub.cap;
+  ABSB_CUDA(cub::DeviceRadixSort::SortPairs(ws_cub.p, tb, keys.p, keys_sorted.p, vals.p, perm.p, (int)n,
+                                            0, bits, st));
+  tb = ws_cub.cap;
+  ABSB_CUDA(cub::DeviceScan::ExclusiveSum(ws_cub.p, tb, hist.p, call_off.p, nlist + 2, st));
+
+  list_growth_kernel<<<(nlist + 255) / 256, 256, 0, st>>>(nlist, P, list_size.p, hist.p, new_size.p,
+                                                          fresh_pages.p, pages_per_list.p);
+  ABSB_CUDA(cudaGetLastError());
+  ABSB_CUDA(cudaMemsetAsync(fresh_pages.p + nlist, 0, sizeof(int), st));
+  ABSB_CUDA(cudaMemsetAsync(pages_per_list.p + nlist, 0, sizeof(long long), st));
+  tb = ws_cub.cap;
+  ABSB_CUDA(cub::DeviceScan::ExclusiveSum(ws_cub.p, tb, fresh_pages.p, fresh_off.p, nlist + 1, st));
+  tb = ws_cub.cap;
+  ABSB_CUDA(cub::DeviceScan::ExclusiveSum(ws_cub.p, tb, pages_per_list.p, new_off.p, nlist + 1, st));
+
+  // host needs: rows kept, fresh pages, total pages
+  unsigned h_dropped_off = 0;
+  int h_fresh_total = 0;
+  long long h_total_pages = 0;
+  ABSB_CUDA(cudaMemcpyAsync(&h_dropped_off, call_off.p + nlist, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  ABSB_CUDA(cudaMemcpyAsync(&h_fresh_total, fresh_off.p + nlist, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ABSB_CUDA(cudaMemcpyAsync(&h_total_pages, new_off.p + nlist, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  ABSB_CUDA(cudaStreamSynchronize(st));
+  const int64_t n_kept = h_dropped_off;  // rows with key < nlist come first
+  ABSB_CHECK(h_total_pages < ((long long)1 << 31), ABSB_ERR_UNSUPPORTED, "page table overflow");
+
+  pool.ensure_pages(pool.pages_used + h_fresh_total, st);
+  DBuf<int> new_pages;
+  new_pages.alloc_exact((size_t)std::max<long long>(h_total_pages, 1));
+  build_page_table_kernel<<<nlist, 64, 0, st>>>(nlist, P, list_size.p, pt_off.p, pt_pages.p, new_off.p,
+                                                fresh_off.p, fresh_pages.p, pool.pages_used, new_pages.p);
+  ABSB_CUDA(cudaGetLastError());
+  if (n_kept > 0) {
+    scatter_rows_kernel<<<grid_for(n_kept * 32, 256, sms), 256, 0, st>>>(
+        n_kept, d / 4, P, pool.slab_shift, keys_sorted.p, perm.p, call_off.p, list_size.p, new_off.p,
+        new_pages.p, pool.d_code_slabs.p, pool.d_id_slabs.p, x, ids, rows_seen);
+    ABSB_CUDA(cudaGetLastError());
+  }
+  ABSB_CUDA(cudaMemcpyAsync(list_size.p, new_size.p, sizeof(long long) * nlist, cudaMemcpyDeviceToDevice, st));
+  ABSB_CUDA(cudaMemcpyAsync(pt_off.p, new_off.p, sizeof(long long) * (nlist + 1), cudaMemcpyDeviceToDevice, st));
+  ABSB_CUDA(cudaStreamSynchronize(st));
+  pt_pages = std::move(new_pages);
+  pt_total_pages = h_total_pages;
+  pool.pages_used += h_fresh_total;
+  // faiss: ids default to ntotal + i over ALL rows of the call; a shard numbers rows the same way
+  // (rows_seen) but counts only the rows it keeps in ntotal.
+  ntotal += n_kept;
+  rows_seen += n;
+  refresh_host_sizes(st);
+  have_last_scan = false;
+}
+
+void IvfIndex::add_dev(int64_t n, const float* x, const long long* ids, cudaStream_t st) {
+  if (n == 0) return;
+  const int64_t step = (int64_t)1 << 22;
+  for (int64_t r0 = 0; r0 < n; r0 += step) {
+    const int64_t nr = std::min(step, n - r0);
+    ws_list_ids.reserve((size_t)nr);
+    assign_dev(nr, x + r0 * d, ws_list_ids.p, st);
+    add_core_dev(nr, x + r0 * d, ids ? ids + r0 : nullptr, ws_list_ids.p, st);
+  }
+}
+
+void IvfIndex::get_list(int64_t l, float* codes, long long* ids) {
+  const int64_t size = h_list_size[l];
+  if (size == 0) return;
+  cudaStream_t st = own_stream;
+  DBuf<float> dc;
+  DBuf<long long> di;
+  if (codes) dc.alloc_exact((size_t)size * d);
+  if (ids) di.alloc_exact((size_t)size);
+  copy_list_kernel<<<(unsigned)std::min<int64_t>(size, 4096), 128, 0, st>>>(table(), l, dc.p, di.p);
+  ABSB_CUDA(cudaGetLastError());
+  if (codes) ABSB_CUDA(cudaMemcpyAsync(codes, dc.p, sizeof(float) * (size_t)size * d, cudaMemcpyDeviceToHost, st));
+  if (ids) ABSB_CUDA(cudaMemcpyAsync(ids, di.p, sizeof(long long) * (size_t)size, cudaMemcpyDeviceToHost, st));
+  ABSB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---------------------------------------------------------------- train --------------------
+namespace {
+// faiss rand_perm: Fisher–Yates driven by std::mt19937, i2 = i + mt() % (n - i)
+std::vector<int> rand_perm_host(int64_t n, int64_t seed) {
+  std::vector<int> perm((size_t)n);
+  std::iota(perm.begin(), perm.end(), 0);
+  std::mt19937 mt((unsigned)seed);
+  for (int64_t i = 0; i + 1 < n; ++i) {
+    const int64_t i2 = i + (int64_t)(mt() % (unsigned)(n - i));
+    std::swap(perm[i], perm[i2]);
+  }
+  return perm;
+}
+
+// Clustering::split_clusters on the host (needs a sequential RNG); returns number of splits.
+int64_t split_clusters_host(int d, int64_t k, int64_t n, std::vector<float>& hassign, float* centroids) {
+  const float EPS = 1.f / 1024.f;
+  int64_t nsplit = 0;
+  std::mt19937 mt(1234u);
+  for (int64_t ci = 0; ci < k; ++ci) {
+    if (hassign[ci] != 0.f) continue;
+    int64_t cj;
+    for (cj = 0;; cj = (cj + 1) % k) {
+      const float p = (float)((hassign[cj] - 1.0) / (float)(n - k));
+      const float r = mt() / (float)mt.max();
+      if (r < p) break;
+    }
+    std::copy(centroids + cj * d, centroids + (cj + 1) * d, centroids + ci * d);
+    for (int j = 0; j < d; ++j) {
+      if (j % 2 == 0) {
+        centroids[ci * d + j] *= 1 + EPS;
+        centroids[cj * d + j] *= 1 - EPS;
+      } else {
+        centroids[ci * d + j] *= 1 - EPS;
+        centroids[cj * d + j] *= 1 + EPS;
+      }
+    }
+    hassign[ci] = hassign[cj] / 2;
+    hassign[cj] -= hassign[ci];
+    ++nsplit;
+  }
+  return nsplit;
+}
+}  // namespace
+
+void IvfIndex::train_dev(int64_t n, const float* x, cudaStream_t st) {
+  const int64_t k = nlist;
+  ABSB_CHECK(n >= k, ABSB_ERR_INVALID,
+             "Number of training points (%lld) should be at least as large as number of clusters (%lld)",
+             (long long)n, (long long)k);
+  ABSB_CHECK(n < ((int64_t)1 << 31), ABSB_ERR_INVALID, "training set too large");
+  const int sms = props.sm_count;
+  const int d4 = d / 4;
+  DBuf<float> sample;
+  DBuf<int> rows;
+  const float* xs = x;
+  int64_t ns = n;
+  if (n > k * cp.max_points_per_centroid) {
+    ns = k * cp.max_points_per_centroid;
+    std::vector<int> perm = rand_perm_host(n, cp.seed);
+    rows.alloc_exact(ns);
+    ABSB_CUDA(cudaMemcpyAsync(rows.p, perm.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, st));
+    sample.alloc_exact((size_t)ns * d);
+    gather_rows_kernel<<<grid_for(ns * 32, 256, sms), 256, 0, st>>>(ns, d4, rows.p, x, sample.p);
+    ABSB_CUDA(cudaGetLastError());
+    ABSB_CUDA(cudaStreamSynchronize(st));
+    xs = sample.p;
+  }
+  if (ns == k) {
+    ABSB_CUDA(cudaMemcpyAsync(centroids.p, xs, sizeof(float) * (size_t)k * d, cudaMemcpyDeviceToDevice, st));
+    trained = true;
+    c3_dirty = true;
+    return;
+  }
+  {
+    std::vector<int> perm = rand_perm_host(ns, cp.seed + 1);
+    rows.alloc_exact(k);
+    ABSB_CUDA(cudaMemcpyAsync(rows.p, perm.data(), sizeof(int) * k, cudaMemcpyHostToDevice, st));
+    gather_rows_kernel<<<grid_for(k * 32, 256, sms), 256, 0, st>>>(k, d4, rows.p, xs, centroids.p);
+    ABSB_CUDA(cudaGetLastError());
+    ABSB_CUDA(cudaStreamSynchronize(st));
+  }
+  trained = true;  // coarse_dev needs it; centroids are valid from here on
+  c3_dirty = true;
+
+  DBuf<long long> assign;
+  DBuf<unsigned> keys, keys_sorted, hist, off;
+  DBuf<int> vals, perm;
+  DBuf<float> hassign_d;
+  assign.alloc_exact(ns); keys.alloc_exact(ns); keys_sorted.alloc_exact(ns); vals.alloc_exact(ns);
+  perm.alloc_exact(ns); hist.alloc_exact(k + 2); off.alloc_exact(k + 2); hassign_d.alloc_exact(k);
+  int bits = 1;
+  while ((1ll << bits) < (long long)k + 1) ++bits;
+  size_t tmp_bytes = 0, t2 = 0;
+  ABSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, vals.p, perm.p, (int)ns, 0, bits, st));
+  ABSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t2, hist.p, off.p, (int)k + 2, st));
+  ws_cub.reserve(std::max(tmp_bytes, t2) + 16);
+  std::vector<float> hassign(k);
+  std::vector<float> hcent;
+
+  for (int it = 0; it < cp.niter; ++it) {
+    assign_dev(ns, xs, assign.p, st);
+    ABSB_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned) * (k + 2), st));
+    make_keys_kernel<<<grid_for(ns, 256, sms), 256, 0, st>>>(ns, assign.p, (int)k, 0, 1, keys.p, vals.p, hist.p);
+    ABSB_CUDA(cudaGetLastError());
+    size_t tb = ws_cub.cap;
+    ABSB_CUDA(cub::DeviceRadixSort::SortPairs(ws_cub.p, tb, keys.p, keys_sorted.p, vals.p, perm.p, (int)ns, 0, bits, st));
+    tb = ws_cub.cap;
+    ABSB_CUDA(cub::DeviceScan::ExclusiveSum(ws_cub.p, tb, hist.p, off.p, (int)k + 2, st));
+    centroid_mean_kernel<<<(unsigned)k, std::min(256, d), 0, st>>>(d, off.p, perm.p, xs, centroids.p, hassign_d.p);
+    ABSB_CUDA(cudaGetLastError());
+    c3_dirty = true;
+    ABSB_CUDA(cudaMemcpyAsync(hassign.data(), hassign_d.p, sizeof(float) * k, cudaMemcpyDeviceToHost, st));
+    ABSB_CUDA(cudaStreamSynchronize(st));
+    bool any_empty = false;
+    for (int64_t c = 0; c < k; ++c) any_empty |= (hassign[c] == 0.f);
+    if (any_empty) {
+      hcent.resize((size_t)k * d);
+      ABSB_CUDA(cudaMemcpy(hcent.data(), centroids.p, sizeof(float) * (size_t)k * d, cudaMemcpyDeviceToHost));
+      split_clusters_host(d, k, ns, hassign, hcent.data());
+      ABSB_CUDA(cudaMemcpy(centroids.p, hcent.data(), sizeof(float) * (size_t)k * d, cudaMemcpyHostToDevice));
+      c3_dirty = true;
+    }
+  }
+}
+
+void IvfIndex::train_host(int64_t n, const float* x) {
+  const int64_t k = nlist;
+  ABSB_CHECK(n >= k, ABSB_ERR_INVALID,
+             "Number of training points (%lld) should be at least as large as number of clusters (%lld)",
+             (long long)n, (long long)k);
+  // Subsample on the host so that only the sample crosses PCIe, then run the device trainer on it
+  // with subsampling disabled (the permutation must not be applied twice).
+  cudaStream_t st = own_stream;
+  DBuf<float> sample;
+  int64_t ns = n;
+  if (n > k * cp.max_points_per_centroid) {
+    ns = k * cp.max_points_per_centroid;
+    std::vector<int> perm = rand_perm_host(n, cp.seed);
+    sample.alloc_exact((size_t)ns * d);
+    const int64_t step = std::max<int64_t>(1, ((int64_t)64 << 20) / (d * (int64_t)sizeof(float)));
+    HBuf<float> stage;
+    stage.reserve((size_t)step * d);
+    for (int64_t r0 = 0; r0 < ns; r0 += step) {
+      const int64_t nr = std::min(step, ns - r0);
+      for (int64_t i = 0; i < nr; ++i)
+        std::copy(x + (size_t)perm[r0 + i] * d, x + (size_t)(perm[r0 + i] + 1) * d, stage.p + (size_t)i * d);
+      ABSB_CUDA(cudaMemcpyAsync(sample.p + (size_t)r0 * d, stage.p, sizeof(float) * (size_t)nr * d,
+                                cudaMemcpyHostToDevice, st));
+      ABSB_CUDA(cudaStreamSynchronize(st));
+    }
+  } else {
+    sample.alloc_exact((size_t)ns * d);
+    ABSB_CUDA(cudaMemcpyAsync(sample.p, x, sizeof(float) * (size_t)ns * d, cudaMemcpyHostToDevice, st));
+    ABSB_CUDA(cudaStreamSynchronize(st));
+  }
+  const int saved = cp.max_points_per_centroid;
+  // ns <= k * max_ppc already holds, so train_dev will not subsample again
+  train_dev(ns, sample.p, st);
+  cp.max_points_per_centroid = saved;
+  ABSB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---------------------------------------------------------------- search -------------------
+void IvfIndex::fold_stats() {
+  if (!stats_pending) return;
+  unsigned long long h[2] = {0, 0};
+  ABSB_CUDA(cudaMemcpy(h, ws_stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+  stats.vectors += (int64_t)h[0];
+  stats.items += (int64_t)h[1];
+  stats.bytes = stats.vectors * ((int64_t)d * 4 + 8);
+  stats_pending = false;
+}
+
+void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int nprobe,
+                                      const long long* coarse, float* D, long long* I,
+                                      cudaStream_t st) {
+  ABSB_CHECK(trained, ABSB_ERR_STATE, "index is not trained");
+  ABSB_CHECK(k >= 1 && k <= ABSB_MAX_K, ABSB_ERR_INVALID, "k=%d outside [1,%d]", k, ABSB_MAX_K);
+  ABSB_CHECK(nprobe >= 1, ABSB_ERR_INVALID, "nprobe=%d", nprobe);
+  if (nq == 0) return;
+  const int64_t per_q = std::max<int64_t>(1, items_bound_per_query(nprobe));
+  // bound the partial-result buffers to ~1 GiB per launch
+  int64_t nb_max = std::min<int64_t>(kMaxPlanQueries, std::max<int64_t>(1, ((int64_t)1 << 30) / (per_q * k * 12)));
+  for (int64_t q0 = 0; q0 < nq; q0 += nb_max) {
+    const int nb = (int)std::min(nb_max, nq - q0);
+    const int64_t max_items = per_q * nb;
+    ABSB_CHECK(max_items < ((int64_t)1 << 31), ABSB_ERR_UNSUPPORTED, "too many scan items");
+    ws_items.reserve((size_t)max_items);
+    ws_part_s.reserve((size_t)max_items * k);
+    ws_part_id.reserve((size_t)max_items * k);
+    ws_q_begin.reserve(kMaxPlanQueries + 1);
+    if (stats_pending) fold_stats();  // only one plan's numbers fit in ws_stats
+    launch_plan(table(), coarse + q0 * nprobe, nb, nprobe, scan_chunk, (int)max_items, ws_items.p,
+                ws_q_begin.p, ws_counters.p, ws_counters.p + 1, ws_stats.p, st);
+    ScanLaunch a;
+    a.Q = q + q0 * d;
+    a.d = d;
+    a.k = k;
+    a.items = ws_items.p;
+    a.n_items = ws_counters.p;
+    a.queue_counter = ws_counters.p + 1;
+    a.part_s = ws_part_s.p;
+    a.part_id = ws_part_id.p;
+    a.sm_count = props.sm_count;
+    a.ctas_per_sm = scan_ctas_per_sm;
+    launch_scan(a, st);
+    merge_partials(nb, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, D + q0 * k, I + q0 * k, st);
+    last_scan = a;
+    have_last_scan = true;
+    stats_pending = true;
+    stats.launches += 3;
+    if (q0 + nb_max < nq) fold_stats();
+  }
+}
+
+void IvfIndex::search_dev(int64_t nq, const float* q, int k, int nprobe, float* D, long long* I,
+                          cudaStream_t st) {
+  ABSB_CHECK(trained, ABSB_ERR_STATE, "index is not trained");
+  const int np = std::min(nprobe, nlist);
+  ABSB_CHECK(np >= 1 && np <= ABSB_MAX_K, ABSB_ERR_INVALID, "nprobe=%d outside [1,%d]", nprobe, ABSB_MAX_K);
+  const int64_t step = kMaxPlanQueries;
+  ws_coarse_s.reserve((size_t)step * np);
+  ws_coarse_i.reserve((size_t)step * np);
+  for (int64_t q0 = 0; q0 < nq; q0 += step) {
+    const int64_t nb = std::min(step, nq - q0);
+    coarse_dev(nb, q + q0 * d, np, ws_coarse_s.p, ws_coarse_i.p, true, st);
+    search_preassigned_dev(nb, q + q0 * d, k, np, ws_coarse_i.p, D + q0 * k, I + q0 * k, st);
+  }
+}
+
+// =========================================================================================
+// FlatIndex
+// =========================================================================================
+FlatIndex::FlatIndex(int d_, int device_) : d(d_), device(device_) {
+  ABSB_CHECK(d > 0 && d % 4 == 0, ABSB_ERR_UNSUPPORTED, "d must be a positive multiple of 4 (d=%d)", d);
+  props = device_props(device);
+  DeviceGuard g(device);
+  ABSB_CUDA(cudaStreamCreate(&own_stream));
+}
+
+FlatIndex::~FlatIndex() {
+  cudaSetDevice(device);
+  if (own_stream) {
+    cudaStreamSynchronize(own_stream);
+    cudaStreamDestroy(own_stream);
+  }
+}
+
+void FlatIndex::add_dev(int64_t n, const float* x, cudaStream_t st) {
+  if (n == 0) return;
+  if ((size_t)(ntotal + n) * d > xb.cap) {
+    DBuf<float> bigger;
+    bigger.alloc_exact(std::max<size_t>((size_t)(ntotal + n) * d, xb.cap * 2));
+    if (ntotal)
+      ABSB_CUDA(cudaMemcpyAsync(bigger.p, xb.p, sizeof(float) * (size_t)ntotal * d, cudaMemcpyDeviceToDevice, st));
+    ABSB_CUDA(cudaStreamSynchronize(st));
+    xb = std::move(bigger);
+  }
+  ABSB_CUDA(cudaMemcpyAsync(xb.p + (size_t)ntotal * d, x, sizeof(float) * (size_t)n * d, cudaMemcpyDeviceToDevice, st));
+  ntotal += n;
+}
+
+void FlatIndex::search_dev(int64_t nq, const float* q, int k, float* D, long long* I, cudaStream_t st) {
+  ABSB_CHECK(k >= 1 && k <= ABSB_MAX_K, ABSB_ERR_INVALID, "k=%d outside [1,%d]", k, ABSB_MAX_K);
+  if (nq == 0) return;
+  const int64_t col_chunk = 65536;
+  const int nchunks = (int)std::max<int64_t>(1, ceil_div(ntotal, col_chunk));
+  const int64_t row_step = 1024;
+  ws_scores.reserve((size_t)row_step * std::min<int64_t>(col_chunk, std::max<int64_t>(ntotal, 1)));
+  ws_part_s.reserve((size_t)row_step * nchunks * k);
+  ws_part_id.reserve((size_t)row_step * nchunks * k);
+  ws_q_begin.reserve(row_step + 1);
+  std::vector<int> qb(row_step + 1);
+  for (int i = 0; i <= row_step; ++i) qb[i] = i * nchunks;
+  ABSB_CUDA(cudaMemcpyAsync(ws_q_begin.p, qb.data(), sizeof(int) * (row_step + 1), cudaMemcpyHostToDevice, st));
+  ABSB_CUDA(cudaStreamSynchronize(st));
+  for (int64_t r0 = 0; r0 < nq; r0 += row_step) {
+    const int64_t nr = std::min(row_step, nq - r0);
+    if (ntotal == 0) {
+      // every slot missing: merge of zero candidates writes the padding
+      std::vector<int> zero(nr + 1, 0);
+      ABSB_CUDA(cudaMemcpyAsync(ws_q_begin.p, zero.data(), sizeof(int) * (nr + 1), cudaMemcpyHostToDevice, st));
+      ABSB_CUDA(cudaStreamSynchronize(st));
+      merge_partials((int)nr, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, D + r0 * k, I + r0 * k, st);
+      continue;
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      const int64_t c0 = (int64_t)c * col_chunk;
+      const int nc = (int)std::min(col_chunk, ntotal - c0);
+      gemm_nt_f32((int)nr, nc, d, q + r0 * d, d, xb.p + (size_t)c0 * d, d, ws_scores.p, nc, st);
+      select_rows(ws_scores.p, nc, nr, nc, c0, k, ws_part_s.p + (size_t)c * k, ws_part_id.p + (size_t)c * k,
+                  (int64_t)nchunks * k, false, st);
+    }
+    merge_partials((int)nr, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, D + r0 * k, I + r0 * k, st);
+  }
+}
+
+}  // namespace absb

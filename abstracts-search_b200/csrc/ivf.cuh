@@ -1,0 +1,142 @@
+// ivf.cuh — host-side state of the B200 IndexIVFFlat / IndexFlatIP replacements.
+#pragma once
+
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+#include "ivf_scan.cuh"
+
+namespace absb {
+
+// Slab pool of list pages.  Page g -> slab g >> shift.  Slabs are plain cudaMalloc blocks that are
+// never moved, so growing the index never copies list data (180 GB HBM: no room for a 2x copy of a
+// 106 GB shard).
+struct PagePool {
+  int d = 0;
+  int page_vecs = 0;
+  int slab_shift = 0;  // pages per slab = 1 << slab_shift
+  int64_t pages_used = 0;
+  std::vector<float*> code_slabs;
+  std::vector<long long*> id_slabs;
+  DBuf<float*> d_code_slabs;
+  DBuf<long long*> d_id_slabs;
+  size_t table_cap = 0;
+
+  void configure(int d_, int page_vecs_);
+  void ensure_pages(int64_t total_pages, cudaStream_t st);
+  void release();
+  ~PagePool() { release(); }
+};
+
+struct ClusteringParams {
+  int niter = 10;
+  int max_points_per_centroid = 256;
+  int min_points_per_centroid = 39;
+  int64_t seed = 1234;
+};
+
+struct SearchStats {
+  int64_t vectors = 0, bytes = 0, items = 0, launches = 0;
+};
+
+struct IvfIndex {
+  int d, nlist, device;
+  DeviceProps props;
+  cudaStream_t own_stream = nullptr;
+  bool trained = false;
+  ClusteringParams cp;
+  int shard_rank = 0, shard_world = 1;
+
+  DBuf<float> centroids;  // [nlist, d]
+  DBuf<uint16_t> centroids3;  // bf16 [nlist, 3d] = [hi | mid | lo] split for the tcgen05 coarse GEMM
+  DBuf<uint16_t> ws_q3;
+  bool c3_dirty = true;
+
+  // inverted lists
+  PagePool pool;
+  DBuf<long long> list_size;  // [nlist]
+  DBuf<long long> pt_off;     // [nlist+1]
+  DBuf<int> pt_pages;
+  int64_t pt_total_pages = 0;
+  std::vector<int64_t> h_list_size;
+  std::vector<int64_t> h_pages_prefix_desc;  // prefix sums of per-list page counts, sorted descending
+  int64_t ntotal = 0;
+  int64_t rows_seen = 0;  // rows offered to add() so far, kept or not: the next default id
+
+  // tunables
+  int scan_chunk = 128;
+  int coarse_impl = 0;
+  int scan_ctas_per_sm = 0;
+
+  // workspaces (single stream at a time)
+  DBuf<float> ws_scores;
+  DBuf<float> ws_coarse_s;
+  DBuf<long long> ws_coarse_i;
+  DBuf<ScanItem> ws_items;
+  DBuf<float> ws_part_s;
+  DBuf<long long> ws_part_id;
+  DBuf<int> ws_q_begin;
+  DBuf<int> ws_counters;  // [0] n_items, [1] queue counter
+  DBuf<unsigned long long> ws_stats;
+  DBuf<unsigned char> ws_cub;
+  DBuf<float> ws_x;  // staged host rows / queries
+  DBuf<long long> ws_ids;
+  DBuf<long long> ws_list_ids;
+  DBuf<float> ws_D;
+  DBuf<long long> ws_I;
+
+  // replay info for absb_ivf_time_scan
+  ScanLaunch last_scan{};
+  bool have_last_scan = false;
+  SearchStats stats;
+  bool stats_pending = false;  // ws_stats holds device-side numbers not yet folded into `stats`
+
+  IvfIndex(int d, int nlist, int device);
+  ~IvfIndex();
+
+  ListTable table() const;
+  void reset_stats() {
+    stats = SearchStats{};
+    stats_pending = false;
+  }
+
+  void reset();
+  void set_centroids_dev(const float* c, cudaStream_t st);
+  void train_dev(int64_t n, const float* x, cudaStream_t st);
+  void train_host(int64_t n, const float* x);
+  // scores -> top-k coarse (k = nprobe) for nq <= chunk rows; Ic int64 [nq, nprobe]
+  void coarse_dev(int64_t nq, const float* q, int nprobe, float* Dc, long long* Ic, bool finalize,
+                  cudaStream_t st);
+  void assign_dev(int64_t n, const float* x, long long* list_ids, cudaStream_t st);
+  void add_core_dev(int64_t n, const float* x, const long long* ids, const long long* list_ids,
+                    cudaStream_t st);
+  void add_dev(int64_t n, const float* x, const long long* ids, cudaStream_t st);
+  void search_preassigned_dev(int64_t nq, const float* q, int k, int nprobe, const long long* coarse,
+                              float* D, long long* I, cudaStream_t st);
+  void search_dev(int64_t nq, const float* q, int k, int nprobe, float* D, long long* I,
+                  cudaStream_t st);
+  void fold_stats();
+  void coarse_scores(int M, const float* q, float* S, cudaStream_t st);
+  void get_list(int64_t list_no, float* codes, long long* ids);
+  int64_t items_bound_per_query(int nprobe) const;
+  void refresh_host_sizes(cudaStream_t st);
+};
+
+struct FlatIndex {
+  int d, device;
+  DeviceProps props;
+  cudaStream_t own_stream = nullptr;
+  DBuf<float> xb;
+  int64_t ntotal = 0;
+  DBuf<float> ws_scores, ws_part_s, ws_x, ws_D;
+  DBuf<long long> ws_part_id, ws_I;
+  DBuf<int> ws_q_begin;
+
+  FlatIndex(int d, int device);
+  ~FlatIndex();
+  void add_dev(int64_t n, const float* x, cudaStream_t st);
+  void search_dev(int64_t nq, const float* q, int k, float* D, long long* I, cudaStream_t st);
+};
+
+}  // namespace absb

@@ -1,0 +1,337 @@
+// ivf_scan.cu — the fine scan of IndexIVFFlat::search: for every (query, probed list) pair, the
+// inner product of the query with every vector of the list, keeping the k best.
+//
+// Stands in for faiss's IVFFlatScanner::scan_codes + heap_replace_top under
+// IndexIVF::search_preassigned — what `sidecar-search index tune` (/root/reference/Makefile:31-32)
+// and app.py's query loop (/root/reference/README.md:16,28) spend their time in.
+//
+// B200 design (HBM-bound: 2 flop per 4 bytes):
+//   * Inverted lists live in fixed-size pages (P vectors, ~64 KB) inside large slabs; a list is a
+//     sequence of pages in insertion order.  A *plan* kernel turns the coarse result
+//     [nq, nprobe] into a flat queue of work items, each a run of physically contiguous vectors
+//     (<= chunk) of one list for one query.
+//   * The *scan* kernel is persistent (grid = SMs x resident CTAs): every WARP pulls items off a
+//     global atomic queue (next index prefetched while the current item streams).  A warp reads
+//     one 4 KB vector as 8 x 128-bit fully coalesced streaming loads per lane (ld.global.cs),
+//     U vectors in flight, FMAs against the query held in registers, butterfly-reduces, and
+//     tests the score against the warp-uniform k-th-best threshold of a register-resident
+//     WarpTopK.  No shared memory, no block barrier, no intermediate score array.
+//   * Each item emits k partial results; merge_partials (dense.cu) reduces them per query.
+// Algorithmic bytes per launch = sum over items of len * (4 d + 8).
+#include "common.cuh"
+#include "ivf_scan.cuh"
+#include "topk.cuh"
+
+namespace absb {
+
+namespace {
+
+// ------------------------------------------------------------------ plan --------------------
+// One CTA of 1024 threads.  Warp w handles queries w, w+32, ...; lanes stride over probes.
+// Pass 1 counts items per query, a block scan turns counts into q_begin, pass 2 emits items.
+__device__ __forceinline__ int walk_list(const ListTable& lt, long long l, int chunk, int q,
+                                         ScanItem* out /* nullptr = count only */,
+                                         long long* vectors) {
+  if (l < 0 || l >= lt.nlist) return 0;
+  const long long size = lt.list_size[l];
+  if (size == 0) return 0;
+  const long long pb = lt.pt_off[l];
+  const int P = lt.page_vecs;
+  const long long npages = (size + P - 1) / P;
+  int n = 0;
+  long long run_first = -1, run_len = 0;  // run of contiguous pages, length in vectors
+  auto flush = [&]() {
+    if (run_len == 0) return;
+    if (out) {
+      const int slab = (int)(run_first >> lt.slab_shift);
+      const long long in_slab = run_first & ((1ll << lt.slab_shift) - 1);
+      ScanItem it;
+      it.codes = lt.code_slabs[slab] + (size_t)in_slab * P * lt.d;
+      it.ids = lt.id_slabs[slab] + (size_t)in_slab * P;
+      it.len = (int)run_len;
+      it.q = q;
+      out[n] = it;
+    }
+    ++n;
+    run_len = 0;
+  };
+  for (long long i = 0; i < npages; ++i) {
+    const long long pg = lt.pt_pages[pb + i];
+    const long long nv = (i == npages - 1) ? size - i * P : P;
+    const bool contiguous = run_len > 0 && pg == run_first + run_len / P &&
+                            (pg >> lt.slab_shift) == (run_first >> lt.slab_shift) &&
+                            run_len + nv <= chunk;
+    if (!contiguous) {
+      flush();
+      run_first = pg;
+    }
+    run_len += nv;
+  }
+  flush();
+  if (vectors) *vectors += size;
+  return n;
+}
+
+__global__ __launch_bounds__(1024) void plan_kernel(ListTable lt, const long long* __restrict__ coarse,
+                                                   int nq, int nprobe, int chunk, int max_items,
+                                                   ScanItem* __restrict__ items,
+                                                   int* __restrict__ q_begin /* [nq+1] */,
+                                                   int* __restrict__ n_items,
+                                                   int* __restrict__ queue_counter,
+                                                   unsigned long long* __restrict__ stats) {
+  __shared__ int q_count[kMaxPlanQueries];
+  __shared__ int warp_tot[32];
+  __shared__ unsigned long long sm_vectors;
+  __shared__ int sm_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) sm_vectors = 0;
+  for (int q = threadIdx.x; q < kMaxPlanQueries; q += blockDim.x) q_count[q] = 0;
+  __syncthreads();
+
+  // pass 1: count
+  long long vec = 0;
+  for (int q = warp; q < nq; q += 32) {
+    int c = 0;
+    for (int p = lane; p < nprobe; p += 32)
+      c += walk_list(lt, coarse[(size_t)q * nprobe + p], chunk, q, nullptr, &vec);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFullMask, c, o);
+    if (lane == 0) q_count[q] = c;
+  }
+  if (vec) atomicAdd(&sm_vectors, (unsigned long long)vec);
+  __syncthreads();
+
+  // block exclusive scan over q_count[0..kMaxPlanQueries)  (1024 threads, one element each)
+  {
+    const int t = threadIdx.x;
+    int v = (t < kMaxPlanQueries) ? q_count[t] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(kFullMask, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFullMask, wi, o);
+        if (lane >= o) wi += y;
+      }
+      warp_tot[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    const int excl = warp_tot[warp] + incl - v;
+    if (t < kMaxPlanQueries) q_count[t] = excl;
+    __syncthreads();
+    if (t < nq) q_begin[t] = excl;
+    if (t == nq - 1) {
+      const int total = excl + v;
+      q_begin[nq] = total;
+      sm_total = total;
+      *n_items = total <= max_items ? total : -1;  // -1: capacity bug, scan does nothing
+      *queue_counter = 0;
+      stats[0] = sm_vectors;
+      stats[1] = (unsigned long long)total;
+    }
+  }
+  __syncthreads();
+  if (sm_total > max_items) return;
+
+  // pass 2: emit.  Lane offsets inside a query via warp exclusive scan of per-probe counts.
+  for (int q = warp; q < nq; q += 32) {
+    int base = q_count[q];
+    for (int p0 = 0; p0 < nprobe; p0 += 32) {
+      const int p = p0 + lane;
+      const long long l = p < nprobe ? coarse[(size_t)q * nprobe + p] : -1;
+      const int c = walk_list(lt, l, chunk, q, nullptr, nullptr);
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const int tot = __shfl_sync(kFullMask, incl, 31);
+      const int off = base + incl - c;
+      if (c > 0 && off + c <= max_items) walk_list(lt, l, chunk, q, items + off, nullptr);
+      base += tot;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ scan --------------------
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+
+__device__ __forceinline__ ScanItem load_item(const ScanItem* p) {
+  // 32-byte item, two 16-byte loads (all lanes the same address: one broadcast transaction)
+  const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+  const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+  ScanItem it;
+  it.codes = reinterpret_cast<const float*>(((unsigned long long)(unsigned)a.y << 32) | (unsigned)a.x);
+  it.ids = reinterpret_cast<const long long*>(((unsigned long long)(unsigned)a.w << 32) | (unsigned)a.z);
+  it.len = b.x;
+  it.q = b.y;
+  return it;
+}
+
+// Fast path: d = 128 * D4, query in registers, U vectors in flight per warp.
+template <int SLOTS, int D4, int U>
+__global__ __launch_bounds__(kScanThreads) void ivf_scan_kernel(
+    const float* __restrict__ Q, const ScanItem* __restrict__ items, const int* __restrict__ n_items_ptr,
+    int* __restrict__ queue_counter, int k, float* __restrict__ part_s, long long* __restrict__ part_id) {
+  constexpr int d4 = D4 * 32;  // float4 per vector
+  const int lane = threadIdx.x & 31;
+  const int n_items = *n_items_ptr;
+  int item = 0;
+  if (lane == 0) item = atomicAdd(queue_counter, 1);
+  item = __shfl_sync(kFullMask, item, 0);
+  while (item < n_items) {
+    int next = 0;
+    if (lane == 0) next = atomicAdd(queue_counter, 1);  // latency hidden behind this item's scan
+    const ScanItem it = load_item(items + item);
+    const float4* qp = reinterpret_cast<const float4*>(Q) + (size_t)it.q * d4 + lane;
+    float4 qv[D4];
+#pragma unroll
+    for (int j = 0; j < D4; ++j) qv[j] = __ldg(qp + j * 32);
+
+    WarpTopK<SLOTS> tk;
+    tk.init(k, lane);
+    const float4* cp = reinterpret_cast<const float4*>(it.codes) + lane;
+    int v = 0;
+    for (; v + U <= it.len; v += U) {
+      float4 x[U][D4];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < D4; ++j) x[u][j] = __ldcs(cp + (size_t)(v + u) * d4 + j * 32);
+      float acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[u] = 0.f;
+#pragma unroll
+        for (int j = 0; j < D4; ++j) acc[u] = dot4(x[u][j], qv[j], acc[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] = warp_sum(acc[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (tk.may_enter(acc[u])) {
+          const long long id = __ldg(it.ids + v + u);
+          if (tk.admits(acc[u], id)) tk.insert(acc[u], id);
+        }
+      }
+    }
+    for (; v < it.len; ++v) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < D4; ++j) acc = dot4(__ldcs(cp + (size_t)v * d4 + j * 32), qv[j], acc);
+      acc = warp_sum(acc);
+      if (tk.may_enter(acc)) {
+        const long long id = __ldg(it.ids + v);
+        if (tk.admits(acc, id)) tk.insert(acc, id);
+      }
+    }
+    tk.store(part_s + (size_t)item * k, part_id + (size_t)item * k);
+    item = __shfl_sync(kFullMask, next, 0);
+  }
+}
+
+// Generic path: any d with d % 4 == 0; the query sits in shared memory (one copy per warp).
+template <int SLOTS>
+__global__ __launch_bounds__(kScanThreads) void ivf_scan_generic_kernel(
+    const float* __restrict__ Q, int d, const ScanItem* __restrict__ items,
+    const int* __restrict__ n_items_ptr, int* __restrict__ queue_counter, int k,
+    float* __restrict__ part_s, long long* __restrict__ part_id) {
+  extern __shared__ __align__(16) float sm_q[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d4 = d / 4;
+  float4* myq = reinterpret_cast<float4*>(sm_q) + (size_t)warp * d4;
+  const int n_items = *n_items_ptr;
+  int item = 0;
+  if (lane == 0) item = atomicAdd(queue_counter, 1);
+  item = __shfl_sync(kFullMask, item, 0);
+  while (item < n_items) {
+    int next = 0;
+    if (lane == 0) next = atomicAdd(queue_counter, 1);
+    const ScanItem it = load_item(items + item);
+    const float4* qp = reinterpret_cast<const float4*>(Q) + (size_t)it.q * d4;
+    __syncwarp();
+    for (int j = lane; j < d4; j += 32) myq[j] = __ldg(qp + j);
+    __syncwarp();
+    WarpTopK<SLOTS> tk;
+    tk.init(k, lane);
+    const float4* cp = reinterpret_cast<const float4*>(it.codes);
+    for (int v = 0; v < it.len; ++v) {
+      float acc = 0.f;
+      for (int j = lane; j < d4; j += 32) acc = dot4(__ldcs(cp + (size_t)v * d4 + j), myq[j], acc);
+      acc = warp_sum(acc);
+      if (tk.may_enter(acc)) {
+        const long long id = __ldg(it.ids + v);
+        if (tk.admits(acc, id)) tk.insert(acc, id);
+      }
+    }
+    tk.store(part_s + (size_t)item * k, part_id + (size_t)item * k);
+    item = __shfl_sync(kFullMask, next, 0);
+  }
+}
+
+template <typename Kern>
+int resident_ctas(Kern kern, size_t smem) {
+  int n = 0;
+  ABSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kScanThreads, smem));
+  return n < 1 ? 1 : n;
+}
+
+}  // namespace
+
+void launch_plan(const ListTable& lt, const long long* coarse, int nq, int nprobe, int chunk,
+                 int max_items, ScanItem* items, int* q_begin, int* n_items, int* queue_counter,
+                 unsigned long long* stats, cudaStream_t st) {
+  ABSB_CHECK(nq >= 1 && nq <= kMaxPlanQueries, ABSB_ERR_INVALID, "plan: nq=%d", nq);
+  plan_kernel<<<1, 1024, 0, st>>>(lt, coarse, nq, nprobe, chunk, max_items, items, q_begin, n_items,
+                                  queue_counter, stats);
+  ABSB_CUDA(cudaGetLastError());
+}
+
+void launch_scan(const ScanLaunch& a, cudaStream_t st) {
+  const int sms = a.sm_count;
+  if (a.d == 1024) {
+    constexpr int D4 = 8;
+    ABSB_DISPATCH_SLOTS(a.k, {
+      auto kern = ivf_scan_kernel<SLOTS, D4, kScanUnroll>;
+      const int per_sm = a.ctas_per_sm > 0 ? a.ctas_per_sm : resident_ctas(kern, 0);
+      kern<<<sms * per_sm, kScanThreads, 0, st>>>(a.Q, a.items, a.n_items, a.queue_counter, a.k,
+                                                  a.part_s, a.part_id);
+    });
+  } else {
+    ABSB_CHECK(a.d % 4 == 0, ABSB_ERR_UNSUPPORTED, "IVF scan needs d %% 4 == 0 (d=%d)", a.d);
+    const size_t smem = (size_t)(kScanThreads / 32) * a.d * sizeof(float);
+    ABSB_CHECK(smem <= 200 * 1024, ABSB_ERR_UNSUPPORTED, "d=%d too large for the generic scan", a.d);
+    ABSB_DISPATCH_SLOTS(a.k, {
+      auto kern = ivf_scan_generic_kernel<SLOTS>;
+      if (smem > 48 * 1024)
+        ABSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int per_sm = a.ctas_per_sm > 0 ? a.ctas_per_sm : resident_ctas(kern, smem);
+      kern<<<sms * per_sm, kScanThreads, smem, st>>>(a.Q, a.d, a.items, a.n_items, a.queue_counter,
+                                                     a.k, a.part_s, a.part_id);
+    });
+  }
+  ABSB_CUDA(cudaGetLastError());
+}
+
+}  // namespace absb

@@ -1,0 +1,72 @@
+// ivf_scan.cuh — data layout shared by the inverted-list storage (ivf.cu) and the scan kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace absb {
+
+constexpr int kMaxPlanQueries = 1024;  // queries per plan/scan launch (host splits larger batches)
+constexpr int kScanThreads = 128;      // 4 warps per CTA, every warp an independent worker
+constexpr int kScanUnroll = 2;         // list vectors in flight per warp (2 x 4 KB)
+
+// One unit of scan work: `len` physically contiguous vectors of one list for query `q`.
+struct __align__(16) ScanItem {
+  const float* codes;    // [len, d]
+  const long long* ids;  // [len]
+  int len;
+  int q;
+  long long pad;
+};
+static_assert(sizeof(ScanItem) == 32, "ScanItem must be 32 bytes");
+
+// Device view of the paged inverted lists.
+//   page g lives in slab g >> slab_shift at slot g & (2^slab_shift - 1);
+//   a page holds page_vecs vectors ([page_vecs, d] f32) and page_vecs ids;
+//   list l owns pages pt_pages[pt_off[l] .. pt_off[l] + ceil(list_size[l] / page_vecs)) in order.
+struct ListTable {
+  int nlist;
+  int d;
+  int page_vecs;
+  int slab_shift;
+  const long long* list_size;  // [nlist]
+  const long long* pt_off;     // [nlist + 1]
+  const int* pt_pages;         // [pt_off[nlist]]
+  float* const* code_slabs;    // device array of slab base pointers
+  long long* const* id_slabs;
+};
+
+struct ScanLaunch {
+  const float* Q;  // [nq, d]
+  int d;
+  int k;
+  const ScanItem* items;
+  const int* n_items;
+  int* queue_counter;
+  float* part_s;       // [max_items, k]
+  long long* part_id;  // [max_items, k]
+  int sm_count;
+  int ctas_per_sm;  // <= 0: occupancy query
+};
+
+void launch_plan(const ListTable& lt, const long long* coarse, int nq, int nprobe, int chunk,
+                 int max_items, ScanItem* items, int* q_begin, int* n_items, int* queue_counter,
+                 unsigned long long* stats, cudaStream_t st);
+void launch_scan(const ScanLaunch& a, cudaStream_t st);
+
+// dense.cu
+void gemm_nt_f32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                 int ldc, cudaStream_t st);
+void select_rows(const float* S, int64_t ld, int64_t nrows, int ncols, long long id_offset, int k,
+                 float* out_s, long long* out_id, int64_t out_ld, bool finalize, cudaStream_t st);
+void merge_partials(int nq, int k, const int* q_begin, const float* part_s, const long long* part_id,
+                    float* D, long long* I, cudaStream_t st);
+void merge_shards(int world, int64_t nq, int k, const float* D_all, const long long* I_all,
+                  int64_t d_stride_bytes, int64_t i_stride_bytes, float* D, long long* I, cudaStream_t st);
+
+// synth.cu
+void synth_fill(int kind, uint64_t seed, int64_t row0, int64_t n, int d, int nlist,
+                int64_t corpus_rows, float* out, cudaStream_t st);
+void synth_cluster(uint64_t seed, int64_t row0, int64_t n, int nlist, long long* out, cudaStream_t st);
+
+}  // namespace absb

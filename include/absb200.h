@@ -1,0 +1,237 @@
+/*
+ * absb200.h — C ABI of libabsb200.so, the B200-native (sm_100a) implementation of the
+ * abstracts-search hot path: stella_en_1.5B_v5 bulk embedding + faiss-style IVF/Flat
+ * inner-product top-k search.
+ *
+ * The reference (colonelwatch/abstracts-search) reaches this path only through the Python
+ * surfaces `SentenceTransformer.encode()` and `faiss.Index.{train,add,search}`:
+ *   - bulk encode          /root/reference/Makefile:65   (sidecar-search build -b 32)
+ *   - Index.train          /root/reference/Makefile:38-39 (sidecar-search index train, -c 65536 README.md:60)
+ *   - Index.add            /root/reference/Makefile:24-25 (sidecar-search index fill)
+ *   - Index.search         /root/reference/Makefile:31-32 (sidecar-search index tune), README.md:16,28 (app.py)
+ * Every entry point below names the reference interface it stands in for.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only. Every function returns 0 (ABSB_OK) or a negative
+ *     error code; the message is available from absb_last_error() (thread-local).
+ *   - No exceptions cross the boundary. The caller owns all host buffers; they are borrowed for
+ *     the duration of the call. Opaque handles own device memory.
+ *   - Functions without a suffix take HOST pointers (numpy arrays in the Python binding) and do the
+ *     host<->device copies themselves. `_dev` variants take DEVICE pointers on the handle's device
+ *     plus a cudaStream_t passed as void* (NULL = the CUDA legacy default stream, as in any CUDA
+ *     API) and do not synchronise unless stated.
+ *   - One handle per host thread (thread-compatible, no hidden globals besides the error string).
+ *   - There is NO CPU fallback: without a usable sm_100 device the create calls fail.
+ */
+#ifndef ABSB200_H
+#define ABSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABSB_OK 0
+#define ABSB_ERR_INVALID (-1)     /* bad argument (shape, dtype contract, k too large, ...)   */
+#define ABSB_ERR_CUDA (-2)        /* CUDA runtime / driver failure                              */
+#define ABSB_ERR_STATE (-3)       /* index not trained, encoder weights missing, ...            */
+#define ABSB_ERR_UNSUPPORTED (-4) /* valid in faiss but outside this path (e.g. METRIC_L2)      */
+#define ABSB_ERR_OOM (-5)         /* device allocation failed                                   */
+
+/* faiss MetricType values (faiss/MetricType.h); only inner product is on the path. */
+#define ABSB_METRIC_INNER_PRODUCT 0
+#define ABSB_METRIC_L2 1
+
+/* Largest k / nprobe the fused warp top-k supports. */
+#define ABSB_MAX_K 256
+
+typedef struct absb_ivf_s* absb_ivf_t;
+typedef struct absb_flat_s* absb_flat_t;
+typedef struct absb_enc_s* absb_enc_t;
+
+/* ---------------------------------------------------------------- library ------------------ */
+int absb_version(void);
+const char* absb_last_error(void);
+/* Number of usable CUDA devices; fails (ABSB_ERR_CUDA) when there is no driver/device. */
+int absb_device_count(int* count);
+/* Name + SM count + compute capability of a device (buffer of at least 128 bytes). */
+int absb_device_info(int device, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- synthetic corpora -------- */
+/* Counter-based integer-lattice generator shared bit-for-bit with oracle/synth.py.
+ * kind 0: corpus rows   x[r] = (mu[c(r)] + eps(r)) / 128
+ * kind 1: centroids     c[j] =  mu[j] / 128           (row index = list number)
+ * kind 2: queries       q[i] = clamp(mu[c(s)] + eps(s) + delta(i)) / 128, s = source row of query i
+ * out is a DEVICE pointer to [n, d] float32. */
+int absb_synth_fill_dev(int kind, uint64_t seed, int64_t row0, int64_t n, int d, int nlist,
+                        int64_t corpus_rows, float* out_dev, void* stream);
+/* cluster id c(r) of corpus rows [row0,row0+n) -> DEVICE int64 (feeds add_preassigned) */
+int absb_synth_cluster_dev(uint64_t seed, int64_t row0, int64_t n, int nlist, int64_t* out_dev,
+                           void* stream);
+
+/* ---------------------------------------------------------------- IndexFlatIP -------------- */
+/* faiss.IndexFlatIP(d): exact inner-product search; the IVF coarse quantiser and config 1. */
+int absb_flat_create(int d, int metric, int device, absb_flat_t* out);
+int absb_flat_destroy(absb_flat_t h);
+int absb_flat_reset(absb_flat_t h);
+int absb_flat_ntotal(absb_flat_t h, int64_t* ntotal);
+/* Index.add(x): x [n,d] float32 C-contiguous. */
+int absb_flat_add(absb_flat_t h, int64_t n, const float* x);
+int absb_flat_add_dev(absb_flat_t h, int64_t n, const float* x_dev, void* stream);
+/* Index.search(x,k) -> D [n,k] f32 descending, I [n,k] i64; missing: I=-1, D=-FLT_MAX. */
+int absb_flat_search(absb_flat_t h, int64_t n, const float* q, int k, float* D, int64_t* I);
+int absb_flat_search_dev(absb_flat_t h, int64_t n, const float* q_dev, int k, float* D_dev,
+                         int64_t* I_dev, void* stream);
+/* Index.reconstruct_n(i0, n) */
+int absb_flat_reconstruct(absb_flat_t h, int64_t i0, int64_t n, float* x);
+
+/* ---------------------------------------------------------------- IndexIVFFlat ------------- */
+/* faiss.index_factory(d, "IVF<nlist>,Flat", METRIC_INNER_PRODUCT)  (SURVEY §8a a4). */
+int absb_ivf_create(int d, int nlist, int metric, int device, absb_ivf_t* out);
+int absb_ivf_destroy(absb_ivf_t h);
+/* Index.reset(): drop inverted lists, keep centroids. */
+int absb_ivf_reset(absb_ivf_t h);
+int absb_ivf_ntotal(absb_ivf_t h, int64_t* ntotal);
+int absb_ivf_is_trained(absb_ivf_t h, int* trained);
+
+/* faiss ClusteringParameters (index.cp): niter=10, max_points_per_centroid=256,
+ * min_points_per_centroid=39, seed=1234 by default. */
+int absb_ivf_set_clustering(absb_ivf_t h, int niter, int max_points_per_centroid,
+                            int min_points_per_centroid, int64_t seed);
+/* Index.train(x)  (SURVEY §8a a5): subsample, random-row init, niter Lloyd iterations with
+ * arg-max-IP assignment, mean update, empty-cluster split. x is a HOST pointer [n,d]. */
+int absb_ivf_train(absb_ivf_t h, int64_t n, const float* x);
+/* Same with x already on the device (the sample gather happens on the device). */
+int absb_ivf_train_dev(absb_ivf_t h, int64_t n, const float* x_dev, void* stream);
+/* quantizer.add(centroids) / quantizer.reconstruct_n: import / export the coarse centroids
+ * [nlist,d] (host). Importing marks the index trained. */
+int absb_ivf_set_centroids(absb_ivf_t h, const float* centroids);
+int absb_ivf_get_centroids(absb_ivf_t h, float* centroids);
+int absb_ivf_set_centroids_dev(absb_ivf_t h, const float* centroids_dev, void* stream);
+
+/* Index.add(x) (ids == NULL: id = ntotal + i) / Index.add_with_ids(x, ids)  (SURVEY §8a a6). */
+int absb_ivf_add(absb_ivf_t h, int64_t n, const float* x, const int64_t* ids);
+int absb_ivf_add_dev(absb_ivf_t h, int64_t n, const float* x_dev, const int64_t* ids_dev,
+                     void* stream);
+/* IndexIVF::add_core(n, x, xids, precomputed list numbers): list_ids [n] int64, -1 = skip row. */
+int absb_ivf_add_preassigned(absb_ivf_t h, int64_t n, const float* x, const int64_t* ids,
+                             const int64_t* list_ids);
+int absb_ivf_add_preassigned_dev(absb_ivf_t h, int64_t n, const float* x_dev,
+                                 const int64_t* ids_dev, const int64_t* list_ids_dev,
+                                 void* stream);
+/* Merge all add() segments into one contiguous list arena (optional; halves nothing in the
+ * result, only the number of scan work items). Needs room for a second copy of the codes. */
+int absb_ivf_compact(absb_ivf_t h);
+
+/* quantizer.search(x, nprobe): Dc [n,nprobe] f32, Ic [n,nprobe] i64, best first. */
+int absb_ivf_coarse(absb_ivf_t h, int64_t n, const float* q, int nprobe, float* Dc, int64_t* Ic);
+int absb_ivf_coarse_dev(absb_ivf_t h, int64_t n, const float* q_dev, int nprobe, float* Dc_dev,
+                        int64_t* Ic_dev, void* stream);
+/* quantizer.assign(x): list number per row. */
+int absb_ivf_assign(absb_ivf_t h, int64_t n, const float* x, int64_t* list_ids);
+
+/* Index.search(x, k) with IndexIVF.nprobe = nprobe  (SURVEY §8a a7, a8). */
+int absb_ivf_search(absb_ivf_t h, int64_t n, const float* q, int k, int nprobe, float* D,
+                    int64_t* I);
+int absb_ivf_search_dev(absb_ivf_t h, int64_t n, const float* q_dev, int k, int nprobe,
+                        float* D_dev, int64_t* I_dev, void* stream);
+/* IndexIVF::search_preassigned(n, x, k, assign, ...): coarse ids [n,nprobe] int64 (-1 = none). */
+int absb_ivf_search_preassigned(absb_ivf_t h, int64_t n, const float* q, int k, int nprobe,
+                                const int64_t* coarse_ids, float* D, int64_t* I);
+int absb_ivf_search_preassigned_dev(absb_ivf_t h, int64_t n, const float* q_dev, int k,
+                                    int nprobe, const int64_t* coarse_ids_dev, float* D_dev,
+                                    int64_t* I_dev, void* stream);
+
+/* invlists.list_size(l) for all lists -> sizes [nlist] int64 (host). */
+int absb_ivf_list_sizes(absb_ivf_t h, int64_t* sizes);
+/* invlists.get_codes(l)/get_ids(l): codes [list_size,d] f32 and ids [list_size] i64 in insertion
+ * order (host buffers sized from absb_ivf_list_sizes; either may be NULL). */
+int absb_ivf_get_list(absb_ivf_t h, int64_t list_no, float* codes, int64_t* ids);
+
+/* Sharding by inverted list: this handle keeps only lists l with
+ * l % world == rank; add() silently drops rows of other lists but ntotal still counts only kept
+ * rows. Must be called before the first add. Coarse quantisation stays replicated. */
+int absb_ivf_set_shard(absb_ivf_t h, int rank, int world);
+/* Merge per-shard partial results (scores f32 / ids i64 [n,k] per rank, DEVICE) into the final
+ * [n,k] with the same (score desc, id asc) order as a single-shard search.  Rank w's arrays start
+ * at D_all_dev + w*rank_stride_bytes and I_all_dev + w*rank_stride_bytes — the layout of ONE
+ * all-gather of a packed per-rank record {I [n,k] i64, D [n,k] f32}.  rank_stride_bytes == 0 means
+ * two dense [world, n, k] arrays. */
+int absb_merge_shards_dev(int device, int world, int64_t n, int k, const float* D_all_dev,
+                          const int64_t* I_all_dev, int64_t rank_stride_bytes, float* D_dev,
+                          int64_t* I_dev, void* stream);
+
+/* Tunables (chunk = vectors per scan work item; coarse_impl 0 = fp32 SIMT, 1 = tcgen05
+ * split-bf16). Values < 0 leave a setting unchanged. */
+int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int scan_ctas_per_sm);
+/* Statistics of the most recent search call on this handle: number of list vectors scanned,
+ * algorithmic bytes (vectors * (4d+8)), number of scan work items, number of kernel launches. */
+int absb_ivf_last_stats(absb_ivf_t h, int64_t* vectors_scanned, int64_t* bytes_scanned,
+                        int64_t* work_items, int64_t* launches);
+/* Replays ONLY the fine-scan kernel of the most recent *_dev search (same work items) `iters`
+ * times on `stream` and returns the mean duration in ms measured with CUDA events on that
+ * stream — used by bench.py for roofline.achieved. */
+int absb_ivf_time_scan(absb_ivf_t h, int iters, void* stream, float* ms_mean);
+
+/* ---------------------------------------------------------------- encoder ------------------ */
+/* stella_en_1.5B_v5 = Qwen2-1.5B backbone (bidirectional) -> mean pool -> Dense 1536->1024 ->
+ * optional L2 normalise; the arithmetic behind SentenceTransformer.encode(). */
+typedef struct absb_enc_config {
+  int32_t vocab_size;        /* 151646 */
+  int32_t hidden_size;       /* 1536   */
+  int32_t num_layers;        /* 28     */
+  int32_t num_heads;         /* 12     */
+  int32_t num_kv_heads;      /* 2      */
+  int32_t head_dim;          /* 128    */
+  int32_t intermediate_size; /* 8960   */
+  int32_t embed_dim;         /* 1024 (Dense out_features) */
+  int32_t max_seq_len;       /* 512    */
+  int32_t causal;            /* 0 = bidirectional (stella), 1 = stock Qwen2 causal */
+  float rms_eps;             /* 1e-6   */
+  float rope_theta;          /* 1e6    */
+} absb_enc_config;
+
+int absb_enc_create(const absb_enc_config* cfg, int device, absb_enc_t* out);
+int absb_enc_destroy(absb_enc_t e);
+/* Load one parameter by its Hugging Face name ("embed_tokens.weight",
+ * "layers.3.self_attn.q_proj.weight", "norm.weight", "dense.weight", "dense.bias", ...).
+ * data is a HOST pointer; dtype 0 = float32, 1 = bfloat16 (raw uint16). Weights are stored bf16
+ * on the device (norm weights and biases fp32). */
+int absb_enc_load_weight(absb_enc_t e, const char* name, const void* data, int dtype,
+                         const int64_t* shape, int ndim);
+/* Initialise all weights on the device from the counter-based generator (normal(0, std)) —
+ * the random-init model of the true architecture used offline (no checkpoint available). */
+int absb_enc_init_random(absb_enc_t e, uint64_t seed, float std);
+/* Read a parameter back (fp32) for the oracle to load the very same weights. */
+int absb_enc_get_weight(absb_enc_t e, const char* name, float* out, int64_t numel);
+/* Forward: input_ids [B,S] int64, attention_mask [B,S] int32 (1 = token, 0 = pad; right padding)
+ * -> out [B, embed_dim] float32 (L2-normalised when normalize != 0). Host pointers. */
+int absb_enc_forward(absb_enc_t e, int B, int S, const int64_t* input_ids,
+                     const int32_t* attention_mask, int normalize, float* out);
+int absb_enc_forward_dev(absb_enc_t e, int B, int S, const int64_t* input_ids_dev,
+                         const int32_t* attention_mask_dev, int normalize, float* out_dev,
+                         void* stream);
+/* Debug / parity taps: last_hidden_state [B,S,hidden] fp32 of the most recent forward. */
+int absb_enc_last_hidden(absb_enc_t e, float* out, int64_t numel);
+/* FLOP count and kernel launches of the most recent forward. */
+int absb_enc_last_stats(absb_enc_t e, double* flops, int64_t* launches);
+/* Per-phase device timing with CUDA events recorded on the forward's own stream around every
+ * kernel: on = 1 start, 0 stop, 2 start with counters reset.  get_profile synchronises and returns
+ * the accumulated milliseconds of the tcgen05 GEMM launches (with their FLOPs), of the attention
+ * kernel and of everything else, plus the number of forwards covered — bench.py's roofline.achieved
+ * for the GEMM comes from here. */
+int absb_enc_set_profile(absb_enc_t e, int on);
+int absb_enc_get_profile(absb_enc_t e, double* gemm_ms, double* gemm_flops, double* attention_ms,
+                         double* other_ms, int64_t* forwards);
+
+/* Stand-alone GEMM entry used by tests and the micro-benchmark: C[M,N] (fp32) = A[M,K] * B[N,K]^T
+ * with bf16 operands on tcgen05 (DEVICE pointers; K % 64 == 0). */
+int absb_gemm_bf16_dev(int device, int M, int N, int K, const void* A_dev, const void* B_dev,
+                       float* C_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABSB200_H */

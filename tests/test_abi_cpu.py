@@ -1,0 +1,154 @@
+"""CPU tests of the C-ABI boundary and the Python host logic (no compute: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_pkg
+
+
+@pytest.fixture(scope="module")
+def P():
+    p = load_pkg()
+    if not os.path.exists(p.LIB_PATH):
+        p.build()
+    return p
+
+
+def test_library_exports_every_declared_symbol(P):
+    names = P.header_functions()
+    assert len(names) >= 50
+    handle = ctypes.CDLL(P.LIB_PATH)
+    missing = [n for n in names if not hasattr(handle, n)]
+    assert not missing, f"declared in include/absb200.h but not exported: {missing}"
+    # and the ctypes table covers the header exactly
+    from importlib import import_module
+
+    sigs = import_module("abstracts-search_b200._lib")._SIGS
+    assert sorted(sigs) == names
+
+
+def test_header_cites_reference_interfaces():
+    src = open(os.path.join(ROOT, "include", "absb200.h")).read()
+    assert "extern \"C\"" in src
+    assert len(re.findall(r"/root/reference/(Makefile|README\.md):\d+", src)) >= 4
+    assert "torch" not in src.lower() and "at::" not in src
+
+
+def test_version_and_error_string(P):
+    L = P.lib()
+    assert L.absb_version() == 100
+    n = ctypes.c_int(-7)
+    rc = L.absb_device_count(ctypes.byref(n))
+    import torch
+
+    if not torch.cuda.is_available():
+        # no device: the library reports a CUDA error instead of pretending
+        assert rc != 0 and len(L.absb_last_error()) > 0
+
+
+def test_product_path_fails_loudly_without_gpu(P):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        P.index_factory(64, "IVF16,Flat", P.METRIC_INNER_PRODUCT)
+    with pytest.raises(RuntimeError):
+        P.IndexFlatIP(64)
+    with pytest.raises(RuntimeError):
+        P.Encoder(config=P.EncoderConfig(vocab_size=100, hidden_size=256, num_layers=1, num_heads=2, num_kv_heads=1,
+                                         intermediate_size=256, embed_dim=64), random_init_seed=0)
+
+
+def test_no_oracle_import_in_product():
+    pk = os.path.join(ROOT, "abstracts-search_b200")
+    for dirpath, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                s = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", s, flags=re.M), f
+                assert "liboracle" not in s and "oracle/" not in s.replace("oracle/synth.py", "").replace(
+                    "oracle/ivf_oracle.c", ""), f
+
+
+def test_index_factory_parsing(P):
+    with pytest.raises(RuntimeError):
+        P.index_factory(64, "IVF16,Flat", P.METRIC_L2)
+    with pytest.raises(RuntimeError):
+        P.index_factory(64, "IVF16,PQ8", P.METRIC_INNER_PRODUCT)
+    with pytest.raises(RuntimeError):
+        P.index_factory(64, "HNSW32", P.METRIC_INNER_PRODUCT)
+
+
+def test_numpy_contract_helpers(P):
+    from importlib import import_module
+
+    ix = import_module("abstracts-search_b200.index")
+    x = ix._as_f32_matrix(np.arange(12, dtype=np.float64).reshape(3, 4), 4)
+    assert x.dtype == np.float32 and x.flags["C_CONTIGUOUS"]
+    x = ix._as_f32_matrix(np.asfortranarray(np.ones((3, 4), dtype=np.float32)), 4)
+    assert x.flags["C_CONTIGUOUS"]
+    with pytest.raises(AssertionError):
+        ix._as_f32_matrix(np.ones((3, 5), dtype=np.float32), 4)
+    with pytest.raises(ValueError):
+        ix._as_f32_matrix(np.ones(4, dtype=np.float32), 4)
+    with pytest.raises(AssertionError):
+        ix._as_i64_vector(np.arange(4), 3, x)
+
+
+def test_merge_partials_host(P):
+    rng = np.random.default_rng(0)
+    world, n, k = 3, 5, 4
+    D = -np.sort(-rng.standard_normal((world, n, k)).astype(np.float32), axis=2)
+    I = rng.permutation(world * n * k).reshape(world, n, k).astype(np.int64)
+    D[1, 2, 2:] = -3.4028234663852886e38
+    I[1, 2, 2:] = -1
+    Dm, Im = P.merge_partials_host(D, I, k)
+    for q in range(n):
+        cand = [(-(D[w, q, j]), I[w, q, j]) for w in range(world) for j in range(k) if I[w, q, j] >= 0]
+        cand.sort()
+        assert [c[1] for c in cand[:k]] == Im[q].tolist()
+    # exact ties resolve by id
+    D2 = np.zeros((2, 1, 2), dtype=np.float32)
+    I2 = np.array([[[9, 4]], [[7, 1]]], dtype=np.int64)
+    assert P.merge_partials_host(D2, I2, 3)[1][0].tolist() == [1, 4, 7]
+
+
+def test_encoder_host_logic(P):
+    cfg = P.EncoderConfig()
+    shapes = cfg.param_shapes()
+    n_params = sum(int(np.prod(s)) for n, s in shapes.items() if not n.startswith("dense."))
+    assert n_params == 1_543_268_864  # Qwen2-1.5B backbone incl. embeddings
+    assert abs(cfg.flops_per_token_linear() - 2.6204e9) / 2.6204e9 < 1e-3
+    tok = import_tok(P)
+    out = tok(["a b c", "hello, world"], max_length=3)
+    assert out["input_ids"].shape == (2, 3) and out["attention_mask"].sum() == 6
+    out = tok(["a", "b c d"])
+    assert out["attention_mask"].tolist() == [[1, 0, 0], [1, 1, 1]]
+
+
+def import_tok(P):
+    from importlib import import_module
+
+    return import_module("abstracts-search_b200.encoder").HashTokenizer(1000)
+
+
+def test_safetensors_reader(tmp_path, P):
+    import json
+    import struct
+    from importlib import import_module
+
+    enc = import_module("abstracts-search_b200.encoder")
+    a = np.arange(6, dtype=np.float32).reshape(2, 3)
+    b = np.array([0x3F80, 0x4000], dtype=np.uint16)  # bf16 1.0, 2.0
+    header = {"w": {"dtype": "F32", "shape": [2, 3], "data_offsets": [0, 24]},
+              "v": {"dtype": "BF16", "shape": [2], "data_offsets": [24, 28]}, "__metadata__": {"format": "pt"}}
+    hj = json.dumps(header).encode()
+    path = tmp_path / "m.safetensors"
+    path.write_bytes(struct.pack("<Q", len(hj)) + hj + a.tobytes() + b.tobytes())
+    t = enc.read_safetensors(str(path))
+    assert np.array_equal(t["w"][0], a) and t["w"][1] == "F32"
+    assert np.array_equal(t["v"][0], b) and t["v"][1] == "BF16"

@@ -1,0 +1,172 @@
+"""GPU parity tests of the encoder half: tcgen05 GEMM vs torch fp32, encoder forward vs the fp32
+CPU oracle.  Tolerance (BASELINE.json north_star): embedding cosine within 1e-3 of the fp32
+reference; the GEMM itself is checked to bf16-input / fp32-accumulate accuracy."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import encoder as oenc
+from tiny_cfg import TINY, TinyCfg
+
+pytestmark = pytest.mark.gpu
+COS_TOL = 1e-3
+
+
+def _cfg(P, base):
+    return P.EncoderConfig(vocab_size=base.vocab_size, hidden_size=base.hidden_size, num_layers=base.num_layers,
+                           num_heads=base.num_heads, num_kv_heads=base.num_kv_heads, head_dim=base.head_dim,
+                           intermediate_size=base.intermediate_size, embed_dim=base.embed_dim,
+                           max_seq_len=base.max_seq_len, causal=base.causal, rms_eps=base.rms_eps,
+                           rope_theta=base.rope_theta)
+
+
+def _loaded(P, base, sd):
+    enc = P.Encoder(config=_cfg(P, base))
+    for name, arr in sd.items():
+        enc.load_weight(name, arr)
+    return enc
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1, 32, 64), (300, 512, 192), (129, 1536, 1536),
+                                    (1000, 2048, 1536), (2048, 1536, 8960), (77, 96, 72)])
+def test_tcgen05_gemm_matches_torch(gpu_pkg, M, N, K):
+    import torch
+    from importlib import import_module
+
+    enc = import_module("abstracts-search_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    B = torch.randn((N, K), device="cuda", generator=g).to(torch.bfloat16)
+    C = enc.gemm_bf16(A, B)
+    ref = A.float() @ B.float().T
+    torch.cuda.synchronize()
+    err = (C - ref).abs().max().item()
+    # fp32 accumulation of exact bf16 products: error ~ K * 2^-24 * |a||b|
+    assert err < 2e-3 * max(1.0, K / 256), (M, N, K, err)
+
+
+def test_tcgen05_gemm_integer_inputs_are_exact(gpu_pkg):
+    import torch
+    from importlib import import_module
+
+    enc = import_module("abstracts-search_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randint(-8, 9, (515, 1024), device="cuda", generator=g).to(torch.bfloat16)
+    B = torch.randint(-8, 9, (640, 1024), device="cuda", generator=g).to(torch.bfloat16)
+    C = enc.gemm_bf16(A, B)
+    ref = (A.double() @ B.double().T).float()
+    assert torch.equal(C, ref)
+
+
+def test_weight_roundtrip(gpu_pkg):
+    sd = oenc.random_state_dict(TINY, seed=0, std=0.05)
+    enc = _loaded(gpu_pkg, TINY, sd)
+    for name in ("embed_tokens.weight", "layers.1.mlp.gate_proj.weight", "layers.1.mlp.up_proj.weight",
+                 "layers.0.self_attn.k_proj.weight", "layers.0.self_attn.v_proj.bias", "layers.1.mlp.down_proj.weight",
+                 "norm.weight", "dense.weight", "dense.bias", "layers.0.self_attn.o_proj.weight"):
+        assert np.array_equal(enc.get_weight(name), sd[name]), name
+    with pytest.raises(RuntimeError):
+        enc.load_weight("layers.9.mlp.up_proj.weight", sd["layers.1.mlp.up_proj.weight"])
+    with pytest.raises(RuntimeError):
+        enc.load_weight("norm.weight", np.zeros(7, np.float32))
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_tiny_encoder_matches_oracle(gpu_pkg, causal):
+    g = golden("encoder_tiny.npz")
+    ids, mask = g["ids"], g["mask"]
+    base = TinyCfg(causal=causal)
+    sd = oenc.random_state_dict(base, seed=0, std=0.05)
+    enc = _loaded(gpu_pkg, base, sd)
+    emb = enc.encode_tokens(ids, mask, normalize_embeddings=True)
+    ref, hid = oenc.forward_plain(base, sd, ids, mask, normalize=True, return_hidden=True)
+    cos = oenc.cosine_rows(emb, ref)
+    assert (1 - cos).max() < COS_TOL, cos
+    if not causal:
+        assert (1 - oenc.cosine_rows(emb, g["emb"])).max() < COS_TOL
+    h = enc.last_hidden_state(*ids.shape)
+    m = mask.astype(bool)
+    rel = np.abs(h - hid)[m].max() / np.abs(hid)[m].max()
+    assert rel < 3e-2, rel
+    assert np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)
+    raw = enc.encode_tokens(ids, mask, normalize_embeddings=False)
+    assert (1 - oenc.cosine_rows(raw, emb)).max() < 1e-6
+
+
+def test_device_tensor_entry_and_padding_invariance(gpu_pkg):
+    import torch
+
+    g = golden("encoder_tiny.npz")
+    ids, mask = g["ids"], g["mask"]
+    sd = oenc.random_state_dict(TINY, seed=0, std=0.05)
+    enc = _loaded(gpu_pkg, TINY, sd)
+    a = enc.encode_tokens(ids, mask, True)
+    b = enc.encode_tokens(torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda(), True).cpu().numpy()
+    assert np.array_equal(a, b)
+    n2 = int(mask[2].sum())
+    alone = enc.encode_tokens(ids[2:3, :n2], mask[2:3, :n2], True)
+    assert (1 - oenc.cosine_rows(alone, a[2:3])).max() < 1e-4
+    # long sequences: several key tiles, ragged lengths
+    rng = np.random.default_rng(5)
+    ids = rng.integers(0, TINY.vocab_size, (3, 300)).astype(np.int64)
+    mask = np.ones((3, 300), dtype=np.int64)
+    mask[0, 257:] = 0
+    mask[1, 64:] = 0
+    emb = enc.encode_tokens(ids, mask, True)
+    ref = oenc.forward_plain(TINY, sd, ids, mask, normalize=True)
+    assert (1 - oenc.cosine_rows(emb, ref)).max() < COS_TOL
+    with pytest.raises(RuntimeError):
+        enc.encode_tokens(np.zeros((1, 513), np.int64))
+
+
+def test_random_init_export_matches_oracle(gpu_pkg):
+    P = gpu_pkg
+    enc = P.Encoder(config=_cfg(P, TINY), random_init_seed=3, random_init_std=0.05)
+    sd = enc.state_dict()
+    assert abs(sd["layers.0.mlp.up_proj.weight"].std() - 0.05) < 5e-3
+    assert abs(sd["norm.weight"].mean() - 1.0) < 2e-2
+    rng = np.random.default_rng(1)
+    ids = rng.integers(0, TINY.vocab_size, (4, 32)).astype(np.int64)
+    emb = enc.encode_tokens(ids, None, True)
+    ref = oenc.forward_plain(TINY, sd, ids, np.ones_like(ids), normalize=True)
+    assert (1 - oenc.cosine_rows(emb, ref)).max() < COS_TOL
+
+
+def test_full_size_stella_architecture_matches_oracle(gpu_pkg):
+    """The true 1.5B architecture (28 layers, 1536 hidden, 12/2 heads, FFN 8960, vocab 151646) with
+    seeded random weights exported to the fp32 CPU oracle: cosine within 1e-3."""
+    P = gpu_pkg
+    enc = P.Encoder(config=P.STELLA_1_5B, random_init_seed=0)
+    sd = enc.state_dict()
+    rng = np.random.default_rng(2)
+    ids = rng.integers(0, P.STELLA_1_5B.vocab_size, (3, 40)).astype(np.int64)
+    mask = np.ones_like(ids)
+    mask[1, 25:] = 0
+    emb = enc.encode_tokens(ids, mask, True)
+    ref = oenc.forward_plain(P.STELLA_1_5B, sd, ids, mask, normalize=True)
+    cos = oenc.cosine_rows(emb, ref)
+    assert (1 - cos).max() < COS_TOL, cos
+    st = enc.last_stats()
+    expect = 3 * 40 * P.STELLA_1_5B.flops_per_token_linear()
+    assert abs(st["flops"] - expect) / expect < 0.05
+
+
+def test_sentence_transformer_surface(gpu_pkg):
+    P = gpu_pkg
+    model = P.SentenceTransformer(config=_cfg(P, TINY), random_init_seed=1, random_init_std=0.05)
+    assert model.get_sentence_embedding_dimension() == TINY.embed_dim and model.max_seq_length == 512
+    docs = ["graph neural networks for molecules", "a", "the quick brown fox jumps over the lazy dog " * 3,
+            "inverted file index", "approximate nearest neighbour search on GPUs"]
+    e = model.encode(docs, batch_size=2, normalize_embeddings=True)
+    assert e.shape == (5, TINY.embed_dim) and e.dtype == np.float32
+    for i, d in enumerate(docs):  # order restored after the length sort, batch composition irrelevant
+        one = model.encode(d, normalize_embeddings=True)
+        assert one.shape == (TINY.embed_dim,)
+        assert 1 - float(one @ e[i]) < 1e-4
+    qp = model.encode("neural search", prompt_name="s2p_query")
+    qm = model.encode(model.prompts["s2p_query"] + "neural search")
+    assert np.array_equal(qp, qm)
+    with pytest.raises(ValueError):
+        model.encode("x", prompt_name="nope")
+    t = model.encode(docs[:2], convert_to_tensor=True)
+    assert t.is_cuda and tuple(t.shape) == (2, TINY.embed_dim)

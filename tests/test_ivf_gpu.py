@@ -1,0 +1,337 @@
+"""GPU parity tests of the index half of the path: CUDA (through the C-ABI / Python surface) vs
+the CPU oracle, on seeded inputs, golden fixtures and size-independent properties.
+Integer/index results must be bit-exact; fp32 scores are bit-exact on the exact-lattice corpus and
+within 1e-5 absolute on gaussian data (tolerance stated per test)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import ivf as oivf
+from oracle import synth as osynth
+
+pytestmark = pytest.mark.gpu
+FLT_MAX = np.float32(3.4028234663852886e38)
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+# ------------------------------------------------------------------ generator -----------------
+def test_device_generator_matches_oracle_bit_for_bit(gpu_pkg):
+    P = gpu_pkg
+    for d, nlist, n, row0 in [(1024, 128, 300, 0), (64, 16, 1000, 12345), (256, 65536, 200, 10**9)]:
+        x = P.synth.corpus(1234, row0, n, d, nlist).cpu().numpy()
+        assert np.array_equal(x, osynth.corpus(1234, row0, n, d, nlist))
+        c = P.synth.cluster_of(1234, row0, n, nlist).cpu().numpy()
+        assert np.array_equal(c, osynth.cluster_of(1234, np.arange(row0, row0 + n), nlist))
+    c = P.synth.centroids(1234, 128, 1024).cpu().numpy()
+    assert np.array_equal(c, osynth.centroids(1234, 128, 1024))
+    q = P.synth.queries(1234, 5, 77, 1024, 128, 8192).cpu().numpy()
+    assert np.array_equal(q, osynth.queries(1234, 5, 77, 1024, 128, 8192))
+
+
+# ------------------------------------------------------------------ golden: lattice ------------
+@pytest.fixture(scope="module")
+def lattice(gpu_pkg):
+    g = golden("ivf_lattice_d1024.npz")
+    d, nlist, n, nq = int(g["d"]), int(g["nlist"]), int(g["n"]), int(g["nq"])
+    seed = int(g["seed"])
+    x = osynth.corpus(seed, 0, n, d, nlist)
+    q = osynth.queries(seed, 0, nq, d, nlist, n)
+    c = osynth.centroids(seed, nlist, d)
+    return g, x, q, c
+
+
+def test_flat_search_matches_golden(gpu_pkg, lattice):
+    g, x, q, _ = lattice
+    ix = gpu_pkg.IndexFlatIP(x.shape[1])
+    ix.add(x[:5000])
+    ix.add(x[5000:])
+    assert ix.ntotal == x.shape[0]
+    D, I = ix.search(q, int(g["k"]))
+    assert np.array_equal(I, g["If"]) and np.array_equal(D, g["Df"])
+    t = _torch()
+    Dd, Id = ix.search(t.from_numpy(q).cuda(), int(g["k"]))
+    assert np.array_equal(Id.cpu().numpy(), g["If"]) and np.array_equal(Dd.cpu().numpy(), g["Df"])
+    assert np.array_equal(ix.reconstruct_n(10, 3), x[10:13])
+
+
+@pytest.mark.parametrize("coarse_impl", [0, 1])
+def test_ivf_matches_golden_lattice(gpu_pkg, lattice, coarse_impl):
+    g, x, q, c = lattice
+    d, nlist, nprobe, k = int(g["d"]), int(g["nlist"]), int(g["nprobe"]), int(g["k"])
+    ix = gpu_pkg.index_factory(d, f"IVF{nlist},Flat", gpu_pkg.METRIC_INNER_PRODUCT)
+    ix.set_tunables(coarse_impl=coarse_impl)
+    assert not ix.is_trained
+    ix.set_centroids(c)
+    assert ix.is_trained and ix.ntotal == 0
+    ix.add(x)
+    assert ix.ntotal == x.shape[0]
+    assert np.array_equal(ix.list_sizes(), g["sizes"])
+    assert np.array_equal(ix.assign(x), g["assign"])
+    Dc, Ic = ix.coarse(q, nprobe)
+    assert np.array_equal(Ic, g["Ic"]) and np.array_equal(Dc, g["Dc"])
+    ix.nprobe = nprobe
+    D, I = ix.search(q, k)
+    assert np.array_equal(I, g["I"]), "top-k ids differ from the oracle"
+    assert np.array_equal(D, g["D"]), "lattice scores must be bit-exact"
+    # device-tensor entry, SearchParametersIVF, search_preassigned
+    t = _torch()
+    Dd, Id = ix.search(t.from_numpy(q).cuda(), k, params=gpu_pkg.SearchParametersIVF(nprobe=nprobe))
+    assert np.array_equal(Id.cpu().numpy(), g["I"]) and np.array_equal(Dd.cpu().numpy(), g["D"])
+    Dp, Ip = ix.search_preassigned(q, k, g["Ic"])
+    assert np.array_equal(Ip, g["I"]) and np.array_equal(Dp, g["D"])
+    # probing every list == exact flat search
+    ix.nprobe = nlist
+    Da, Ia = ix.search(q, k)
+    assert np.array_equal(Ia, g["If"]) and np.array_equal(Da, g["Df"])
+    st = ix.last_stats()
+    assert st["vectors"] == q.shape[0] * x.shape[0] and st["bytes"] == st["vectors"] * (4 * d + 8)
+
+
+def test_list_contents_keep_insertion_order_across_adds(gpu_pkg, lattice):
+    g, x, q, c = lattice
+    d, nlist = int(g["d"]), int(g["nlist"])
+    ix = gpu_pkg.IndexIVFFlat(d, nlist)
+    ix.set_centroids(c)
+    o = oivf.IVFFlat(d, nlist)
+    o.set_centroids(c)
+    for a, b in [(0, 1000), (1000, 1001), (1001, 5000), (5000, 8192)]:
+        ix.add(x[a:b])
+        o.add(x[a:b])
+    assert np.array_equal(ix.list_sizes(), o.list_sizes())
+    for l in (0, 17, nlist - 1):
+        codes, ids = ix.get_list(l)
+        assert np.array_equal(ids, o.ids[l]) and np.array_equal(codes, o.codes[l])
+    ix.nprobe = int(g["nprobe"])
+    D, I = ix.search(q, int(g["k"]))
+    assert np.array_equal(I, g["I"]) and np.array_equal(D, g["D"])
+    ix.reset()
+    assert ix.ntotal == 0 and ix.is_trained and ix.list_sizes().sum() == 0
+
+
+# ------------------------------------------------------------------ golden: gaussian -----------
+def test_ivf_gauss_search_and_train(gpu_pkg):
+    g = golden("ivf_gauss_d64.npz")
+    d, nlist, nprobe, k = int(g["d"]), int(g["nlist"]), int(g["nprobe"]), int(g["k"])
+    x, q = g["x"], g["q"]
+    ix = gpu_pkg.IndexIVFFlat(d, nlist)
+    ix.set_centroids(g["centroids"])
+    ix.add(x)
+    agree = (ix.assign(x) == g["assign"]).mean()
+    assert agree > 0.999
+    ix.nprobe = nprobe
+    D, I = ix.search(q, k)
+    # fp32 summation order differs from the oracle's: demand exact ids wherever the fp64 margins
+    # exceed the fp32 rounding bound (1e-5 on unit vectors), scores within 1e-5
+    safe = (g["coarse_margin"] > 1e-5) & (g["fine_margin"] > 1e-5)
+    assert safe.sum() >= 30
+    assert np.array_equal(I[safe], g["I"][safe])
+    assert np.abs(D[safe] - g["D"][safe]).max() < 1e-5
+    # Index.train: same subsample/init/Lloyd iterations as the oracle
+    ix2 = gpu_pkg.IndexIVFFlat(d, nlist)
+    ix2.train(x)
+    c = ix2.get_centroids()
+    # a point whose two best centroids tie within fp32 rounding may switch cluster between two
+    # correct fp32 implementations; demand near-identity, not bit-identity
+    diff = np.abs(c - g["centroids"]).max(axis=1)
+    assert np.median(diff) < 1e-5 and (diff < 1e-4).mean() >= 0.8 and diff.max() < 5e-2
+    o = oivf.IVFFlat(d, nlist)
+    o.set_centroids(c)
+    assert (o.assign(x) == g["assign"]).mean() > 0.99
+
+
+def test_train_matches_oracle_on_lattice(gpu_pkg):
+    d, nlist, n = 64, 16, 4000
+    x = osynth.corpus(99, 0, n, d, nlist)
+    ix = gpu_pkg.IndexIVFFlat(d, nlist)
+    ix.train(x)
+    ref = oivf.kmeans_train(x, nlist)
+    diff = np.abs(ix.get_centroids() - ref).max(axis=1)
+    assert np.median(diff) < 1e-5 and diff.max() < 5e-2
+    # subsampling branch: n > nlist * max_points_per_centroid
+    ix3 = gpu_pkg.IndexIVFFlat(d, 4)
+    ix3.cp.max_points_per_centroid = 256
+    x3 = osynth.corpus(5, 0, 4 * 300, d, 4)
+    ix3.train(x3)
+    diff = np.abs(ix3.get_centroids() - oivf.kmeans_train(x3, 4)).max(axis=1)
+    assert np.median(diff) < 1e-5 and diff.max() < 5e-2
+    with pytest.raises(RuntimeError):
+        gpu_pkg.IndexIVFFlat(d, 64).train(x[:10])
+
+
+# ------------------------------------------------------------------ edge cases -----------------
+def test_empty_ragged_and_padded_results(gpu_pkg):
+    P = gpu_pkg
+    d, nlist = 64, 8
+    c = osynth.centroids(1, nlist, d)
+    ix = P.IndexIVFFlat(d, nlist)
+    q = osynth.queries(1, 0, 3, d, nlist, 6)
+    with pytest.raises(RuntimeError):
+        ix.add(q)  # not trained
+    ix.set_centroids(c)
+    ix.nprobe = 4
+    D, I = ix.search(q, 5)  # empty index
+    assert (I == -1).all() and (D == -FLT_MAX).all()
+    x = osynth.corpus(1, 0, 6, d, nlist)
+    ix.add(x)
+    ix.nprobe = 100  # > nlist: clamped like faiss
+    D, I = ix.search(q, 10)
+    o = oivf.IVFFlat(d, nlist)
+    o.set_centroids(c)
+    o.add(x)
+    Do, Io = o.search(q, 10, nprobe=nlist)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+    assert (I[:, 6:] == -1).all() and (D[:, 6:] == -FLT_MAX).all()
+    # zero queries, -1 coarse entries
+    D0, I0 = ix.search(np.zeros((0, d), np.float32), 3)
+    assert D0.shape == (0, 3) and I0.shape == (0, 3)
+    Dp, Ip = ix.search_preassigned(q, 4, np.full((3, 2), -1, dtype=np.int64))
+    assert (Ip == -1).all()
+    # argument contract
+    with pytest.raises(AssertionError):
+        ix.search(np.zeros((2, d + 1), np.float32), 3)
+    with pytest.raises(RuntimeError):
+        ix.search(q, 100000)
+    with pytest.raises(AssertionError):
+        ix.add_with_ids(x, np.arange(5))
+    D64, I64 = ix.search(q.astype(np.float64), 3)  # coerced like faiss's wrapper
+    assert np.array_equal(I64, Io[:, :3])
+
+
+def test_ties_resolve_by_id_and_large_k(gpu_pkg):
+    P = gpu_pkg
+    d, nlist = 64, 4
+    c = osynth.centroids(2, nlist, d)
+    row = osynth.corpus(2, 0, 1, d, nlist)
+    ix = P.IndexIVFFlat(d, nlist)
+    ix.set_centroids(c)
+    ix.add_with_ids(np.repeat(row, 7, axis=0), np.array([50, 3, 99, 7, 21, 1, 64]))
+    ix.nprobe = nlist
+    D, I = ix.search(row, 5)
+    assert I[0].tolist() == [1, 3, 7, 21, 50]
+    # k spanning every register-slot variant of the warp top-k
+    n = 3000
+    x = osynth.corpus(3, 0, n, d, nlist)
+    q = osynth.queries(3, 0, 9, d, nlist, n)
+    ix = P.IndexIVFFlat(d, nlist)
+    ix.set_centroids(c := osynth.centroids(3, nlist, d))
+    ix.add(x)
+    o = oivf.IVFFlat(d, nlist)
+    o.set_centroids(c)
+    o.add(x)
+    for k in (1, 32, 33, 100, 256):
+        ix.nprobe = 2
+        D, I = ix.search(q, k)
+        Do, Io = o.search(q, k, nprobe=2, impl="c")
+        assert np.array_equal(I, Io) and np.array_equal(D, Do), k
+
+
+def test_write_read_roundtrip(gpu_pkg, tmp_path, lattice):
+    g, x, q, c = lattice
+    ix = gpu_pkg.IndexIVFFlat(int(g["d"]), int(g["nlist"]))
+    ix.set_centroids(c)
+    ix.add(x)
+    ix.nprobe = int(g["nprobe"])
+    path = str(tmp_path / "ix.absb")
+    gpu_pkg.write_index(ix, path)
+    ix2 = gpu_pkg.read_index(path)
+    assert ix2.ntotal == ix.ntotal and ix2.nprobe == ix.nprobe
+    D, I = ix2.search(q, int(g["k"]))
+    assert np.array_equal(I, g["I"]) and np.array_equal(D, g["D"])
+
+
+# ------------------------------------------------------------------ shards ---------------------
+def test_sharded_by_list_equals_single_index(gpu_pkg, lattice):
+    P = gpu_pkg
+    t = _torch()
+    g, x, q, c = lattice
+    d, nlist, nprobe, k = int(g["d"]), int(g["nlist"]), int(g["nprobe"]), int(g["k"])
+    world = 3
+    parts = []
+    for r in range(world):
+        ix = P.IndexIVFFlat(d, nlist)
+        ix.set_shard(r, world)
+        ix.set_centroids(c)
+        ix.add(x[:3000])
+        ix.add(x[3000:])
+        ix.nprobe = nprobe
+        parts.append(ix)
+    assert sum(p.ntotal for p in parts) == x.shape[0]
+    sizes = sum(p.list_sizes() for p in parts)
+    assert np.array_equal(sizes, g["sizes"])
+    for r, p in enumerate(parts):
+        assert (p.list_sizes()[np.arange(nlist) % world != r] == 0).all()
+    qd = t.from_numpy(q).cuda()
+    res = [p.search(qd, k) for p in parts]
+    # dense [world, n, k] layout
+    D_all = t.stack([r[0] for r in res]).contiguous()
+    I_all = t.stack([r[1] for r in res]).contiguous()
+    Dm = t.empty((q.shape[0], k), dtype=t.float32, device="cuda")
+    Im = t.empty((q.shape[0], k), dtype=t.int64, device="cuda")
+    L = P.lib()
+    rc = L.absb_merge_shards_dev(0, world, q.shape[0], k, ctypes.c_void_p(D_all.data_ptr()),
+                                 ctypes.c_void_p(I_all.data_ptr()), 0, ctypes.c_void_p(Dm.data_ptr()),
+                                 ctypes.c_void_p(Im.data_ptr()), None)
+    assert rc == 0
+    t.cuda.synchronize()
+    assert np.array_equal(Im.cpu().numpy(), g["I"]) and np.array_equal(Dm.cpu().numpy(), g["D"])
+    Dh, Ih = P.merge_partials_host(D_all.cpu().numpy(), I_all.cpu().numpy(), k)
+    assert np.array_equal(Ih, g["I"]) and np.array_equal(Dh, g["D"])
+
+
+# ------------------------------------------------------------------ larger, property-based -----
+def test_two_million_rows_properties(gpu_pkg):
+    """2M x 1024 built from the device generator with precomputed list ids (the faiss add_core
+    path): (1) probing all lists of a query's shortlist equals exact flat search restricted to those
+    lists; (2) the oracle, rebuilding only the probed lists from the counter-based generator, agrees
+    bit-for-bit; (3) searching twice is idempotent; (4) scores are sorted, ids unique."""
+    P = gpu_pkg
+    t = _torch()
+    d, nlist, n, nq, nprobe, k = 1024, 8192, 2_000_000, 64, 32, 10
+    seed = 1234
+    ix = P.IndexIVFFlat(d, nlist)
+    ix.set_centroids(P.synth.centroids(seed, nlist, d))
+    step = 250_000
+    for r0 in range(0, n, step):
+        xb = P.synth.corpus(seed, r0, step, d, nlist)
+        lb = P.synth.cluster_of(seed, r0, step, nlist)
+        ix.add_core(xb, t.arange(r0, r0 + step, device="cuda"), lb)
+    del xb, lb
+    assert ix.ntotal == n
+    sizes = ix.list_sizes()
+    assert sizes.sum() == n
+    assert np.array_equal(sizes, np.bincount(osynth.cluster_of(seed, np.arange(n), nlist), minlength=nlist))
+    q = P.synth.queries(seed, 0, nq, d, nlist, n)
+    ix.nprobe = nprobe
+    D, I = ix.search(q, k)
+    D2, I2 = ix.search(q, k)
+    assert t.equal(D, D2) and t.equal(I, I2)
+    Dn, In = D.cpu().numpy(), I.cpu().numpy()
+    assert (np.diff(Dn, axis=1) <= 0).all()
+    assert all(len(set(r.tolist())) == k for r in In)
+    _, Ic = ix.coarse(q, nprobe)
+    Ic = Ic.cpu().numpy()
+    qn = q.cpu().numpy()
+    # oracle on the first 6 queries: regenerate only their probed lists
+    sel = np.arange(6)
+    lists = np.unique(Ic[sel])
+    rows = osynth.rows_of_lists(seed, n, nlist, lists)
+    cent = osynth.centroids(seed, nlist, d)
+    Dco, Ico = oivf.FlatIP(d), None
+    o = oivf.IVFFlat(d, nlist)
+    o.set_centroids(cent)
+    for l in lists:
+        r = rows[int(l)]
+        o.add(osynth.corpus_rows(seed, r, d, nlist), ids=r, list_ids=np.full(len(r), l))
+    _, Ico = o.coarse(qn[sel], nprobe)
+    assert np.array_equal(Ico, Ic[sel])
+    Do, Io = o.search_preassigned(qn[sel], k, Ic[sel], impl="c")
+    assert np.array_equal(Io, In[sel]) and np.array_equal(Do, Dn[sel])
+    st = ix.last_stats()
+    assert st["vectors"] == sizes[Ic].sum()
