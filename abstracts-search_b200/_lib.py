@@ -67,6 +67,7 @@ _SIGS = {
     "absb_device_count": ([POINTER(c_int)], c_int),
     "absb_device_info": ([c_int, c_char_p, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)], c_int),
     "absb_synth_fill_dev": ([c_int, c_uint64, c_int64, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p], c_int),
+    "absb_synth_fill_rows_dev": ([c_int, c_uint64, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p], c_int),
     "absb_synth_cluster_dev": ([c_uint64, c_int64, c_int64, c_int, c_void_p, c_void_p], c_int),
     # flat
     "absb_flat_create": ([c_int, c_int, c_int, POINTER(_H)], c_int),
@@ -108,6 +109,8 @@ _SIGS = {
     "absb_merge_shards_dev": ([c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p], c_int),
     "absb_ivf_set_tunables": ([_H, c_int, c_int, c_int], c_int),
     "absb_ivf_last_stats": ([_H, _PI64, _PI64, _PI64, _PI64], c_int),
+    "absb_ivf_set_profile": ([_H, c_int], c_int),
+    "absb_ivf_get_profile": ([_H, _PD, _PD, _PD, _PI64], c_int),
     "absb_ivf_time_scan": ([_H, c_int, c_void_p, _PF], c_int),
     # encoder
     "absb_enc_create": ([POINTER(EncConfig), c_int, POINTER(_H)], c_int),

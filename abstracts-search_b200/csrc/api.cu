@@ -106,7 +106,16 @@ int absb_synth_fill_dev(int kind, uint64_t seed, int64_t row0, int64_t n, int d,
                         int64_t corpus_rows, float* out_dev, void* stream) {
   ABSB_API_BEGIN
   ABSB_CHECK(n == 0 || out_dev, ABSB_ERR_INVALID, "null output");
-  synth_fill(kind, seed, row0, n, d, nlist, corpus_rows, out_dev, (cudaStream_t)stream);
+  synth_fill(kind, seed, row0, nullptr, n, d, nlist, corpus_rows, out_dev, (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_synth_fill_rows_dev(int kind, uint64_t seed, const int64_t* rows_dev, int64_t n, int d, int nlist,
+                             int64_t corpus_rows, float* out_dev, void* stream) {
+  ABSB_API_BEGIN
+  ABSB_CHECK(n == 0 || (out_dev && rows_dev), ABSB_ERR_INVALID, "null argument");
+  synth_fill(kind, seed, 0, reinterpret_cast<const long long*>(rows_dev), n, d, nlist, corpus_rows, out_dev,
+             (cudaStream_t)stream);
   ABSB_API_END
 }
 
@@ -590,6 +599,36 @@ int absb_ivf_last_stats(absb_ivf_t h, int64_t* vectors_scanned, int64_t* bytes_s
   if (bytes_scanned) *bytes_scanned = ix.stats.bytes;
   if (work_items) *work_items = ix.stats.items;
   if (launches) *launches = ix.stats.launches;
+  ABSB_API_END
+}
+
+int absb_ivf_set_profile(absb_ivf_t h, int on) {
+  ABSB_API_BEGIN
+  NEED(h);
+  IvfIndex& ix = h->ix;
+  DeviceGuard g(ix.device);
+  ABSB_CUDA(cudaDeviceSynchronize());
+  if (ix.profile) ix.fold_profile();
+  ix.profile = on != 0;
+  if (on == 2) {
+    ix.prof_ms[0] = ix.prof_ms[1] = ix.prof_ms[2] = 0;
+    ix.prof_scan_launches = 0;
+  }
+  ABSB_API_END
+}
+
+int absb_ivf_get_profile(absb_ivf_t h, double* scan_ms, double* coarse_gemm_ms, double* other_ms,
+                         int64_t* scan_launches) {
+  ABSB_API_BEGIN
+  NEED(h);
+  IvfIndex& ix = h->ix;
+  DeviceGuard g(ix.device);
+  ABSB_CUDA(cudaDeviceSynchronize());
+  ix.fold_profile();
+  if (scan_ms) *scan_ms = ix.prof_ms[0];
+  if (coarse_gemm_ms) *coarse_gemm_ms = ix.prof_ms[1];
+  if (other_ms) *other_ms = ix.prof_ms[2];
+  if (scan_launches) *scan_launches = ix.prof_scan_launches;
   ABSB_API_END
 }
 

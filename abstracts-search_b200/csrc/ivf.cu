@@ -198,6 +198,7 @@ void PagePool::release() {
 // TMEM) — fp32-faithful scores at tensor-core speed; needs d % 64 == 0 and nlist % 32 == 0, other
 // shapes take the FFMA kernel.
 void IvfIndex::coarse_scores(int M, const float* q, float* S, cudaStream_t st) {
+  Span sp(this, st, 1);
   if (coarse_impl == 1 && d % 64 == 0 && nlist % 32 == 0) {
     if (c3_dirty) {
       centroids3.reserve((size_t)nlist * 3 * d);
@@ -245,6 +246,35 @@ IvfIndex::~IvfIndex() {
     cudaStreamSynchronize(own_stream);
     cudaStreamDestroy(own_stream);
   }
+  for (auto& e : ev_pool) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+}
+
+IvfIndex::Span::Span(IvfIndex* ix_, cudaStream_t st_, int kind) : ix(ix_), st(st_), on(ix_->profile) {
+  if (!on) return;
+  if (ix->ev_used == ix->ev_pool.size()) {
+    cudaEvent_t a, b;
+    ABSB_CUDA(cudaEventCreate(&a));
+    ABSB_CUDA(cudaEventCreate(&b));
+    ix->ev_pool.emplace_back(a, b);
+  }
+  auto& pr = ix->ev_pool[ix->ev_used++];
+  ix->ev_kind.push_back(kind);
+  stop = pr.second;
+  cudaEventRecord(pr.first, st);
+}
+
+// call with the stream idle
+void IvfIndex::fold_profile() {
+  for (size_t i = 0; i < ev_used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev_pool[i].first, ev_pool[i].second) == cudaSuccess) prof_ms[ev_kind[i]] += ms;
+    if (ev_kind[i] == 0) ++prof_scan_launches;
+  }
+  ev_used = 0;
+  ev_kind.clear();
 }
 
 ListTable IvfIndex::table() const {
@@ -293,8 +323,11 @@ void IvfIndex::coarse_dev(int64_t nq, const float* q, int nprobe, float* Dc, lon
     const int64_t nr = std::min(rows_max, nq - r0);
     ws_scores.reserve((size_t)std::min(rows_max, nq) * nlist);
     coarse_scores((int)nr, q + r0 * d, ws_scores.p, st);
-    select_rows(ws_scores.p, nlist, nr, nlist, 0, nprobe, Dc + r0 * nprobe, Ic + r0 * nprobe, nprobe,
-                finalize, st);
+    {
+      Span sp(this, st, 2);
+      select_rows(ws_scores.p, nlist, nr, nlist, 0, nprobe, Dc + r0 * nprobe, Ic + r0 * nprobe, nprobe,
+                  finalize, st);
+    }
     stats.launches += 1;
   }
 }
@@ -631,8 +664,11 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
     ws_part_id.reserve((size_t)max_items * k);
     ws_q_begin.reserve(kMaxPlanQueries + 1);
     if (stats_pending) fold_stats();  // only one plan's numbers fit in ws_stats
-    launch_plan(table(), coarse + q0 * nprobe, nb, nprobe, scan_chunk, (int)max_items, ws_items.p,
-                ws_q_begin.p, ws_counters.p, ws_counters.p + 1, ws_stats.p, st);
+    {
+      Span sp(this, st, 2);
+      launch_plan(table(), coarse + q0 * nprobe, nb, nprobe, scan_chunk, (int)max_items, ws_items.p,
+                  ws_q_begin.p, ws_counters.p, ws_counters.p + 1, ws_stats.p, st);
+    }
     ScanLaunch a;
     a.Q = q + q0 * d;
     a.d = d;
@@ -644,8 +680,14 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
     a.part_id = ws_part_id.p;
     a.sm_count = props.sm_count;
     a.ctas_per_sm = scan_ctas_per_sm;
-    launch_scan(a, st);
-    merge_partials(nb, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, D + q0 * k, I + q0 * k, st);
+    {
+      Span sp(this, st, 0);
+      launch_scan(a, st);
+    }
+    {
+      Span sp(this, st, 2);
+      merge_partials(nb, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, D + q0 * k, I + q0 * k, st);
+    }
     last_scan = a;
     have_last_scan = true;
     stats_pending = true;

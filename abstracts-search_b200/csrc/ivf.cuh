@@ -92,6 +92,27 @@ struct IvfIndex {
   SearchStats stats;
   bool stats_pending = false;  // ws_stats holds device-side numbers not yet folded into `stats`
 
+  // optional per-phase device timing (absb_ivf_set_profile): CUDA events recorded on the search's
+  // own stream around the fine-scan kernel (0), the coarse GEMM (1) and everything else (2)
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  size_t ev_used = 0;
+  std::vector<int> ev_kind;
+  double prof_ms[3] = {0, 0, 0};
+  int64_t prof_scan_launches = 0;
+  int64_t prof_vectors = 0;
+  struct Span {
+    IvfIndex* ix;
+    cudaStream_t st;
+    bool on;
+    cudaEvent_t stop = nullptr;
+    Span(IvfIndex* ix_, cudaStream_t st_, int kind);
+    ~Span() {
+      if (on) cudaEventRecord(stop, st);
+    }
+  };
+  void fold_profile();
+
   IvfIndex(int d, int nlist, int device);
   ~IvfIndex();
 

@@ -65,8 +65,8 @@ void merge_shards(int world, int64_t nq, int k, const float* D_all, const long l
                   int64_t d_stride_bytes, int64_t i_stride_bytes, float* D, long long* I, cudaStream_t st);
 
 // synth.cu
-void synth_fill(int kind, uint64_t seed, int64_t row0, int64_t n, int d, int nlist,
-                int64_t corpus_rows, float* out, cudaStream_t st);
+void synth_fill(int kind, uint64_t seed, int64_t row0, const long long* row_ids, int64_t n, int d,
+                int nlist, int64_t corpus_rows, float* out, cudaStream_t st);
 void synth_cluster(uint64_t seed, int64_t row0, int64_t n, int nlist, long long* out, cudaStream_t st);
 
 }  // namespace absb

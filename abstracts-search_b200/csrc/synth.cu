@@ -35,7 +35,8 @@ __host__ __device__ __forceinline__ int cluster_of(uint64_t seed, uint64_t row, 
   return (int)((row_key(seed ^ SALT_CL, row) >> 33) % (uint64_t)nlist);
 }
 
-__global__ void synth_fill_kernel(int kind, uint64_t seed, int64_t row0, int64_t n, int d,
+__global__ void synth_fill_kernel(int kind, uint64_t seed, int64_t row0,
+                                  const long long* __restrict__ row_ids, int64_t n, int d,
                                   int nlist, int64_t corpus_rows, float* __restrict__ out) {
   const int groups = d / 8;
   const int64_t total = n * groups;
@@ -43,7 +44,7 @@ __global__ void synth_fill_kernel(int kind, uint64_t seed, int64_t row0, int64_t
        t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = t / groups;
     const int g = (int)(t % groups);
-    const uint64_t r = (uint64_t)(row0 + i);
+    const uint64_t r = row_ids ? (uint64_t)row_ids[i] : (uint64_t)(row0 + i);
     int v[8];
     if (kind == 1) {  // centroid r
       const uint64_t w = word(row_key(seed ^ SALT_MU, r), g);
@@ -84,8 +85,8 @@ __global__ void synth_cluster_kernel(uint64_t seed, int64_t row0, int64_t n, int
 
 }  // namespace
 
-void synth_fill(int kind, uint64_t seed, int64_t row0, int64_t n, int d, int nlist,
-                int64_t corpus_rows, float* out, cudaStream_t st) {
+void synth_fill(int kind, uint64_t seed, int64_t row0, const long long* row_ids, int64_t n, int d,
+                int nlist, int64_t corpus_rows, float* out, cudaStream_t st) {
   ABSB_CHECK(kind >= 0 && kind <= 2, ABSB_ERR_INVALID, "synth kind %d", kind);
   ABSB_CHECK(d > 0 && d % 8 == 0, ABSB_ERR_INVALID, "synth needs d %% 8 == 0 (d=%d)", d);
   ABSB_CHECK(nlist > 0 && n >= 0, ABSB_ERR_INVALID, "synth nlist/n");
@@ -93,7 +94,7 @@ void synth_fill(int kind, uint64_t seed, int64_t row0, int64_t n, int d, int nli
   if (n == 0) return;
   const int64_t total = n * (d / 8);
   const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
-  synth_fill_kernel<<<blocks, 256, 0, st>>>(kind, seed, row0, n, d, nlist, corpus_rows, out);
+  synth_fill_kernel<<<blocks, 256, 0, st>>>(kind, seed, row0, row_ids, n, d, nlist, corpus_rows, out);
   ABSB_CUDA(cudaGetLastError());
 }
 

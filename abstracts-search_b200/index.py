@@ -385,6 +385,16 @@ class IndexIVFFlat:
         check(lib().absb_ivf_last_stats(self._h, byref(v), byref(b), byref(w), byref(l)))
         return {"vectors": v.value, "bytes": b.value, "items": w.value, "launches": l.value}
 
+    def set_profile(self, on: int):
+        check(lib().absb_ivf_set_profile(self._h, int(on)))
+
+    def get_profile(self) -> dict:
+        from ctypes import c_double
+
+        s, c, o, n = c_double(), c_double(), c_double(), c_int64()
+        check(lib().absb_ivf_get_profile(self._h, byref(s), byref(c), byref(o), byref(n)))
+        return {"scan_ms": s.value, "coarse_gemm_ms": c.value, "other_ms": o.value, "scan_launches": n.value}
+
     def time_scan(self, iters: int = 10) -> float:
         ms = c_float()
         check(lib().absb_ivf_time_scan(self._h, iters, _lib.current_stream_ptr(), byref(ms)))

@@ -31,6 +31,21 @@ def queries(seed, q0, n, d, nlist, corpus_rows, out=None, device=0):
     return fill(KIND_QUERIES, seed, q0, n, d, nlist, corpus_rows, out, device)
 
 
+def corpus_rows(seed, rows, d, nlist, out=None):
+    """Corpus rows for an explicit CUDA int64 tensor of row numbers."""
+    import torch
+
+    assert rows.is_cuda and rows.dtype == torch.int64 and rows.is_contiguous()
+    n = rows.numel()
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=rows.device)
+    assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= n * d
+    with torch.cuda.device(rows.device):
+        check(lib().absb_synth_fill_rows_dev(KIND_CORPUS, seed, ptr(rows), n, d, nlist, 0, ptr(out),
+                                             current_stream_ptr()))
+    return out[:n] if out.shape[0] != n else out
+
+
 def cluster_of(seed, row0, n, nlist, out=None, device=0):
     import torch
 

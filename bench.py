@@ -1,0 +1,484 @@
+#!/usr/bin/env python
+"""bench.py — queries/sec of the abstracts-search hot path (encode + IVF search, k=10) on B200.
+
+One "step" = one 512-query batch through the whole path:
+    stella_en_1.5B_v5 encode of 512 x 32-token queries (data-parallel over ranks)
+    -> all-gather of the embeddings (N > 1)
+    -> IVF65536,Flat search, nprobe 32, k 10, over this rank's inverted lists
+    -> ONE all-gather of the per-shard partial top-k + merge (N > 1).
+
+Workload (config.workload): BASELINE.json's metric is quoted on 207M x 1024 sharded by inverted list
+over 8 GPUs (configs[3]); that index is 848 GB and does not fit fewer than 5 GPUs, so every GPU
+holds the shard it holds in that configuration — 207M / 8 = 25,875,000 rows (106 GB) — and the total
+grows with N ("scaling": "weak"): N = 8 is exactly the 207M x 1024 index of the metric, N = 1 is a
+25.9M x 1024 IVF65536 index, larger than the 10M single-GPU search config (configs[2]; run it with
+--rows-per-gpu 10000000).  The per-GPU scan work per query (32 probes x ~395 vectors x 4,104 B) is
+the same at every N; the encode work per GPU shrinks as 1/N.
+
+    value     device-resident inputs, CUDA events on the launching stream, max over ranks
+    e2e       the same step through the numpy (host-buffer) API a faiss/sentence-transformers user
+              calls: pinned host token ids -> encode -> host embeddings -> search -> host (D, I)
+    roofline  the dominant kernel of the step, timed live with CUDA events inside the timed region
+    cpu_baseline  the oracle port (torch-CPU fp32 encoder + C/OpenMP IVF) on a bounded sample
+
+`--impl reference` times the CPU path alone (rank 0) — the reference's own CPU stack
+(sentence-transformers + faiss-cpu) is not installable offline, so the oracle port stands in
+(cpu_baseline.kind = "port").
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec (encode+IVF search, k=10, nprobe=32, IVF65536 over 1024-d fp32)"
+UNIT = "queries/s"
+SEED = 1234
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows-per-gpu", type=int, default=25_875_000)
+    ap.add_argument("--nlist", type=int, default=65536)
+    ap.add_argument("--nprobe", type=int, default=32)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=512, help="queries per step (whole job)")
+    ap.add_argument("--query-tokens", type=int, default=32)
+    ap.add_argument("--coarse-impl", type=int, default=1, help="0 fp32 FFMA GEMM, 1 tcgen05 split-bf16 GEMM")
+    ap.add_argument("--scan-chunk", type=int, default=-1)
+    ap.add_argument("--no-kernel-events", action="store_true", help="do not time individual kernels in the timed region")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": float(j["hbm_gbs"]), "tf_burst": float(j["bf16_tflops"]),
+                "tf_sustained": float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (oracle port) — used by cpu_baseline and by --impl reference
+# ------------------------------------------------------------------------------------------------
+class CpuPath:
+    """torch-CPU fp32 stella encoder + C/OpenMP IVF over the probed lists of a bounded query sample."""
+
+    def __init__(self, total_rows: int, nlist: int, nprobe: int, k: int, nq: int, tokens: int, d: int = 1024):
+        import torch
+
+        from oracle import encoder as oenc
+        from oracle import ivf as oivf
+        from oracle import synth as osynth
+
+        P = importlib.import_module("abstracts-search_b200.encoder")
+        self.cfg = P.STELLA_1_5B
+        self.oenc, self.k, self.nprobe, self.nq = oenc, k, nprobe, nq
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        g = torch.Generator().manual_seed(0)
+        t0 = time.time()
+        self.sd = {}
+        for name, shape in self.cfg.param_shapes().items():
+            t = torch.empty(shape, dtype=torch.float32)
+            if name.endswith("layernorm.weight") or name == "norm.weight":
+                t.normal_(1.0, 0.05, generator=g)
+            else:
+                t.normal_(0.0, 0.02, generator=g)
+            self.sd[name] = t.numpy()
+        rng = np.random.default_rng(4321)
+        self.ids = rng.integers(0, self.cfg.vocab_size, (nq, tokens)).astype(np.int64)
+        self.mask = np.ones_like(self.ids)
+        # index: the real centroids, and only the inverted lists this sample probes (what faiss-cpu
+        # would touch), rebuilt from the counter-based generator
+        emb = oenc.forward_plain(self.cfg, self.sd, self.ids, self.mask, normalize=True)
+        cent = np.empty((nlist, d), dtype=np.float32)
+        for l0 in range(0, nlist, 8192):
+            cent[l0:l0 + 8192] = osynth.centroids(SEED, nlist, d, l0, min(8192, nlist - l0))
+        self.o = oivf.IVFFlat(d, nlist)
+        self.o.set_centroids(cent)
+        _, Ic = self.o.coarse(emb, nprobe, impl="c")
+        want = np.unique(Ic)
+        rows_l, lists_l = [], []
+        for r0 in range(0, total_rows, 1 << 22):
+            rows = np.arange(r0, min(r0 + (1 << 22), total_rows), dtype=np.int64)
+            c = osynth.cluster_of(SEED, rows, nlist)
+            m = np.isin(c, want)
+            rows_l.append(rows[m])
+            lists_l.append(c[m].astype(np.int64))
+        rows, lists = np.concatenate(rows_l), np.concatenate(lists_l)
+        for r0 in range(0, len(rows), 32768):
+            r, l = rows[r0:r0 + 32768], lists[r0:r0 + 32768]
+            self.o.add(osynth.corpus_rows(SEED, r, d, nlist), ids=r, list_ids=l)
+        self.o._as_csr()
+        self.vectors_per_query = float(self.o.list_sizes()[Ic].sum()) / nq
+        self.setup_s = time.time() - t0
+
+    def step(self):
+        emb = self.oenc.forward_plain(self.cfg, self.sd, self.ids, self.mask, normalize=True)
+        _, Ic = self.o.coarse(emb, self.nprobe, impl="c")
+        return self.o.search_preassigned(emb, self.k, Ic, impl="c")
+
+    def describe(self):
+        return (f"{self.nq} queries x {self.ids.shape[1]} tokens per step: torch-CPU fp32 Qwen2-1.5B forward + C/OpenMP "
+                f"coarse over {self.o.nlist} centroids + scan of the probed lists "
+                f"({self.vectors_per_query:.0f} vectors/query)")
+
+
+def auto_cpu_sample(total_rows: int, nlist: int, nprobe: int) -> int:
+    # 16 queries, fewer only if their probed lists would exceed ~1.7M vectors (7 GB, ~1 min to regenerate)
+    per_q = max(1.0, total_rows / nlist * nprobe)
+    return int(max(2, min(16, 1_700_000 // per_q)))
+
+
+def time_cpu(cp: CpuPath, steps: int, warmup: int):
+    for _ in range(warmup):
+        cp.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cp.step()
+    dt = time.perf_counter() - t0
+    return cp.nq * steps / dt, dt / steps
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    total_rows = args.rows_per_gpu * world
+    nq = args.cpu_sample or auto_cpu_sample(total_rows, args.nlist, args.nprobe)
+    cp = CpuPath(total_rows, args.nlist, args.nprobe, args.k, nq, args.query_tokens)
+    qps, s_per_step = time_cpu(cp, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cp.cores, "kind": "port", "sample": cp.describe()},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world: int):
+    total = args.rows_per_gpu * world
+    return {
+        "workload": (f"end-to-end encode+search (BASELINE configs[3]): stella_en_1.5B_v5 encode of {args.batch} x "
+                     f"{args.query_tokens}-token queries + IVF{args.nlist},Flat search k={args.k} nprobe={args.nprobe} over "
+                     f"{total} x 1024 fp32 rows sharded by inverted list over {world} GPU(s) "
+                     f"({args.rows_per_gpu} rows = {args.rows_per_gpu * 4104 / 1e9:.0f} GB per GPU; 8 GPUs = the 207M index)"),
+        "rows_total": total, "rows_per_gpu": args.rows_per_gpu, "nlist": args.nlist, "nprobe": args.nprobe, "k": args.k,
+        "queries_per_step": args.batch, "query_tokens": args.query_tokens,
+        "parallelism": f"encode dp{world}; index sharded by list x{world}; 1 all-gather of partial top-k",
+        "l2": "inputs larger than L2: >= 20 GB of list codes and 3.1 GB of weights stream per step (L2 = 126 MB)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = os.path.join(tempfile.gettempdir(), f"absb_clocks_{os.getpid()}.csv")
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def build_shard(P, torch, args, rank: int, world: int, dev: int):
+    d, nlist = 1024, args.nlist
+    total = args.rows_per_gpu * world
+    ix = P.index_factory(d, f"IVF{nlist},Flat", P.METRIC_INNER_PRODUCT, device=dev)
+    ix.set_tunables(scan_chunk=args.scan_chunk, coarse_impl=args.coarse_impl)
+    if world > 1:
+        ix.set_shard(rank, world)
+    ix.set_centroids(P.synth.centroids(SEED, nlist, d, device=dev))
+    keep = 1 << 20  # rows materialised per add
+    span = keep * world
+    xbuf = torch.empty((int(keep * 1.05) + 4096, d), dtype=torch.float32, device=f"cuda:{dev}")
+    t0 = time.time()
+    for r0 in range(0, total, span):
+        n = min(span, total - r0)
+        lists = P.synth.cluster_of(SEED, r0, n, nlist, device=dev)
+        if world > 1:
+            sel = torch.nonzero(lists % world == rank).squeeze(1)
+            rows = (sel + r0).contiguous()
+            lists = lists[sel].contiguous()
+        else:
+            rows = torch.arange(r0, r0 + n, dtype=torch.int64, device=f"cuda:{dev}")
+        x = P.synth.corpus_rows(SEED, rows, d, nlist, out=xbuf)
+        ix.add_core(x, rows, lists)
+    torch.cuda.synchronize()
+    del xbuf
+    torch.cuda.empty_cache()
+    return ix, time.time() - t0
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+
+    P = importlib.import_module("abstracts-search_b200")
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback of the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    device = f"cuda:{dev}"
+    pk = peaks()
+    assert args.batch % world == 0
+    nq, S, k = args.batch, args.query_tokens, args.k
+    per = nq // world
+
+    enc = P.Encoder(config=P.STELLA_1_5B, device=device, random_init_seed=0)
+    ix, build_s = build_shard(P, torch, args, rank, world, dev)
+    ix.nprobe = args.nprobe
+    sh = P.ShardedIndexIVFFlat(ix) if world > 1 else None
+    if sh is not None:
+        sh.nprobe = args.nprobe
+
+    # inputs: pinned host token ids (e2e) and their device copies (value)
+    g = torch.Generator().manual_seed(4321)
+    ids_h = torch.randint(0, P.STELLA_1_5B.vocab_size, (nq, S), generator=g, dtype=torch.int64).pin_memory()
+    mask_h = torch.ones((nq, S), dtype=torch.int32).pin_memory()
+    ids_np, mask_np = ids_h.numpy(), mask_h.numpy()
+    ids_d, mask_d = ids_h.to(device), mask_h.to(device)
+    lo, hi = rank * per, (rank + 1) * per
+    emb_all = torch.empty((nq, 1024), dtype=torch.float32, device=device)
+
+    def step_dev():
+        e = enc.encode_tokens(ids_d[lo:hi], mask_d[lo:hi], normalize_embeddings=True)
+        if world > 1:
+            dist.all_gather_into_tensor(emb_all, e)
+            return sh.search(emb_all, k)
+        return ix.search(e, k)
+
+    def step_e2e():
+        e = enc.encode_tokens(ids_np[lo:hi], mask_np[lo:hi], normalize_embeddings=True)  # host in, host out
+        if world > 1:
+            dist.all_gather_into_tensor(emb_all, torch.from_numpy(e).to(device, non_blocking=True))
+            D, I = sh.search(emb_all, k)
+            return D.cpu().numpy(), I.cpu().numpy()
+        return ix.search(e, k)  # numpy in, numpy out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up + correctness of the step's plumbing ------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        D, I = step_dev()
+    torch.cuda.synchronize()
+    st = ix.last_stats()
+    es = enc.last_stats()
+    Iw = I.cpu().numpy()
+    assert (Iw >= 0).all() and Iw.shape == (nq, k), "search returned missing results on a full index"
+    _, Ic = ix.coarse(emb_all if world > 1 else enc.encode_tokens(ids_d, mask_d, True), args.nprobe)
+    distinct_lists = int(torch.unique(Ic).numel())
+    launches_per_step = int(es["launches"] + st["launches"] + (1 if world > 1 else 0))
+
+    # ---- timed region: value -------------------------------------------------------------------
+    kernel_events = not args.no_kernel_events
+    if kernel_events:
+        enc.set_profile(2)
+        ix.set_profile(2)
+    sampler = ClockSampler(dev) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if sampler else None
+    enc_prof = ix_prof = None
+    if kernel_events:
+        enc_prof, ix_prof = enc.get_profile(), ix.get_profile()
+        enc.set_profile(0)
+        ix.set_profile(0)
+    st = ix.last_stats()
+    ms_per_step = ms_total / args.steps
+    value = nq / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the public numpy API ----------------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        for _ in range(2):
+            De, Ie = step_e2e()
+        assert np.array_equal(Ie, Iw), "host-API result differs from the device-API result"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+        h2d = per * S * (8 + 4) + (nq * 1024 * 4 if world == 1 else per * 1024 * 4)
+        d2h = per * 1024 * 4 + nq * k * 12
+        e2e = {"value": nq / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h),
+               "api": "Encoder.encode_tokens(numpy) -> IndexIVFFlat.search(numpy): absb_enc_forward + absb_ivf_search"}
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    rooflines = {}
+    if kernel_events:
+        scan_ms = ix_prof["scan_ms"] / max(1, ix_prof["scan_launches"])
+        scan_gbs = st["bytes"] / max(1, ix_prof["scan_launches"] // args.steps) / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+        rooflines["ivf_scan_kernel"] = {
+            "bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": scan_gbs / pk["hbm_gbs"],
+            "traffic": None, "peak_source": pk["source"] + " copy bandwidth",
+            "ms_per_launch": scan_ms, "ms_per_step": ix_prof["scan_ms"] / args.steps,
+            "algorithmic_bytes_per_step": st["bytes"], "vectors_per_step": st["vectors"]}
+        gemm_tf = enc_prof["gemm_flops"] / (enc_prof["gemm_ms"] * 1e-3) / 1e12 if enc_prof["gemm_ms"] > 0 else 0.0
+        n_gemm = 4 * P.STELLA_1_5B.num_layers + 1
+        rooflines["gemm_bf16_tc_kernel"] = {
+            "bound": "tensor", "achieved": gemm_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+            "frac": gemm_tf / pk["tf_sustained"], "traffic": None,
+            "peak_source": pk["source"] + " cuBLAS bf16, sustained (kernel timed inside a long step)",
+            "ms_per_launch": enc_prof["gemm_ms"] / max(1, enc_prof["forwards"] * n_gemm),
+            "ms_per_step": enc_prof["gemm_ms"] / args.steps,
+            "algorithmic_flops_per_step": enc_prof["gemm_flops"] / args.steps}
+        phases = {"encode_gemm_ms": enc_prof["gemm_ms"] / args.steps, "encode_attention_ms": enc_prof["attention_ms"] / args.steps,
+                  "encode_other_ms": enc_prof["other_ms"] / args.steps, "coarse_gemm_ms": ix_prof["coarse_gemm_ms"] / args.steps,
+                  "scan_ms": ix_prof["scan_ms"] / args.steps, "search_other_ms": ix_prof["other_ms"] / args.steps}
+        dominant = max(rooflines, key=lambda n: rooflines[n]["ms_per_step"])
+    else:
+        phases, dominant = {}, None
+    load_traffic(rooflines)
+
+    if rank != 0:
+        return
+    # ---- CPU baseline (oracle port) on a bounded sample ----------------------------------------
+    cpu = None
+    if world == 1 and not args.skip_cpu_baseline:
+        n_cpu = args.cpu_sample or auto_cpu_sample(args.rows_per_gpu, args.nlist, args.nprobe)
+        cp = CpuPath(args.rows_per_gpu, args.nlist, args.nprobe, k, n_cpu, S)
+        qps, _ = time_cpu(cp, 2, 1)
+        cpu = {"value": qps, "unit": UNIT, "cores": cp.cores, "kind": "port", "sample": cp.describe()}
+
+    cfg = workload_config(args, world)
+    cfg.update({"index_build_s": build_s, "distinct_probed_lists_per_step": distinct_lists,
+                "scan_work_items_per_step": st["items"], "coarse_impl": "tcgen05 split-bf16 (6 bf16 products, fp32-faithful)"
+                if args.coarse_impl == 1 else "fp32 FFMA", "kernel_events_in_timed_region": kernel_events})
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 (encoder GEMMs, fp32 accumulate) + f32 (IVF scores)", "data": "synthetic", "config": cfg,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+        "roofline": dict(rooflines[dominant], kernel=dominant) if dominant else None,
+        "rooflines": rooflines, "phases_ms_per_step": phases, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def load_traffic(rooflines: dict):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json), if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return
+    try:
+        t = json.load(open(p))
+    except Exception:
+        return
+    for name, r in rooflines.items():
+        if name in t:
+            r["traffic"] = t[name].get("dram_bytes_per_launch")
+            r["traffic_source"] = t[name].get("source")
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -67,6 +67,10 @@ int absb_device_info(int device, char* name, int name_len, int* sm_count, int* c
  * out is a DEVICE pointer to [n, d] float32. */
 int absb_synth_fill_dev(int kind, uint64_t seed, int64_t row0, int64_t n, int d, int nlist,
                         int64_t corpus_rows, float* out_dev, void* stream);
+/* Same generator for an explicit list of row numbers rows_dev [n] (DEVICE int64): lets a shard
+ * materialise only the rows whose inverted list it owns. */
+int absb_synth_fill_rows_dev(int kind, uint64_t seed, const int64_t* rows_dev, int64_t n, int d,
+                             int nlist, int64_t corpus_rows, float* out_dev, void* stream);
 /* cluster id c(r) of corpus rows [row0,row0+n) -> DEVICE int64 (feeds add_preassigned) */
 int absb_synth_cluster_dev(uint64_t seed, int64_t row0, int64_t n, int nlist, int64_t* out_dev,
                            void* stream);
@@ -170,6 +174,14 @@ int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int sca
  * algorithmic bytes (vectors * (4d+8)), number of scan work items, number of kernel launches. */
 int absb_ivf_last_stats(absb_ivf_t h, int64_t* vectors_scanned, int64_t* bytes_scanned,
                         int64_t* work_items, int64_t* launches);
+/* Per-phase device timing with CUDA events recorded on the search's own stream: on = 1 start,
+ * 0 stop, 2 start with counters reset.  get_profile synchronises and returns the accumulated
+ * milliseconds of the fine-scan kernel, of the coarse GEMM and of everything else (plan, selects,
+ * merges) plus the number of fine-scan launches covered — bench.py's roofline.achieved for the
+ * scan comes from here (bytes from absb_ivf_last_stats). */
+int absb_ivf_set_profile(absb_ivf_t h, int on);
+int absb_ivf_get_profile(absb_ivf_t h, double* scan_ms, double* coarse_gemm_ms, double* other_ms,
+                         int64_t* scan_launches);
 /* Replays ONLY the fine-scan kernel of the most recent *_dev search (same work items) `iters`
  * times on `stream` and returns the mean duration in ms measured with CUDA events on that
  * stream — used by bench.py for roofline.achieved. */
