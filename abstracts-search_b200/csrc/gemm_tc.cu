@@ -8,16 +8,19 @@
 //
 // C[M,N] = A[M,K] * B[N,K]^T, both operands K-major (row-major activations, nn.Linear weights).
 //
-// Kernel anatomy (persistent, one CTA per SM, 256 threads):
-//   warp 0   TMA producer: cp.async.bulk.tensor 128x64 (A) and BNx64 (B) bf16 boxes, SWIZZLE_128B,
-//            into a 4-stage shared-memory ring, completion on `full` mbarriers;
-//   warp 1   MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16
-//            (M=128, N=BN, K=16) x4 per stage into a TMEM accumulator, tcgen05.commit releases the
-//            stage (`empty`) and finally signals `tmem_full`;
-//   warp 2   allocates / frees the 2 x BN TMEM columns (double-buffered accumulator);
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused epilogue, direct global
-//            stores (each thread owns one output row: 64-128 contiguous bytes per store burst),
-//            then release the accumulator (`tmem_empty`) so the next tile's MMAs overlap.
+// Kernel anatomy (persistent, one CTA per SM, 256 threads; NCTA = 2 pairs the two SMs of a TPC on one
+// 256 x BN tile with cta_group::2 so that each SM stages only half of the B tile):
+//   warp 0   TMA producer: cp.async.bulk.tensor 128x64 (A) and (BN/NCTA)x64 (B) bf16 boxes,
+//            SWIZZLE_128B, into a 4-7 stage shared-memory ring; completion bytes of both CTAs of a
+//            pair are credited to the leader's `full` mbarrier;
+//   warp 1   MMA issuer (leader CTA): one thread issues tcgen05.mma.cta_group::{1,2}.kind::f16
+//            (M=128*NCTA, N=BN, K=16) x4 per stage into a TMEM accumulator, tcgen05.commit releases
+//            the stage (`empty`, multicast to both CTAs) and finally signals `tmem_full`;
+//   warp 2   allocates / frees the 512 TMEM columns (double-buffered accumulator);
+//   warps 4-11 epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused epilogue straight from
+//            registers (each thread owns one output row: 64-128 contiguous bytes per burst; the
+//            residual add is a red.global.add.v4.f32), then release the accumulator (`tmem_empty`,
+//            remote arrive from the peer CTA) so the next tile's MMAs overlap.
 #include <mutex>
 
 #include "common.cuh"
@@ -28,28 +31,34 @@ namespace absb {
 
 namespace {
 
-constexpr int BM = 128;
-constexpr int BK = 64;  // bf16 elements = 128 bytes = one swizzle span
-constexpr int kStages = 4;
-constexpr int kThreads = 256;
+constexpr int BM = 128;  // rows of A per CTA (UMMA M = 128 * NCTA)
+constexpr int BK = 64;   // bf16 elements = 128 bytes = one swizzle span
+constexpr int kThreads = 384;  // TMA, MMA, TMEM-alloc, spare + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;
+constexpr int kTmemCols = 512;   // two accumulator stages at column 0 and 256
+constexpr int kAccStride = 256;
 
-template <int BN>
+template <int BN, int NCTA>
 struct SmemLayout {
+  static constexpr int kBRows = BN / NCTA;  // B rows this CTA stages (a pair splits the N tile)
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (216 * 1024) / kStageBytes;
   static constexpr int kBarOff = kStages * kStageBytes;
   // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr
   static constexpr int kTotal = kBarOff + (2 * kStages + 4) * 8 + 16;
   static constexpr int kDyn = kTotal + 1024;  // slack for manual 1024-byte alignment
+  static_assert(kBBytes % 1024 == 0, "SWIZZLE_128B tiles must stay 1024-byte aligned");
+  static_assert(kDyn <= 227 * 1024, "shared memory budget");
 };
 
 struct KernelParams {
   int M, N, K;
-  int tiles_m, tiles_n;
-  int num_kb;  // k-blocks per tile over all segments
-  int seg_kb;  // k-blocks per segment
+  int tiles_m, tiles_n;  // tiles_m counts (128 * NCTA)-row blocks
+  int n_fast;            // raster: 1 = consecutive tiles walk N (A tile shared), 0 = walk M (B tile shared)
+  int num_kb;            // k-blocks per tile over all segments
+  int seg_kb;            // k-blocks per segment
   int a_off[kMaxGemmSegs];
   int b_off[kMaxGemmSegs];
   void* out;
@@ -64,11 +73,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
 
-template <int BN, int EPI>
+__device__ __forceinline__ void tile_coords(const KernelParams& p, int tile, int& tm, int& tn) {
+  if (p.n_fast) {
+    tm = tile / p.tiles_n;
+    tn = tile - tm * p.tiles_n;
+  } else {
+    tn = tile / p.tiles_m;
+    tm = tile - tn * p.tiles_m;
+  }
+}
+
+template <int BN, int EPI, int NCTA>
 __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const KernelParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, NCTA>;
+  constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -80,6 +100,8 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
+  const int cta_rank = NCTA == 1 ? 0 : (int)tc::cluster_ctarank();
+  const int worker = blockIdx.x / NCTA, num_workers = gridDim.x / NCTA;  // a worker = one CTA or one CTA pair
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
@@ -92,34 +114,44 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(tmem_full + i, 1);
-      tc::mbar_init(tmem_empty + i, 4);  // one arrive per epilogue warp
+      tc::mbar_init(tmem_empty + i, 8 * NCTA);  // one arrive per epilogue warp of every CTA of the pair
     }
     tc::fence_barrier_init();
   }
   if (warp == 2) {
-    tc::tmem_alloc(tmem_slot, 2 * BN);
-    tc::tmem_relinquish();
+    tc::tmem_alloc<NCTA>(tmem_slot, kTmemCols);
+    tc::tmem_relinquish<NCTA>();
   }
   tc::tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 1) __syncthreads();
+  else tc::cluster_sync();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA stages its own A rows and its share of B) ========
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        // consecutive tiles share the B (weight) tile row-block: m fastest
-        const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        int tm, tn;
+        tile_coords(p, tile, tm, tn);
+        const int row_a = (tm * NCTA + cta_rank) * BM;
+        const int row_b = tn * BN + cta_rank * L::kBRows;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           const int seg = kb / p.seg_kb, within = kb - seg * p.seg_kb;
           tc::mbar_wait(empty_bar + stage, phase ^ 1);
-          tc::mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
           uint8_t* sa = smem + stage * L::kStageBytes;
-          tc::tma_load_2d(sa, &tmA, full_bar + stage, p.a_off[seg] + within * BK, tm * BM);
-          tc::tma_load_2d(sa + L::kABytes, &tmB, full_bar + stage, p.b_off[seg] + within * BK, tn * BN);
+          if constexpr (NCTA == 1) {
+            tc::mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
+            tc::tma_load_2d(sa, &tmA, full_bar + stage, p.a_off[seg] + within * BK, row_a);
+            tc::tma_load_2d(sa + L::kABytes, &tmB, full_bar + stage, p.b_off[seg] + within * BK, row_b);
+          } else {
+            // both CTAs' bytes are credited to the leader's barrier; only the leader arrives on it
+            if (cta_rank == 0) tc::mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes * NCTA);
+            tc::tma_load_2d_2cta(sa, &tmA, full_bar + stage, p.a_off[seg] + within * BK, row_a);
+            tc::tma_load_2d_2cta(sa + L::kABytes, &tmB, full_bar + stage, p.b_off[seg] + within * BK, row_b);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -128,17 +160,17 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM, BN);
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM * NCTA, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         tc::mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         tc::tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           tc::mbar_wait(full_bar + stage, phase);
           tc::tcgen05_fence_after();
@@ -148,15 +180,15 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
-            tc::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            tc::umma_bf16<NCTA>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc::umma_commit(empty_bar + stage);
+          tc::umma_commit<NCTA>(empty_bar + stage);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc::umma_commit(tmem_full + acc);
+        tc::umma_commit<NCTA>(tmem_full + acc);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -164,17 +196,24 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (every CTA drains its own 128 accumulator rows) ===============
+    // 8 warps: warp w reads TMEM lane quarter w % 4 (hardware restriction) and column half (w - 4) / 4.
+    // Each thread owns one output row: 32 consecutive columns per tcgen05.ld, written as 64-128
+    // contiguous bytes.  The residual add is a fire-and-forget red.global.add.v4.f32 (every element is
+    // touched by exactly one thread, so the result does not depend on timing).
+    const int q = warp & 3;
+    const int chalf = (warp - kEpiWarp0) >> 2;
+    const uint32_t tmem_empty_addr0 = NCTA == 1 ? 0u : tc::map_to_cta(tc::smem_u32(tmem_empty), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
-      const int row = tm * BM + q * 32 + lane;
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      int tm, tn;
+      tile_coords(p, tile, tm, tn);
+      const int row = (tm * NCTA + cta_rank) * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
       tc::mbar_wait(tmem_full + acc, acc_phase);
       tc::tcgen05_fence_after();
-      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
 
       if constexpr (EPI == EPI_SWIGLU_BF16) {
         // tile columns [0, BN/2) are gate rows, [BN/2, BN) the matching up rows
@@ -183,7 +222,7 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
         const int ocol0 = tn * H;
         const int ncols = p.N / 2;
 #pragma unroll 1
-        for (int c = 0; c < H; c += 32) {
+        for (int c = chalf * (H / 2); c < (chalf + 1) * (H / 2); c += 32) {
           uint32_t g[32], u[32];
           tc::tmem_ld_32x32(t_base + c, g);
           tc::tmem_ld_32x32(t_base + H + c, u);
@@ -206,7 +245,7 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
       } else {
         const int col0 = tn * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
           uint32_t v[32];
           tc::tmem_ld_32x32(t_base + c, v);
           tc::tmem_ld_wait();
@@ -230,29 +269,34 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
                                     pack_bf16x2(f[6], f[7]));
               }
             } else {
-              float* out = reinterpret_cast<float*>(p.out);
-              float4* dst = reinterpret_cast<float4*>(out + (size_t)row * p.ldc + col);
+              float* dst = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldc + col;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 float4 f = make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]),
                                        __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
                 if constexpr (EPI == EPI_F32_ADD) {
-                  const float4 o = dst[j];
-                  f.x += o.x; f.y += o.y; f.z += o.z; f.w += o.w;
-                } else if (p.bias) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j * 4));
-                  f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j * 4), "f"(f.x), "f"(f.y),
+                               "f"(f.z), "f"(f.w)
+                               : "memory");
+                } else {
+                  if (p.bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j * 4));
+                    f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
+                  }
+                  reinterpret_cast<float4*>(dst)[j] = f;
                 }
-                dst[j] = f;
               }
             }
           }
         }
       }
-      // accumulator drained: hand it back to the MMA warp
+      // accumulator drained: hand it back to the MMA warp of the leader CTA
       tc::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
+      if (lane == 0) {
+        if (NCTA == 1 || cta_rank == 0) tc::mbar_arrive(tmem_empty + acc);
+        else tc::mbar_arrive_cluster(tmem_empty_addr0 + (uint32_t)(acc * 8));
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -261,10 +305,11 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
   }
 
   tc::tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 1) __syncthreads();
+  else tc::cluster_sync();  // the peer may still be signalling this CTA's barriers / reading its smem
   if (warp == 2) {
     tc::tcgen05_fence_after();
-    tc::tmem_dealloc(tmem_base, 2 * BN);
+    tc::tmem_dealloc<NCTA>(tmem_base, kTmemCols);
   }
 }
 
@@ -303,20 +348,62 @@ CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, 
   return m;
 }
 
-template <int BN, int EPI>
-void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p, int sms, cudaStream_t st) {
-  auto kern = gemm_bf16_tc_kernel<BN, EPI>;
+template <int BN, int EPI, int NCTA>
+void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const void* B, int64_t b_rows, int64_t b_cols,
+            int64_t ldb, KernelParams p, int sms, cudaStream_t st) {
+  using L = SmemLayout<BN, NCTA>;
+  auto kern = gemm_bf16_tc_kernel<BN, EPI, NCTA>;
   static bool configured = false;  // per instantiation
   if (!configured) {
-    ABSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::kDyn));
+    ABSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn));
     configured = true;
   }
-  const int grid = std::min(p.tiles_m * p.tiles_n, sms);
-  kern<<<grid, kThreads, SmemLayout<BN>::kDyn, st>>>(tmA, tmB, p);
-  ABSB_CUDA(cudaGetLastError());
+  p.tiles_m = (int)ceil_div(p.M, BM * NCTA);
+  p.tiles_n = (int)ceil_div(p.N, BN);
+  // Few N tiles: walk N first so the CTAs running concurrently share A tiles (A is the big operand of the
+  // down/O projections and would otherwise be re-read from HBM once per N tile).  Many N tiles: walk M first
+  // so that they share the weight tile.
+  p.n_fast = p.tiles_n <= 16 ? 1 : 0;
+  const CUtensorMap tmA = make_tmap(A, a_rows, a_cols, lda, BM);
+  const CUtensorMap tmB = make_tmap(B, b_rows, b_cols, ldb, L::kBRows);
+  const int workers = std::max(1, std::min(p.tiles_m * p.tiles_n, sms / NCTA));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(workers * NCTA));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L::kDyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ABSB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
 }
 
+template <int BN, int NCTA>
+void launch_epi(int epi, const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const void* B, int64_t b_rows,
+                int64_t b_cols, int64_t ldb, const KernelParams& p, int sms, cudaStream_t st) {
+  switch (epi) {
+    case EPI_BF16_BIAS: launch<BN, EPI_BF16_BIAS, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st); break;
+    case EPI_F32_BIAS: launch<BN, EPI_F32_BIAS, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st); break;
+    case EPI_F32_ADD: launch<BN, EPI_F32_ADD, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st); break;
+    case EPI_SWIGLU_BF16:
+      if constexpr (BN == 256) {
+        launch<BN, EPI_SWIGLU_BF16, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st);
+        break;
+      }
+      fail(ABSB_ERR_INVALID, "SwiGLU epilogue needs 256-column tiles");
+    default: fail(ABSB_ERR_INVALID, "unknown epilogue %d", epi);
+  }
+}
+
+int g_gemm_variant = 0;  // 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3 = CTA pair x BN 192
+
 }  // namespace
+
+void gemm_set_variant(int v) { g_gemm_variant = v; }
 
 void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
                   int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st) {
@@ -324,13 +411,10 @@ void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, cons
   ABSB_CHECK(K > 0 && K % 8 == 0, ABSB_ERR_INVALID, "tcgen05 GEMM needs K %% 8 == 0 (K=%d)", K);
   ABSB_CHECK(N % 32 == 0, ABSB_ERR_INVALID, "tcgen05 GEMM needs N %% 32 == 0 (N=%d)", N);
   ABSB_CHECK(epi != EPI_SWIGLU_BF16 || N % 256 == 0, ABSB_ERR_INVALID, "SwiGLU epilogue needs N %% 256 == 0 (N=%d)", N);
-  constexpr int BN = 256;
   KernelParams p{};
   p.M = M;
   p.N = N;
   p.K = K;
-  p.tiles_m = (int)ceil_div(M, BM);
-  p.tiles_n = (int)ceil_div(N, BN);
   int64_t a_cols = K, b_cols = K;
   if (segs && segs->nseg > 0) {
     ABSB_CHECK(segs->nseg <= kMaxGemmSegs, ABSB_ERR_INVALID, "too many GEMM segments");
@@ -353,14 +437,30 @@ void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, cons
   p.out = out;
   p.ldc = ldc;
   p.bias = bias;
-  const CUtensorMap tmA = make_tmap(A, M, a_cols, lda, BM);
-  const CUtensorMap tmB = make_tmap(B, N, b_cols, ldb, BN);
-  switch (epi) {
-    case EPI_BF16_BIAS: launch<BN, EPI_BF16_BIAS>(tmA, tmB, p, sms, st); break;
-    case EPI_F32_BIAS: launch<BN, EPI_F32_BIAS>(tmA, tmB, p, sms, st); break;
-    case EPI_F32_ADD: launch<BN, EPI_F32_ADD>(tmA, tmB, p, sms, st); break;
-    case EPI_SWIGLU_BF16: launch<BN, EPI_SWIGLU_BF16>(tmA, tmB, p, sms, st); break;
-    default: fail(ABSB_ERR_INVALID, "unknown epilogue %d", epi);
+
+  // Tile shape: CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row block;
+  // 192-column tiles when they cut the work into fewer, fuller waves (N = 1536: 8 x 192 instead of 6 x 256).
+  int variant = g_gemm_variant;
+  if (variant == 0) {
+    if (M <= BM) {
+      variant = 1;
+    } else {
+      variant = 2;
+      if (epi != EPI_SWIGLU_BF16 && N % 192 == 0) {
+        const int64_t workers = std::max(1, sms / 2);
+        const int64_t tm = ceil_div(M, 2 * BM);
+        const int64_t cost256 = ceil_div(tm * ceil_div(N, 256), workers) * 256;
+        const int64_t cost192 = ceil_div(tm * ceil_div(N, 192), workers) * 192;
+        if (cost192 < cost256) variant = 3;
+      }
+    }
+  }
+  if (variant == 3 && epi == EPI_SWIGLU_BF16) variant = 2;
+  switch (variant) {
+    case 1: launch_epi<256, 1>(epi, A, M, a_cols, lda, B, N, b_cols, ldb, p, sms, st); break;
+    case 2: launch_epi<256, 2>(epi, A, M, a_cols, lda, B, N, b_cols, ldb, p, sms, st); break;
+    case 3: launch_epi<192, 2>(epi, A, M, a_cols, lda, B, N, b_cols, ldb, p, sms, st); break;
+    default: fail(ABSB_ERR_INVALID, "unknown GEMM variant %d", variant);
   }
 }
 
@@ -411,6 +511,13 @@ void gemm_split3_f32(int M, int N, int K, const void* A3, const void* B3, float*
 }
 
 }  // namespace absb
+
+extern "C" int absb_gemm_set_variant(int variant) {
+  ABSB_API_BEGIN
+  ABSB_CHECK(variant >= 0 && variant <= 3, ABSB_ERR_INVALID, "GEMM variant %d outside [0,3]", variant);
+  absb::gemm_set_variant(variant);
+  ABSB_API_END
+}
 
 extern "C" int absb_gemm_bf16_dev(int device, int M, int N, int K, const void* A_dev, const void* B_dev, float* C_dev,
                                   void* stream) {

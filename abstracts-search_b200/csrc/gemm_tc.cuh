@@ -29,6 +29,9 @@ struct GemmSegs {
 void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
                   int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st);
 
+// test hook: 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3 = CTA pair x BN 192
+void gemm_set_variant(int v);
+
 // fp32 [rows,K] -> bf16 [rows, 3K] = [hi | mid | lo]
 void split3_bf16(int64_t rows, int K, const float* x, void* out, cudaStream_t st);
 // S[M,N] (fp32, pitch lds) = A * B^T from split operands A3 [M,3K], B3 [N,3K]

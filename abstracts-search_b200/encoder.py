@@ -326,6 +326,11 @@ class Encoder:
 SentenceTransformer = Encoder
 
 
+def gemm_set_variant(variant: int = 0):
+    """Test hook: 0 auto, 1 = one CTA 128x256 tiles, 2 = CTA pair 256x256, 3 = CTA pair 256x192."""
+    check(lib().absb_gemm_set_variant(int(variant)))
+
+
 def gemm_bf16(A, B):
     """C[M,N] fp32 = A[M,K] @ B[N,K]^T on tcgen05 (CUDA bf16 tensors) — test / micro-benchmark hook."""
     import torch

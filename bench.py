@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--query-tokens", type=int, default=32)
     ap.add_argument("--coarse-impl", type=int, default=1, help="0 fp32 FFMA GEMM, 1 tcgen05 split-bf16 GEMM")
     ap.add_argument("--scan-chunk", type=int, default=-1)
+    ap.add_argument("--gemm-variant", type=int, default=0, help="tcgen05 GEMM tile shape (0 auto; see absb_gemm_set_variant)")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not time individual kernels in the timed region")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -291,6 +292,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     nq, S, k = args.batch, args.query_tokens, args.k
     per = nq // world
 
+    if args.gemm_variant:
+        importlib.import_module("abstracts-search_b200.encoder").gemm_set_variant(args.gemm_variant)
     enc = P.Encoder(config=P.STELLA_1_5B, device=device, random_init_seed=0)
     ix, build_s = build_shard(P, torch, args, rank, world, dev)
     ix.nprobe = args.nprobe

@@ -240,6 +240,9 @@ int absb_enc_get_profile(absb_enc_t e, double* gemm_ms, double* gemm_flops, doub
 
 /* Stand-alone GEMM entry used by tests and the micro-benchmark: C[M,N] (fp32) = A[M,K] * B[N,K]^T
  * with bf16 operands on tcgen05 (DEVICE pointers; K % 64 == 0). */
+/* Test hook: force the tile shape of the tcgen05 GEMM (0 = automatic; 1 = one CTA, 128x256 tiles;
+ * 2 = CTA pair (cta_group::2), 256x256 tiles; 3 = CTA pair, 256x192 tiles). Process-wide. */
+int absb_gemm_set_variant(int variant);
 int absb_gemm_bf16_dev(int device, int M, int N, int K, const void* A_dev, const void* B_dev,
                        float* C_dev, void* stream);
 

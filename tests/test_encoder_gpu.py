@@ -27,9 +27,13 @@ def _loaded(P, base, sd):
     return enc
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1, 32, 64), (300, 512, 192), (129, 1536, 1536),
-                                    (1000, 2048, 1536), (2048, 1536, 8960), (77, 96, 72)])
-def test_tcgen05_gemm_matches_torch(gpu_pkg, M, N, K):
+                                    (1000, 2048, 1536), (2048, 1536, 8960), (77, 96, 72), (4096, 768, 512),
+                                    (257, 192, 128), (40000, 384, 256)])
+def test_tcgen05_gemm_matches_torch(gpu_pkg, M, N, K, variant):
+    """Every tile shape of the kernel (one CTA / CTA pair with cta_group::2, 256- and 192-column tiles),
+    ragged M and N, many tiles per CTA (TMEM double buffering, pipeline phase wrap-around)."""
     import torch
     from importlib import import_module
 
@@ -37,9 +41,13 @@ def test_tcgen05_gemm_matches_torch(gpu_pkg, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
     A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
     B = torch.randn((N, K), device="cuda", generator=g).to(torch.bfloat16)
-    C = enc.gemm_bf16(A, B)
+    enc.gemm_set_variant(variant)
+    try:
+        C = enc.gemm_bf16(A, B)
+        torch.cuda.synchronize()
+    finally:
+        enc.gemm_set_variant(0)
     ref = A.float() @ B.float().T
-    torch.cuda.synchronize()
     err = (C - ref).abs().max().item()
     # fp32 accumulation of exact bf16 products: error ~ K * 2^-24 * |a||b|
     assert err < 2e-3 * max(1.0, K / 256), (M, N, K, err)
@@ -53,9 +61,14 @@ def test_tcgen05_gemm_integer_inputs_are_exact(gpu_pkg):
     g = torch.Generator(device="cuda").manual_seed(0)
     A = torch.randint(-8, 9, (515, 1024), device="cuda", generator=g).to(torch.bfloat16)
     B = torch.randint(-8, 9, (640, 1024), device="cuda", generator=g).to(torch.bfloat16)
-    C = enc.gemm_bf16(A, B)
     ref = (A.double() @ B.double().T).float()
-    assert torch.equal(C, ref)
+    for variant in (1, 2, 3, 0):
+        enc.gemm_set_variant(variant)
+        try:
+            C = enc.gemm_bf16(A, B)
+        finally:
+            enc.gemm_set_variant(0)
+        assert torch.equal(C, ref), variant
 
 
 def test_weight_roundtrip(gpu_pkg):

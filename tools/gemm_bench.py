@@ -1,0 +1,48 @@
+"""Micro-benchmark of the tcgen05 GEMM on the encoder's shapes against cuBLAS (torch.matmul), every
+tile variant.  Run under gpurun: python tools/gemm_bench.py [tokens]"""
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+enc = importlib.import_module("abstracts-search_b200.encoder")
+
+
+def timeit(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    T = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+    shapes = [("qkv", T, 2048, 1536), ("o", T, 1536, 1536), ("ffn_in", T, 17920, 1536), ("ffn_down", T, 1536, 8960)]
+    for name, M, N, K in shapes:
+        A = torch.randn((M, K), device="cuda").to(torch.bfloat16)
+        B = torch.randn((N, K), device="cuda").to(torch.bfloat16)
+        fl = 2.0 * M * N * K
+        ms = timeit(lambda: torch.matmul(A, B.T))
+        row = [f"{name:9s} M={M} N={N} K={K}  cuBLAS {ms*1e3:7.1f} us {fl/ms/1e9:7.0f} TF"]
+        for v in (1, 2, 3):
+            enc.gemm_set_variant(v)
+            try:
+                ms = timeit(lambda: enc.gemm_bf16(A, B))
+                row.append(f"v{v} {ms*1e3:7.1f} us {fl/ms/1e9:7.0f} TF")
+            except Exception as e:  # noqa: BLE001
+                row.append(f"v{v} failed: {e}")
+        enc.gemm_set_variant(0)
+        print(" | ".join(row), flush=True)
+
+
+if __name__ == "__main__":
+    main()
