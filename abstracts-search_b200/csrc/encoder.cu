@@ -85,26 +85,6 @@ __global__ void rmsnorm_kernel(int64_t T, int H, float eps, const float* __restr
   }
 }
 
-// Rotate-half RoPE in place on the q and k heads of the fused qkv buffer [T, (nh + 2 nkv) * hd].
-// cs: [max_seq, hd/2] float2 (cos, sin).  One thread per (token, head, i < hd/2).
-__global__ void rope_kernel(int64_t T, int S, int nheads_qk, int hd, int ld, bf16* __restrict__ qkv,
-                            const float2* __restrict__ cs) {
-  const int half = hd / 2;
-  const int64_t total = T * nheads_qk * half;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(i % half);
-    const int64_t r = i / half;
-    const int head = (int)(r % nheads_qk);
-    const int64_t t = r / nheads_qk;
-    const int pos = (int)(t % S);
-    bf16* p = qkv + (size_t)t * ld + (size_t)head * hd;
-    const float x1 = __bfloat162float(p[j]), x2 = __bfloat162float(p[j + half]);
-    const float2 c = __ldg(cs + (size_t)pos * half + j);
-    p[j] = __float2bfloat16_rn(x1 * c.x - x2 * c.y);
-    p[j + half] = __float2bfloat16_rn(x2 * c.x + x1 * c.y);
-  }
-}
-
 // Masked mean pool of the final-normed hidden states: pooled[b, j] = w[j] * sum_s m[b,s] *
 // h[b,s,j] * rinv[b,s] / max(sum_s m[b,s], 1e-9)   (sentence-transformers Pooling, mean mode).
 __global__ void pool_kernel(int S, int H, const float* __restrict__ h, const float* __restrict__ rinv,
@@ -137,8 +117,8 @@ __global__ void l2norm_kernel(int64_t B, int E, float* __restrict__ x) {
 }
 
 // ------------------------------------------------------------------ attention ---------------
-// Flash-style attention on mma.sync m16n8k16 (bf16 in, fp32 accumulate), head_dim 128.
-// grid (ceil(S/64), num_heads, B); 4 warps, 16 query rows each; 64-key tiles staged in shared memory.
+// Flash-style attention on mma.sync m16n8k16 (bf16 in, fp32 accumulate), head_dim 128; 64-key tiles
+// staged in shared memory and shared by the q heads of one kv head.
 constexpr int kHD = 128;
 constexpr int kKT = 64;         // keys per tile
 constexpr int kRowPad = kHD + 8;  // 272-byte rows: conflict-free fragment loads and ldmatrix
@@ -155,31 +135,42 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ __launch_bounds__(128) void attention_kernel(const bf16* __restrict__ qkv, int ld, const int* __restrict__ mask,
-                                                        bf16* __restrict__ out, int ldo, int S, int nh, int nkv,
-                                                        int causal, float scale_log2) {
+constexpr int kAttnWarps = 12;
+
+// One CTA per (batch, kv head, block of 12 work units); a unit = 16 query rows of one of the q heads
+// that share this kv head (GQA), one warp per unit, so K/V tiles are staged once for all of them.
+__global__ __launch_bounds__(kAttnWarps * 32) void attention_kernel(const bf16* __restrict__ qkv, int ld,
+                                                                  const int* __restrict__ mask, bf16* __restrict__ out,
+                                                                  int ldo, int S, int nh, int nkv, int causal,
+                                                                  float scale_log2) {
   __shared__ __align__(16) bf16 sK[kKT][kRowPad];
   __shared__ __align__(16) bf16 sV[kKT][kRowPad];
   __shared__ float sBias[kKT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-  const int kvh = head / (nh / nkv);
+  const int kvh = blockIdx.y, b = blockIdx.z;
+  const int group = nh / nkv;
+  const int nblk = (S + 15) / 16;
+  const int unit = blockIdx.x * kAttnWarps + warp;
+  const bool active = unit < group * nblk;
+  const int head = kvh * group + (active ? unit / nblk : 0);
+  const int rb = active ? unit % nblk : 0;
   const int64_t tok0 = (int64_t)b * S;
   const bf16* Qb = qkv + (size_t)head * kHD;
   const bf16* Kb = qkv + (size_t)(nh + kvh) * kHD;
   const bf16* Vb = qkv + (size_t)(nh + nkv + kvh) * kHD;
 
-  const int r0 = qt * 64 + warp * 16 + g, r1 = r0 + 8;
+  const int r0 = rb * 16 + g, r1 = r0 + 8;
   uint32_t qa[kHD / 16][4];
 #pragma unroll
   for (int ks = 0; ks < kHD / 16; ++ks) {
     const int c = ks * 16 + t4 * 2;
-    qa[ks][0] = r0 < S ? *reinterpret_cast<const uint32_t*>(Qb + (size_t)(tok0 + r0) * ld + c) : 0u;
-    qa[ks][1] = r1 < S ? *reinterpret_cast<const uint32_t*>(Qb + (size_t)(tok0 + r1) * ld + c) : 0u;
-    qa[ks][2] = r0 < S ? *reinterpret_cast<const uint32_t*>(Qb + (size_t)(tok0 + r0) * ld + c + 8) : 0u;
-    qa[ks][3] = r1 < S ? *reinterpret_cast<const uint32_t*>(Qb + (size_t)(tok0 + r1) * ld + c + 8) : 0u;
+    const bool ok0 = active && r0 < S, ok1 = active && r1 < S;
+    qa[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(Qb + (size_t)(tok0 + r0) * ld + c) : 0u;
+    qa[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(Qb + (size_t)(tok0 + r1) * ld + c) : 0u;
+    qa[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(Qb + (size_t)(tok0 + r0) * ld + c + 8) : 0u;
+    qa[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(Qb + (size_t)(tok0 + r1) * ld + c + 8) : 0u;
   }
 
   float o[kHD / 8][4];
@@ -187,9 +178,18 @@ __global__ __launch_bounds__(128) void attention_kernel(const bf16* __restrict__
   for (int i = 0; i < kHD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  int kmax = S;
-  if (causal) kmax = min(S, qt * 64 + 64);
-  for (int k0 = 0; k0 < kmax; k0 += kKT) {
+  // keys needed by this CTA: all of them, or (causal) up to the last row of its last unit
+  int kmax_cta = S;
+  if (causal) {
+    const int last_unit = min((int)(blockIdx.x + 1) * kAttnWarps, group * nblk) - 1;
+    const int first_unit = blockIdx.x * kAttnWarps;
+    // units of several heads may share the CTA: the largest row block among them bounds the keys
+    int rb_max = 0;
+    for (int u = first_unit; u <= last_unit; ++u) rb_max = max(rb_max, u % nblk);
+    kmax_cta = min(S, rb_max * 16 + 16);
+  }
+  const int kmax_warp = causal ? min(S, rb * 16 + 16) : S;
+  for (int k0 = 0; k0 < kmax_cta; k0 += kKT) {
     __syncthreads();  // previous tile fully consumed
     // stage K, V tiles: 64 rows x 16 chunks of 16 bytes
     for (int i = threadIdx.x; i < kKT * (kHD / 8); i += blockDim.x) {
@@ -208,17 +208,22 @@ __global__ __launch_bounds__(128) void attention_kernel(const bf16* __restrict__
       sBias[threadIdx.x] = (key < S && mask[tok0 + key] != 0) ? 0.f : -INFINITY;
     }
     __syncthreads();
+    if (!active || k0 >= kmax_warp) continue;
+    // 8-key column blocks of this tile that hold any key at all (short sequences: skip the padding)
+    const int nb_valid = min(kKT, S - k0 + 7) / 8;
 
     // S = Q K^T for this warp's 16 rows x 64 keys
     float s[kKT / 8][4];
 #pragma unroll
     for (int nb = 0; nb < kKT / 8; ++nb) {
       s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+      if (nb < nb_valid) {
 #pragma unroll
-      for (int ks = 0; ks < kHD / 16; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sK[nb * 8 + g][ks * 16 + t4 * 2]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[nb * 8 + g][ks * 16 + t4 * 2 + 8]);
-        mma_bf16_16816(s[nb], qa[ks], b0, b1);
+        for (int ks = 0; ks < kHD / 16; ++ks) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sK[nb * 8 + g][ks * 16 + t4 * 2]);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[nb * 8 + g][ks * 16 + t4 * 2 + 8]);
+          mma_bf16_16816(s[nb], qa[ks], b0, b1);
+        }
       }
     }
     // scale, mask, running max
@@ -269,6 +274,7 @@ __global__ __launch_bounds__(128) void attention_kernel(const bf16* __restrict__
     // O += P V
 #pragma unroll
     for (int kk = 0; kk < kKT / 16; ++kk) {
+      if (kk * 2 >= nb_valid) continue;  // 16-key block entirely past the sequence: P = 0 there
       uint32_t pa[4];
       pa[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
       pa[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
@@ -287,6 +293,7 @@ __global__ __launch_bounds__(128) void attention_kernel(const bf16* __restrict__
       }
     }
   }
+  if (!active) return;
   l0 += __shfl_xor_sync(kFull, l0, 1);
   l0 += __shfl_xor_sync(kFull, l0, 2);
   l1 += __shfl_xor_sync(kFull, l1, 1);
@@ -599,9 +606,9 @@ struct Encoder {
   };
 
   void gemm(int epi, int M, int N, int K, const void* A, const void* W, void* out, int64_t ldc, const float* bias,
-            cudaStream_t st) {
+            cudaStream_t st, const GemmRope* rope = nullptr) {
     Span sp(this, st, 0);
-    gemm_bf16_tc(epi, M, N, K, A, K, W, K, out, ldc, bias, nullptr, props.sm_count, st);
+    gemm_bf16_tc(epi, M, N, K, A, K, W, K, out, ldc, bias, nullptr, props.sm_count, st, rope);
     last_flops += 2.0 * M * N * K;
     if (profile) prof_gemm_flops += 2.0 * M * N * K;
     ++last_launches;
@@ -635,16 +642,19 @@ struct Encoder {
         rmsnorm_kernel<bf16><<<wblocks, 256, 0, st>>>(T, H, cfg.rms_eps, h.p, L.ln1.p, xn.p, nullptr);
         ABSB_CUDA(cudaGetLastError());
       }
-      gemm(EPI_BF16_BIAS, (int)T, QKV, H, xn.p, L.wqkv.p, qkv.p, QKV, L.bqkv.p, st);
       {
-        Span sp(this, st, 2);
-        rope_kernel<<<blocks_for(T * (nh + nkv) * (kHD / 2)), 256, 0, st>>>(T, S, nh + nkv, kHD, QKV, qkv.p, rope_cs.p);
-        ABSB_CUDA(cudaGetLastError());
+        // QKV projection with bias and RoPE (q and k heads) fused into the epilogue
+        GemmRope rope;
+        rope.cs = rope_cs.p;
+        rope.S = S;
+        rope.cols = (nh + nkv) * kHD;
+        gemm(EPI_BF16_BIAS_ROPE, (int)T, QKV, H, xn.p, L.wqkv.p, qkv.p, QKV, L.bqkv.p, st, &rope);
       }
       {
         Span sp(this, st, 1);
-        dim3 grid((unsigned)ceil_div(S, 64), (unsigned)nh, (unsigned)B);
-        attention_kernel<<<grid, 128, 0, st>>>(qkv.p, QKV, mask, ao.p, nh * kHD, S, nh, nkv, cfg.causal, scale_log2);
+        const int units = (nh / nkv) * (int)ceil_div(S, 16);
+        dim3 grid((unsigned)ceil_div(units, kAttnWarps), (unsigned)nkv, (unsigned)B);
+        attention_kernel<<<grid, kAttnWarps * 32, 0, st>>>(qkv.p, QKV, mask, ao.p, nh * kHD, S, nh, nkv, cfg.causal, scale_log2);
         ABSB_CUDA(cudaGetLastError());
       }
       last_flops += 4.0 * (double)B * S * S * kHD * nh;
@@ -656,7 +666,7 @@ struct Encoder {
       }
       gemm(EPI_SWIGLU_BF16, (int)T, 2 * I, H, xn.p, L.wgu.p, act.p, I, nullptr, st);
       gemm(EPI_F32_ADD, (int)T, H, I, act.p, L.wd.p, h.p, H, nullptr, st);
-      last_launches += 4;
+      last_launches += 3;
     }
     {
       Span sp(this, st, 2);

@@ -64,6 +64,8 @@ struct KernelParams {
   void* out;
   int64_t ldc;
   const float* bias;
+  const float2* rope_cs;  // EPI_BF16_BIAS_ROPE only
+  int rope_S, rope_cols;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -242,6 +244,57 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
             }
           }
         }
+      } else if constexpr (EPI == EPI_BF16_BIAS_ROPE) {
+        // this warp's column half is exactly one 128-wide head: rotate-half pairs (j, j + 64)
+        static_assert(BN == 256, "the RoPE epilogue maps one head to one epilogue warp pair");
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+        const int hc = tn * BN + chalf * 128;  // first column of the head
+        const bool rotate = hc < p.rope_cols;
+        const float2* cs = p.rope_cs + (size_t)(row_ok ? row % p.rope_S : 0) * 64;
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t v1[32], v2[32];
+          tc::tmem_ld_32x32(t_base + chalf * 128 + c, v1);
+          tc::tmem_ld_32x32(t_base + chalf * 128 + 64 + c, v2);
+          tc::tmem_ld_wait();
+          if (row_ok && hc < p.N) {
+            uint4* dst1 = reinterpret_cast<uint4*>(out + (size_t)row * p.ldc + hc + c);
+            uint4* dst2 = reinterpret_cast<uint4*>(out + (size_t)row * p.ldc + hc + 64 + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a[8], b[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                a[e] = __uint_as_float(v1[j * 8 + e]);
+                b[e] = __uint_as_float(v2[j * 8 + e]);
+              }
+              if (p.bias) {
+#pragma unroll
+                for (int e = 0; e < 8; e += 4) {
+                  const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + hc + c + j * 8 + e));
+                  const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + hc + 64 + c + j * 8 + e));
+                  a[e] += ba.x; a[e + 1] += ba.y; a[e + 2] += ba.z; a[e + 3] += ba.w;
+                  b[e] += bb.x; b[e + 1] += bb.y; b[e + 2] += bb.z; b[e + 3] += bb.w;
+                }
+              }
+              if (rotate) {
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(cs + c + j * 8 + e));  // cos0 sin0 cos1 sin1
+                  const float x0 = a[e], y0 = b[e], x1 = a[e + 1], y1 = b[e + 1];
+                  a[e] = x0 * t.x - y0 * t.y;
+                  b[e] = y0 * t.x + x0 * t.y;
+                  a[e + 1] = x1 * t.z - y1 * t.w;
+                  b[e + 1] = y1 * t.z + x1 * t.w;
+                }
+              }
+              dst1[j] = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]),
+                                   pack_bf16x2(a[6], a[7]));
+              dst2[j] = make_uint4(pack_bf16x2(b[0], b[1]), pack_bf16x2(b[2], b[3]), pack_bf16x2(b[4], b[5]),
+                                   pack_bf16x2(b[6], b[7]));
+            }
+          }
+        }
       } else {
         const int col0 = tn * BN;
 #pragma unroll 1
@@ -395,6 +448,12 @@ void launch_epi(int epi, const void* A, int64_t a_rows, int64_t a_cols, int64_t 
         break;
       }
       fail(ABSB_ERR_INVALID, "SwiGLU epilogue needs 256-column tiles");
+    case EPI_BF16_BIAS_ROPE:
+      if constexpr (BN == 256) {
+        launch<BN, EPI_BF16_BIAS_ROPE, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st);
+        break;
+      }
+      fail(ABSB_ERR_INVALID, "RoPE epilogue needs 256-column tiles");
     default: fail(ABSB_ERR_INVALID, "unknown epilogue %d", epi);
   }
 }
@@ -406,8 +465,10 @@ int g_gemm_variant = 0;  // 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3
 void gemm_set_variant(int v) { g_gemm_variant = v; }
 
 void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
-                  int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st) {
+                  int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st, const GemmRope* rope) {
   if (M == 0 || N == 0) return;
+  ABSB_CHECK(epi != EPI_BF16_BIAS_ROPE || (rope && rope->cs && rope->S >= 1 && rope->cols % 128 == 0 && N % 128 == 0),
+             ABSB_ERR_INVALID, "RoPE epilogue needs a table, S >= 1 and 128-wide heads");
   ABSB_CHECK(K > 0 && K % 8 == 0, ABSB_ERR_INVALID, "tcgen05 GEMM needs K %% 8 == 0 (K=%d)", K);
   ABSB_CHECK(N % 32 == 0, ABSB_ERR_INVALID, "tcgen05 GEMM needs N %% 32 == 0 (N=%d)", N);
   ABSB_CHECK(epi != EPI_SWIGLU_BF16 || N % 256 == 0, ABSB_ERR_INVALID, "SwiGLU epilogue needs N %% 256 == 0 (N=%d)", N);
@@ -437,6 +498,12 @@ void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, cons
   p.out = out;
   p.ldc = ldc;
   p.bias = bias;
+  if (rope) {
+    p.rope_cs = rope->cs;
+    p.rope_S = rope->S;
+    p.rope_cols = rope->cols;
+  }
+  const bool needs256 = epi == EPI_SWIGLU_BF16 || epi == EPI_BF16_BIAS_ROPE;
 
   // Tile shape: CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row block;
   // 192-column tiles when they cut the work into fewer, fuller waves (N = 1536: 8 x 192 instead of 6 x 256).
@@ -446,7 +513,7 @@ void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, cons
       variant = 1;
     } else {
       variant = 2;
-      if (epi != EPI_SWIGLU_BF16 && N % 192 == 0) {
+      if (!needs256 && N % 192 == 0) {
         const int64_t workers = std::max(1, sms / 2);
         const int64_t tm = ceil_div(M, 2 * BM);
         const int64_t cost256 = ceil_div(tm * ceil_div(N, 256), workers) * 256;
@@ -455,7 +522,7 @@ void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, cons
       }
     }
   }
-  if (variant == 3 && epi == EPI_SWIGLU_BF16) variant = 2;
+  if (variant == 3 && needs256) variant = 2;
   switch (variant) {
     case 1: launch_epi<256, 1>(epi, A, M, a_cols, lda, B, N, b_cols, ldb, p, sms, st); break;
     case 2: launch_epi<256, 2>(epi, A, M, a_cols, lda, B, N, b_cols, ldb, p, sms, st); break;

@@ -12,6 +12,16 @@ enum GemmEpilogue {
   EPI_F32_ADD = 2,      // out f32  [M,N]  += acc                      (residual stream)
   EPI_SWIGLU_BF16 = 3,  // out bf16 [M,N/2] = silu(gate) * up, weight rows interleaved per 256-row
                         //                    tile: [128 gate rows | 128 up rows]
+  EPI_BF16_BIAS_ROPE = 4,  // EPI_BF16_BIAS + rotate-half RoPE on the 128-wide heads that start below
+                           // rope.cols (the q and k heads of the fused QKV projection)
+};
+
+// RoPE side input of EPI_BF16_BIAS_ROPE: cs[pos, i] = (cos, sin) of pos * inv_freq[i], i < 64;
+// the position of GEMM row r is r % S.
+struct GemmRope {
+  const float2* cs = nullptr;
+  int S = 1;
+  int cols = 0;
 };
 
 constexpr int kMaxGemmSegs = 8;
@@ -27,7 +37,8 @@ struct GemmSegs {
 
 // C[M,N] = A[M,K] * B[N,K]^T; A, B bf16 with row pitches lda, ldb (elements).
 void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
-                  int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st);
+                  int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st,
+                  const GemmRope* rope = nullptr);
 
 // test hook: 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3 = CTA pair x BN 192
 void gemm_set_variant(int v);

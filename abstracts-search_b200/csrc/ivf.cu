@@ -666,8 +666,13 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
     if (stats_pending) fold_stats();  // only one plan's numbers fit in ws_stats
     {
       Span sp(this, st, 2);
+      const size_t npairs_max = (size_t)kMaxPlanQueries * nprobe;
+      ws_pair_counts.reserve(npairs_max + 1);
+      ws_pair_offs.reserve(npairs_max + 1);
+      ws_plan_tmp.reserve(plan_scan_tmp_bytes((int)npairs_max) + 16);
       launch_plan(table(), coarse + q0 * nprobe, nb, nprobe, scan_chunk, (int)max_items, ws_items.p,
-                  ws_q_begin.p, ws_counters.p, ws_counters.p + 1, ws_stats.p, st);
+                  ws_q_begin.p, ws_counters.p, ws_counters.p + 1, ws_stats.p, ws_pair_counts.p, ws_pair_offs.p,
+                  ws_plan_tmp.p, ws_plan_tmp.cap, st);
     }
     ScanLaunch a;
     a.Q = q + q0 * d;
@@ -691,7 +696,7 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
     last_scan = a;
     have_last_scan = true;
     stats_pending = true;
-    stats.launches += 3;
+    stats.launches += 5;
     if (q0 + nb_max < nq) fold_stats();
   }
 }

@@ -77,6 +77,8 @@ struct IvfIndex {
   DBuf<float> ws_part_s;
   DBuf<long long> ws_part_id;
   DBuf<int> ws_q_begin;
+  DBuf<int> ws_pair_counts, ws_pair_offs;  // plan: items per (query, probe) pair and their prefix sums
+  DBuf<unsigned char> ws_plan_tmp;
   DBuf<int> ws_counters;  // [0] n_items, [1] queue counter
   DBuf<unsigned long long> ws_stats;
   DBuf<unsigned char> ws_cub;

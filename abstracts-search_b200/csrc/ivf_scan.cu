@@ -18,6 +18,8 @@
 //     WarpTopK.  No shared memory, no block barrier, no intermediate score array.
 //   * Each item emits k partial results; merge_partials (dense.cu) reduces them per query.
 // Algorithmic bytes per launch = sum over items of len * (4 d + 8).
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 #include "ivf_scan.cuh"
 #include "topk.cuh"
@@ -27,8 +29,8 @@ namespace absb {
 namespace {
 
 // ------------------------------------------------------------------ plan --------------------
-// One CTA of 1024 threads.  Warp w handles queries w, w+32, ...; lanes stride over probes.
-// Pass 1 counts items per query, a block scan turns counts into q_begin, pass 2 emits items.
+// count (one thread per (query, probe) pair) -> exclusive scan (cub) -> emit: three small grid-wide
+// launches instead of one serial CTA.
 __device__ __forceinline__ int walk_list(const ListTable& lt, long long l, int chunk, int q,
                                          ScanItem* out /* nullptr = count only */,
                                          long long* vectors) {
@@ -72,94 +74,38 @@ __device__ __forceinline__ int walk_list(const ListTable& lt, long long l, int c
   return n;
 }
 
-__global__ __launch_bounds__(1024) void plan_kernel(ListTable lt, const long long* __restrict__ coarse,
-                                                   int nq, int nprobe, int chunk, int max_items,
-                                                   ScanItem* __restrict__ items,
-                                                   int* __restrict__ q_begin /* [nq+1] */,
-                                                   int* __restrict__ n_items,
-                                                   int* __restrict__ queue_counter,
-                                                   unsigned long long* __restrict__ stats) {
-  __shared__ int q_count[kMaxPlanQueries];
-  __shared__ int warp_tot[32];
-  __shared__ unsigned long long sm_vectors;
-  __shared__ int sm_total;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) sm_vectors = 0;
-  for (int q = threadIdx.x; q < kMaxPlanQueries; q += blockDim.x) q_count[q] = 0;
-  __syncthreads();
-
-  // pass 1: count
+// Pass 1: one thread per (query, probe) pair counts the work items of that list.
+__global__ void plan_count_kernel(ListTable lt, const long long* __restrict__ coarse, int npairs, int chunk,
+                                  int* __restrict__ counts /* [npairs + 1] */,
+                                  unsigned long long* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   long long vec = 0;
-  for (int q = warp; q < nq; q += 32) {
-    int c = 0;
-    for (int p = lane; p < nprobe; p += 32)
-      c += walk_list(lt, coarse[(size_t)q * nprobe + p], chunk, q, nullptr, &vec);
+  if (i < npairs) counts[i] = walk_list(lt, coarse[i], chunk, 0, nullptr, &vec);
+  if (i == npairs) counts[i] = 0;
+  // vectors scanned = sum of probed list sizes (statistics only)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFullMask, c, o);
-    if (lane == 0) q_count[q] = c;
-  }
-  if (vec) atomicAdd(&sm_vectors, (unsigned long long)vec);
-  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) vec += __shfl_xor_sync(kFullMask, vec, o);
+  if ((threadIdx.x & 31) == 0 && vec) atomicAdd(&stats[0], (unsigned long long)vec);
+}
 
-  // block exclusive scan over q_count[0..kMaxPlanQueries)  (1024 threads, one element each)
-  {
-    const int t = threadIdx.x;
-    int v = (t < kMaxPlanQueries) ? q_count[t] : 0;
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(kFullMask, incl, o);
-      if (lane >= o) incl += y;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int w = warp_tot[lane];
-      int wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(kFullMask, wi, o);
-        if (lane >= o) wi += y;
-      }
-      warp_tot[lane] = wi - w;  // exclusive
-    }
-    __syncthreads();
-    const int excl = warp_tot[warp] + incl - v;
-    if (t < kMaxPlanQueries) q_count[t] = excl;
-    __syncthreads();
-    if (t < nq) q_begin[t] = excl;
-    if (t == nq - 1) {
-      const int total = excl + v;
-      q_begin[nq] = total;
-      sm_total = total;
-      *n_items = total <= max_items ? total : -1;  // -1: capacity bug, scan does nothing
-      *queue_counter = 0;
-      stats[0] = sm_vectors;
-      stats[1] = (unsigned long long)total;
-    }
+// Pass 3 (after an exclusive scan of the counts): every pair writes its items at its offset.
+__global__ void plan_emit_kernel(ListTable lt, const long long* __restrict__ coarse, int nq, int nprobe, int chunk,
+                                 int max_items, const int* __restrict__ offs /* [npairs + 1] */,
+                                 ScanItem* __restrict__ items, int* __restrict__ q_begin /* [nq + 1] */,
+                                 int* __restrict__ n_items, int* __restrict__ queue_counter,
+                                 unsigned long long* __restrict__ stats) {
+  const int npairs = nq * nprobe;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = offs[npairs];
+  if (i == 0) {
+    *n_items = total <= max_items ? total : -1;  // -1: capacity bug, the scan does nothing
+    *queue_counter = 0;
+    stats[1] = (unsigned long long)total;
   }
-  __syncthreads();
-  if (sm_total > max_items) return;
-
-  // pass 2: emit.  Lane offsets inside a query via warp exclusive scan of per-probe counts.
-  for (int q = warp; q < nq; q += 32) {
-    int base = q_count[q];
-    for (int p0 = 0; p0 < nprobe; p0 += 32) {
-      const int p = p0 + lane;
-      const long long l = p < nprobe ? coarse[(size_t)q * nprobe + p] : -1;
-      const int c = walk_list(lt, l, chunk, q, nullptr, nullptr);
-      int incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(kFullMask, incl, o);
-        if (lane >= o) incl += y;
-      }
-      const int tot = __shfl_sync(kFullMask, incl, 31);
-      const int off = base + incl - c;
-      if (c > 0 && off + c <= max_items) walk_list(lt, l, chunk, q, items + off, nullptr);
-      base += tot;
-    }
-  }
+  if (i <= nq) q_begin[i] = offs[min(i * nprobe, npairs)];
+  if (i >= npairs || total > max_items) return;
+  const int off = offs[i];
+  if (offs[i + 1] > off) walk_list(lt, coarse[i], chunk, i / nprobe, items + off, nullptr);
 }
 
 // ------------------------------------------------------------------ scan --------------------
@@ -301,11 +247,27 @@ int resident_ctas(Kern kern, size_t smem) {
 
 void launch_plan(const ListTable& lt, const long long* coarse, int nq, int nprobe, int chunk,
                  int max_items, ScanItem* items, int* q_begin, int* n_items, int* queue_counter,
-                 unsigned long long* stats, cudaStream_t st) {
+                 unsigned long long* stats, int* pair_counts, int* pair_offs, void* scan_tmp,
+                 size_t scan_tmp_bytes, cudaStream_t st) {
   ABSB_CHECK(nq >= 1 && nq <= kMaxPlanQueries, ABSB_ERR_INVALID, "plan: nq=%d", nq);
-  plan_kernel<<<1, 1024, 0, st>>>(lt, coarse, nq, nprobe, chunk, max_items, items, q_begin, n_items,
-                                  queue_counter, stats);
+  const int npairs = nq * nprobe;
+  ABSB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), st));
+  const int threads = 256;
+  plan_count_kernel<<<(npairs + 1 + threads - 1) / threads, threads, 0, st>>>(lt, coarse, npairs, chunk, pair_counts,
+                                                                             stats);
   ABSB_CUDA(cudaGetLastError());
+  ABSB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_tmp_bytes, pair_counts, pair_offs, npairs + 1, st));
+  const int work = std::max(npairs, nq + 1);
+  plan_emit_kernel<<<(work + threads - 1) / threads, threads, 0, st>>>(lt, coarse, nq, nprobe, chunk, max_items,
+                                                                      pair_offs, items, q_begin, n_items,
+                                                                      queue_counter, stats);
+  ABSB_CUDA(cudaGetLastError());
+}
+
+size_t plan_scan_tmp_bytes(int max_pairs) {
+  size_t bytes = 0;
+  ABSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int*)nullptr, (int*)nullptr, max_pairs + 1));
+  return bytes;
 }
 
 void launch_scan(const ScanLaunch& a, cudaStream_t st) {

@@ -51,7 +51,9 @@ struct ScanLaunch {
 
 void launch_plan(const ListTable& lt, const long long* coarse, int nq, int nprobe, int chunk,
                  int max_items, ScanItem* items, int* q_begin, int* n_items, int* queue_counter,
-                 unsigned long long* stats, cudaStream_t st);
+                 unsigned long long* stats, int* pair_counts, int* pair_offs, void* scan_tmp,
+                 size_t scan_tmp_bytes, cudaStream_t st);
+size_t plan_scan_tmp_bytes(int max_pairs);
 void launch_scan(const ScanLaunch& a, cudaStream_t st);
 
 // dense.cu
