@@ -53,6 +53,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="search", choices=["search", "encode"],
+                    help="search = the headline metric (encode+IVF search); encode = BASELINE configs[1], bulk embedding")
+    ap.add_argument("--encode-batch", type=int, default=32)
+    ap.add_argument("--seq-len", type=int, default=256)
     ap.add_argument("--rows-per-gpu", type=int, default=25_875_000)
     ap.add_argument("--nlist", type=int, default=65536)
     ap.add_argument("--nprobe", type=int, default=32)
@@ -351,25 +355,33 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     launches_per_step = int(es["launches"] + st["launches"] + (1 if world > 1 else 0))
 
     # ---- timed region: value -------------------------------------------------------------------
+    # Pass A (clean): K steps, CUDA events around the whole region on the launching stream -> value.
+    # Pass B (instrumented): the same K steps again with the library recording a CUDA-event pair
+    # around every kernel on that stream -> per-kernel durations for the roofline.  The ~230 extra
+    # event records per step cost up to 8% at N=8 (short kernels), so they stay out of `value`.
+    def timed(steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            step_dev()
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1))
+
+    sampler = ClockSampler(dev) if rank == 0 else None
+    ms_total = timed(args.steps)
     kernel_events = not args.no_kernel_events
+    enc_prof = ix_prof = None
+    ms_instrumented = None
     if kernel_events:
         enc.set_profile(2)
         ix.set_profile(2)
-    sampler = ClockSampler(dev) if rank == 0 else None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step_dev()
-    ev1.record()
-    barrier()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    clocks = sampler.stop() if sampler else None
-    enc_prof = ix_prof = None
-    if kernel_events:
+        ms_instrumented = timed(args.steps) / args.steps
         enc_prof, ix_prof = enc.get_profile(), ix.get_profile()
         enc.set_profile(0)
         ix.set_profile(0)
+    clocks = sampler.stop() if sampler else None
     st = ix.last_stats()
     ms_per_step = ms_total / args.steps
     value = nq / (ms_per_step * 1e-3)
@@ -431,8 +443,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     cfg = workload_config(args, world)
     cfg.update({"index_build_s": build_s, "distinct_probed_lists_per_step": distinct_lists,
-                "scan_work_items_per_step": st["items"], "coarse_impl": "tcgen05 split-bf16 (6 bf16 products, fp32-faithful)"
-                if args.coarse_impl == 1 else "fp32 FFMA", "kernel_events_in_timed_region": kernel_events})
+                "scan_work_items_per_step": st["items"], "ms_per_step_with_kernel_events": ms_instrumented, "coarse_impl": "tcgen05 split-bf16 (6 bf16 products, fp32-faithful)"
+                if args.coarse_impl == 1 else "fp32 FFMA", "kernel_events": "second timed pass of the same K steps" if kernel_events else "off"})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -440,6 +452,138 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "roofline": dict(rooflines[dominant], kernel=dominant) if dominant else None,
         "rooflines": rooflines, "phases_ms_per_step": phases, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# secondary workload: bulk encode (BASELINE configs[1]: b=32, 256-token abstracts) -> embeddings/s
+# ------------------------------------------------------------------------------------------------
+def cpu_encode_rate(B: int, S: int, steps: int = 2):
+    import torch
+
+    from oracle import encoder as oenc
+
+    P = importlib.import_module("abstracts-search_b200.encoder")
+    cfg = P.STELLA_1_5B
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for name, shape in cfg.param_shapes().items():
+        t = torch.empty(shape, dtype=torch.float32)
+        t.normal_(1.0 if name.endswith("norm.weight") else 0.0, 0.05 if name.endswith("norm.weight") else 0.02, generator=g)
+        sd[name] = t.numpy()
+    ids = np.random.default_rng(1).integers(0, cfg.vocab_size, (B, S)).astype(np.int64)
+    mask = np.ones_like(ids)
+    oenc.forward_plain(cfg, sd, ids, mask, normalize=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oenc.forward_plain(cfg, sd, ids, mask, normalize=True)
+    return B * steps / (time.perf_counter() - t0)
+
+
+def run_encode(args, rank: int, world: int, local_rank: int):
+    metric = f"embeddings/sec (stella_en_1.5B_v5 bulk encode, b={args.encode_batch}, {args.seq_len}-token abstracts)"
+    if args.impl == "reference":
+        if rank == 0:
+            nb = 4
+            v = cpu_encode_rate(nb, args.seq_len, max(1, args.steps))
+            print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "embeddings/s", "n_gpus": args.gpus,
+                              "steps": args.steps, "warmup": 1, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
+                              "data": "synthetic", "config": {"workload": "BASELINE configs[1] bulk encode"},
+                              "cpu_baseline": {"value": v, "unit": "embeddings/s", "cores": os.cpu_count(), "kind": "port",
+                                               "sample": f"{nb} x {args.seq_len}-token sequences per step, torch-CPU fp32"},
+                              "e2e": {"value": v, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                              "gpu_launches": 0}), flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+
+    P = importlib.import_module("abstracts-search_b200")
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    pk = peaks()
+    B, S = args.encode_batch, args.seq_len
+    if args.gemm_variant:
+        importlib.import_module("abstracts-search_b200.encoder").gemm_set_variant(args.gemm_variant)
+    enc = P.Encoder(config=P.STELLA_1_5B, device=device, random_init_seed=0)
+    nbuf = 4
+    g = torch.Generator().manual_seed(99 + rank)
+    ids_h = torch.randint(0, P.STELLA_1_5B.vocab_size, (nbuf, B, S), generator=g, dtype=torch.int64).pin_memory()
+    mask_h = torch.ones((B, S), dtype=torch.int32).pin_memory()
+    ids_np, mask_np = ids_h.numpy(), mask_h.numpy()
+    ids_d, mask_d = ids_h.to(device), mask_h.to(device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(steps):
+            enc.encode_tokens(ids_d[i % nbuf], mask_d, normalize_embeddings=True)
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1))
+
+    for i in range(max(3, args.warmup)):
+        out = enc.encode_tokens(ids_d[i % nbuf], mask_d, normalize_embeddings=True)
+    es = enc.last_stats()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms = timed(args.steps) / args.steps
+    enc.set_profile(2)
+    ms_instr = timed(args.steps) / args.steps
+    prof = enc.get_profile()
+    enc.set_profile(0)
+    clocks = sampler.stop() if sampler else None
+    # e2e: numpy in, numpy out
+    ref = out.cpu().numpy()
+    for i in range(2):
+        e = enc.encode_tokens(ids_np[(max(3, args.warmup) - 1) % nbuf], mask_np, normalize_embeddings=True)
+    assert np.array_equal(e, ref), "host-API embeddings differ from the device-API embeddings"
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        enc.encode_tokens(ids_np[i % nbuf], mask_np, normalize_embeddings=True)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    if rank != 0:
+        return
+    gemm_tf = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12
+    cpu = None
+    if world == 1 and not args.skip_cpu_baseline:
+        v = cpu_encode_rate(4, S, 2)
+        cpu = {"value": v, "unit": "embeddings/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"4 x {S}-token sequences per step, 2 steps, torch-CPU fp32 oracle"}
+    line = {
+        "metric": metric, "value": B * world / (ms * 1e-3), "unit": "embeddings/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 (fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1]: stella_en_1.5B_v5 batch encode, b={B}, {S}-token synthetic abstracts, "
+                               f"one batch per step per GPU (pure data parallel)", "batch": B, "seq_len": S,
+                   "tokens_per_step_per_gpu": B * S, "flops_per_step_per_gpu": es["flops"],
+                   "ms_per_step_with_kernel_events": ms_instr, "l2": "3.1 GB of bf16 weights stream per step (L2 = 126 MB)"},
+        "clocks": clocks,
+        "e2e": {"value": B * world / e2e_s, "unit": "embeddings/s", "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": B * S * 12, "d2h_bytes_per_step": B * 1024 * 4, "api": "Encoder.encode_tokens(numpy)"},
+        "gpu_launches": int(es["launches"]) * args.steps,
+        "roofline": {"kernel": "gemm_bf16_tc_kernel", "bound": "tensor", "achieved": gemm_tf, "peak": pk["tf_sustained"],
+                     "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sustained"], "traffic": None,
+                     "ms_per_step": prof["gemm_ms"] / args.steps},
+        "phases_ms_per_step": {"encode_gemm_ms": prof["gemm_ms"] / args.steps, "encode_attention_ms": prof["attention_ms"] / args.steps,
+                               "encode_other_ms": prof["other_ms"] / args.steps},
+        "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
 
@@ -460,12 +604,18 @@ def load_traffic(rooflines: dict):
 
 
 def main():
+    # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the JSON line only
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.workload == "encode":
+            run_encode(args, rank, world, local_rank)
+        else:
+            run_reference(args, rank, world)
         return
     if world > 1:
         import torch
@@ -474,7 +624,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.workload == "encode":
+            run_encode(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist
