@@ -10,6 +10,6 @@ from ._lib import AbsbError, LIB_PATH, build, header_functions, lib  # noqa: F40
 from .index import (METRIC_INNER_PRODUCT, METRIC_L2, ClusteringParameters, IndexFlatIP,  # noqa: F401
                     IndexIVFFlat, ParameterSpace, SearchParametersIVF, extract_index_ivf,
                     index_factory, read_index, write_index)
-from .sharded import ShardedIndexIVFFlat, merge_partials_host, owner_of_list  # noqa: F401
+from .sharded import DeviceOps, ShardedIndexIVFFlat, merge_partials_host, owner_of_list  # noqa: F401
 from .encoder import STELLA_1_5B, Encoder, EncoderConfig, SentenceTransformer  # noqa: F401
 from . import synth  # noqa: F401

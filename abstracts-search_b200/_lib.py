@@ -105,6 +105,9 @@ _SIGS = {
     "absb_ivf_search_preassigned_dev": ([_H, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "absb_ivf_list_sizes": ([_H, c_void_p], c_int),
     "absb_ivf_get_list": ([_H, c_int64, c_void_p, c_void_p], c_int),
+    "absb_ivf_centroid_sums_dev": ([_H, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "absb_rand_perm": ([c_int64, c_int64, c_void_p], c_int),
+    "absb_kmeans_split_clusters": ([c_int, c_int64, c_int64, c_void_p, c_void_p, _PI64], c_int),
     "absb_ivf_set_shard": ([_H, c_int, c_int], c_int),
     "absb_merge_shards_dev": ([c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p], c_int),
     "absb_ivf_set_tunables": ([_H, c_int, c_int, c_int], c_int),

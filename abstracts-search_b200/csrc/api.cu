@@ -602,6 +602,32 @@ int absb_ivf_last_stats(absb_ivf_t h, int64_t* vectors_scanned, int64_t* bytes_s
   ABSB_API_END
 }
 
+int absb_ivf_centroid_sums_dev(absb_ivf_t h, int64_t n, const float* x_dev, const int64_t* list_ids_dev,
+                               float* sums_dev, float* counts_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(h); NEED(sums_dev); NEED(counts_dev);
+  ABSB_CHECK(n >= 0 && (n == 0 || (x_dev && list_ids_dev)), ABSB_ERR_INVALID, "bad centroid_sums arguments");
+  DeviceGuard g(h->ix.device);
+  h->ix.centroid_sums_dev(n, x_dev, reinterpret_cast<const long long*>(list_ids_dev), sums_dev, counts_dev,
+                          (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_rand_perm(int64_t n, int64_t seed, int32_t* out) {
+  ABSB_API_BEGIN
+  ABSB_CHECK(n >= 0 && n < ((int64_t)1 << 31) && (n == 0 || out), ABSB_ERR_INVALID, "bad rand_perm arguments");
+  rand_perm_export(n, seed, out);
+  ABSB_API_END
+}
+
+int absb_kmeans_split_clusters(int d, int64_t k, int64_t n, float* hassign, float* centroids, int64_t* nsplit) {
+  ABSB_API_BEGIN
+  ABSB_CHECK(d > 0 && k > 0 && n > k && hassign && centroids, ABSB_ERR_INVALID, "bad split_clusters arguments");
+  const int64_t ns = split_clusters_export(d, k, n, hassign, centroids);
+  if (nsplit) *nsplit = ns;
+  ABSB_API_END
+}
+
 int absb_ivf_set_profile(absb_ivf_t h, int on) {
   ABSB_API_BEGIN
   NEED(h);

@@ -66,6 +66,7 @@ struct KernelParams {
   const float* bias;
   const float2* rope_cs;  // EPI_BF16_BIAS_ROPE only
   int rope_S, rope_cols;
+  int* arg_idx;  // EPI_ARGMAX only: [M, ldc] next to out = float [M, ldc]
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -243,6 +244,31 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
               dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
+        }
+      } else if constexpr (EPI == EPI_ARGMAX) {
+        float best = -INFINITY;
+        int bidx = 0x7fffffff;
+        const int col0 = tn * BN;
+#pragma unroll 1
+        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(t_base + c, v);
+          tc::tmem_ld_wait();
+          const int col = col0 + c;
+          if (col < p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float f = __uint_as_float(v[j]);
+              if (f > best) {  // ascending columns + strict compare: ties keep the smallest column
+                best = f;
+                bidx = col + j;
+              }
+            }
+          }
+        }
+        if (row_ok) {
+          reinterpret_cast<float*>(p.out)[(size_t)row * p.ldc + tn * 2 + chalf] = best;
+          p.arg_idx[(size_t)row * p.ldc + tn * 2 + chalf] = bidx;
         }
       } else if constexpr (EPI == EPI_BF16_BIAS_ROPE) {
         // this warp's column half is exactly one 128-wide head: rotate-half pairs (j, j + 64)
@@ -448,6 +474,12 @@ void launch_epi(int epi, const void* A, int64_t a_rows, int64_t a_cols, int64_t 
         break;
       }
       fail(ABSB_ERR_INVALID, "SwiGLU epilogue needs 256-column tiles");
+    case EPI_ARGMAX:
+      if constexpr (BN == 256) {
+        launch<BN, EPI_ARGMAX, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st);
+        break;
+      }
+      fail(ABSB_ERR_INVALID, "arg-max epilogue needs 256-column tiles");
     case EPI_BF16_BIAS_ROPE:
       if constexpr (BN == 256) {
         launch<BN, EPI_BF16_BIAS_ROPE, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st);
@@ -464,8 +496,18 @@ int g_gemm_variant = 0;  // 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3
 
 void gemm_set_variant(int v) { g_gemm_variant = v; }
 
+void gemm_bf16_tc_ex(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
+                     int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st, const GemmRope* rope,
+                     int* arg_idx);
+
 void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
                   int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st, const GemmRope* rope) {
+  gemm_bf16_tc_ex(epi, M, N, K, A, lda, B, ldb, out, ldc, bias, segs, sms, st, rope, nullptr);
+}
+
+void gemm_bf16_tc_ex(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
+                     int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st, const GemmRope* rope,
+                     int* arg_idx) {
   if (M == 0 || N == 0) return;
   ABSB_CHECK(epi != EPI_BF16_BIAS_ROPE || (rope && rope->cs && rope->S >= 1 && rope->cols % 128 == 0 && N % 128 == 0),
              ABSB_ERR_INVALID, "RoPE epilogue needs a table, S >= 1 and 128-wide heads");
@@ -503,7 +545,9 @@ void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, cons
     p.rope_S = rope->S;
     p.rope_cols = rope->cols;
   }
-  const bool needs256 = epi == EPI_SWIGLU_BF16 || epi == EPI_BF16_BIAS_ROPE;
+  p.arg_idx = arg_idx;
+  ABSB_CHECK(epi != EPI_ARGMAX || arg_idx, ABSB_ERR_INVALID, "arg-max epilogue needs an index buffer");
+  const bool needs256 = epi == EPI_SWIGLU_BF16 || epi == EPI_BF16_BIAS_ROPE || epi == EPI_ARGMAX;
 
   // Tile shape: CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row block;
   // 192-column tiles when they cut the work into fewer, fuller waves (N = 1536: 8 x 192 instead of 6 x 256).
@@ -575,6 +619,61 @@ void gemm_split3_f32(int M, int N, int K, const void* A3, const void* B3, float*
   }
   segs.a_cols = segs.b_cols = 3 * (int64_t)K;
   gemm_bf16_tc(EPI_F32_BIAS, M, N, K, A3, 3 * (int64_t)K, B3, 3 * (int64_t)K, S, lds, nullptr, &segs, sms, st);
+}
+
+// ------------------------------------------------------------------ fused arg-max -----------
+namespace {
+// One warp per row: reduce the per-span partials with the order (score desc, column asc).
+__global__ void argmax_reduce_kernel(int M, int P, const float* __restrict__ pmax, const int* __restrict__ pidx,
+                                     long long* __restrict__ out_idx, float* __restrict__ out_score) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= M) return;
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  for (int i = lane; i < P; i += 32) {
+    const float f = pmax[(size_t)row * P + i];
+    const int c = pidx[(size_t)row * P + i];
+    if (f > best || (f == best && c < bidx)) {
+      best = f;
+      bidx = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float f = __shfl_xor_sync(0xffffffffu, best, o);
+    const int c = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (f > best || (f == best && c < bidx)) {
+      best = f;
+      bidx = c;
+    }
+  }
+  if (lane == 0) {
+    out_idx[row] = bidx == 0x7fffffff ? -1 : bidx;
+    if (out_score) out_score[row] = best;
+  }
+}
+}  // namespace
+
+int argmax_partials_per_row(int N) { return 2 * (int)ceil_div(N, 256); }
+
+void gemm_split3_argmax(int M, int N, int K, const void* A3, const void* B3, float* ws_max, int* ws_idx,
+                        long long* out_idx, float* out_score, int sms, cudaStream_t st) {
+  if (M == 0) return;
+  GemmSegs segs{};
+  const int pa[6] = {1, 0, 2, 0, 1, 0};
+  const int pb[6] = {1, 2, 0, 1, 0, 0};
+  segs.nseg = 6;
+  for (int i = 0; i < 6; ++i) {
+    segs.a_off[i] = pa[i] * K;
+    segs.b_off[i] = pb[i] * K;
+  }
+  segs.a_cols = segs.b_cols = 3 * (int64_t)K;
+  const int P = argmax_partials_per_row(N);
+  gemm_bf16_tc_ex(EPI_ARGMAX, M, N, K, A3, 3 * (int64_t)K, B3, 3 * (int64_t)K, ws_max, P, nullptr, &segs, sms, st,
+                  nullptr, ws_idx);
+  argmax_reduce_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, st>>>(M, P, ws_max, ws_idx, out_idx, out_score);
+  ABSB_CUDA(cudaGetLastError());
 }
 
 }  // namespace absb

@@ -12,6 +12,8 @@ enum GemmEpilogue {
   EPI_F32_ADD = 2,      // out f32  [M,N]  += acc                      (residual stream)
   EPI_SWIGLU_BF16 = 3,  // out bf16 [M,N/2] = silu(gate) * up, weight rows interleaved per 256-row
                         //                    tile: [128 gate rows | 128 up rows]
+  EPI_ARGMAX = 5,  // no C at all: per (row, 128-column span) the best score and its column, for
+                   // quantizer.assign (k = 1) without ever writing the [M, nlist] score matrix
   EPI_BF16_BIAS_ROPE = 4,  // EPI_BF16_BIAS + rotate-half RoPE on the 128-wide heads that start below
                            // rope.cols (the q and k heads of the fused QKV projection)
 };
@@ -39,6 +41,13 @@ struct GemmSegs {
 void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
                   int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st,
                   const GemmRope* rope = nullptr);
+
+// Row-wise arg-max of A * B^T from split-bf16 operands (see gemm_split3_f32): out_idx[r] = smallest
+// column holding the row maximum, out_score[r] (optional) that maximum.  ws_max / ws_idx are scratch
+// of argmax_partials_per_row(N) entries per row.
+int argmax_partials_per_row(int N);
+void gemm_split3_argmax(int M, int N, int K, const void* A3, const void* B3, float* ws_max, int* ws_idx,
+                        long long* out_idx, float* out_score, int sms, cudaStream_t st);
 
 // test hook: 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3 = CTA pair x BN 192
 void gemm_set_variant(int v);

@@ -106,14 +106,15 @@ __global__ void gather_rows_kernel(int64_t n, int d4, const int* __restrict__ ro
 // ascending row order; fp32 running sum in that order, then multiply by 1/count.
 __global__ void centroid_mean_kernel(int d, const unsigned* __restrict__ off,
                                      const int* __restrict__ perm, const float* __restrict__ x,
-                                     float* __restrict__ centroids, float* __restrict__ hassign) {
+                                     float* __restrict__ centroids, float* __restrict__ hassign,
+                                     int normalise = 1) {
   const int c = blockIdx.x;
   const unsigned b = off[c], e = off[c + 1];
   if (threadIdx.x == 0) hassign[c] = (float)(e - b);
   for (int j = threadIdx.x; j < d; j += blockDim.x) {
     float acc = 0.f;
     for (unsigned i = b; i < e; ++i) acc += x[(size_t)perm[i] * d + j];
-    if (e > b) acc *= 1.f / (float)(e - b);
+    if (normalise && e > b) acc *= 1.f / (float)(e - b);
     centroids[(size_t)c * d + j] = acc;
   }
 }
@@ -333,6 +334,32 @@ void IvfIndex::coarse_dev(int64_t nq, const float* q, int nprobe, float* Dc, lon
 }
 
 void IvfIndex::assign_dev(int64_t n, const float* x, long long* list_ids, cudaStream_t st) {
+  ABSB_CHECK(trained, ABSB_ERR_STATE, "index is not trained");
+  if (coarse_impl == 1 && d % 64 == 0 && nlist % 32 == 0) {
+    // tensor-core path: split-bf16 GEMM with the arg-max fused into the epilogue — the [n, nlist]
+    // score matrix (262 KB per row at nlist = 65536) is never written
+    if (c3_dirty) {
+      centroids3.reserve((size_t)nlist * 3 * d);
+      split3_bf16(nlist, d, centroids.p, centroids3.p, st);
+      c3_dirty = false;
+      stats.launches += 1;
+    }
+    const int P = argmax_partials_per_row(nlist);
+    const int64_t slice = std::max<int64_t>(256, std::min<int64_t>(65536, ((int64_t)1 << 27) / P));
+    const int64_t cap = std::min(slice, n);
+    ws_q3.reserve((size_t)cap * 3 * d);
+    ws_amax.reserve((size_t)cap * P);
+    ws_aidx.reserve((size_t)cap * P);
+    for (int64_t r0 = 0; r0 < n; r0 += slice) {
+      const int64_t nr = std::min(slice, n - r0);
+      Span sp(this, st, 1);
+      split3_bf16(nr, d, x + r0 * d, ws_q3.p, st);
+      gemm_split3_argmax((int)nr, nlist, d, ws_q3.p, centroids3.p, ws_amax.p, ws_aidx.p, list_ids + r0, nullptr,
+                         props.sm_count, st);
+      stats.launches += 3;
+    }
+    return;
+  }
   ws_coarse_s.reserve((size_t)std::min<int64_t>(n, (int64_t)1 << 22));
   // Dc is scratch: process in slices that fit ws_coarse_s
   const int64_t slice = (int64_t)1 << 22;
@@ -515,6 +542,50 @@ int64_t split_clusters_host(int d, int64_t k, int64_t n, std::vector<float>& has
   return nsplit;
 }
 }  // namespace
+
+void rand_perm_export(int64_t n, int64_t seed, int* out) {
+  std::vector<int> p = rand_perm_host(n, seed);
+  std::copy(p.begin(), p.end(), out);
+}
+
+int64_t split_clusters_export(int d, int64_t k, int64_t n, float* hassign, float* centroids) {
+  std::vector<float> h(hassign, hassign + k);
+  const int64_t ns = split_clusters_host(d, k, n, h, centroids);
+  std::copy(h.begin(), h.end(), hassign);
+  return ns;
+}
+
+// Per-list fp32 sums (members in ascending row order) and member counts of one slice of rows — the
+// local half of Clustering::compute_centroids when the training rows are spread over ranks.
+void IvfIndex::centroid_sums_dev(int64_t n, const float* x, const long long* assign, float* sums, float* counts,
+                                 cudaStream_t st) {
+  const int64_t k = nlist;
+  ABSB_CHECK(n < ((int64_t)1 << 31), ABSB_ERR_INVALID, "too many rows in one call");
+  const int sms = props.sm_count;
+  DBuf<unsigned> keys, keys_sorted, hist, off;
+  DBuf<int> vals, perm;
+  keys.alloc_exact(std::max<int64_t>(n, 1)); keys_sorted.alloc_exact(std::max<int64_t>(n, 1));
+  vals.alloc_exact(std::max<int64_t>(n, 1)); perm.alloc_exact(std::max<int64_t>(n, 1));
+  hist.alloc_exact(k + 2); off.alloc_exact(k + 2);
+  int bits = 1;
+  while ((1ll << bits) < (long long)k + 1) ++bits;
+  size_t tmp_bytes = 0, t2 = 0;
+  ABSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, vals.p, perm.p, (int)n, 0, bits, st));
+  ABSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t2, hist.p, off.p, (int)k + 2, st));
+  ws_cub.reserve(std::max(tmp_bytes, t2) + 16);
+  ABSB_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned) * (k + 2), st));
+  if (n > 0) {
+    make_keys_kernel<<<grid_for(n, 256, sms), 256, 0, st>>>(n, assign, (int)k, 0, 1, keys.p, vals.p, hist.p);
+    ABSB_CUDA(cudaGetLastError());
+    size_t tb = ws_cub.cap;
+    ABSB_CUDA(cub::DeviceRadixSort::SortPairs(ws_cub.p, tb, keys.p, keys_sorted.p, vals.p, perm.p, (int)n, 0, bits, st));
+  }
+  size_t tb = ws_cub.cap;
+  ABSB_CUDA(cub::DeviceScan::ExclusiveSum(ws_cub.p, tb, hist.p, off.p, (int)k + 2, st));
+  centroid_mean_kernel<<<(unsigned)k, std::min(256, d), 0, st>>>(d, off.p, perm.p, x, sums, counts, 0);
+  ABSB_CUDA(cudaGetLastError());
+  ABSB_CUDA(cudaStreamSynchronize(st));  // scratch buffers die with this frame
+}
 
 void IvfIndex::train_dev(int64_t n, const float* x, cudaStream_t st) {
   const int64_t k = nlist;

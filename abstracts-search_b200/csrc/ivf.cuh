@@ -51,6 +51,8 @@ struct IvfIndex {
   DBuf<float> centroids;  // [nlist, d]
   DBuf<uint16_t> centroids3;  // bf16 [nlist, 3d] = [hi | mid | lo] split for the tcgen05 coarse GEMM
   DBuf<uint16_t> ws_q3;
+  DBuf<float> ws_amax;  // fused arg-max partials of assign_dev
+  DBuf<int> ws_aidx;
   bool c3_dirty = true;
 
   // inverted lists
@@ -66,7 +68,7 @@ struct IvfIndex {
 
   // tunables
   int scan_chunk = 128;
-  int coarse_impl = 0;
+  int coarse_impl = 1;  // 1 = tcgen05 split-bf16 (falls back to the FFMA GEMM for shapes it cannot take)
   int scan_ctas_per_sm = 0;
 
   // workspaces (single stream at a time)
@@ -128,6 +130,8 @@ struct IvfIndex {
   void set_centroids_dev(const float* c, cudaStream_t st);
   void train_dev(int64_t n, const float* x, cudaStream_t st);
   void train_host(int64_t n, const float* x);
+  void centroid_sums_dev(int64_t n, const float* x, const long long* assign, float* sums, float* counts,
+                         cudaStream_t st);
   // scores -> top-k coarse (k = nprobe) for nq <= chunk rows; Ic int64 [nq, nprobe]
   void coarse_dev(int64_t nq, const float* q, int nprobe, float* Dc, long long* Ic, bool finalize,
                   cudaStream_t st);
@@ -145,6 +149,9 @@ struct IvfIndex {
   int64_t items_bound_per_query(int nprobe) const;
   void refresh_host_sizes(cudaStream_t st);
 };
+
+void rand_perm_export(int64_t n, int64_t seed, int* out);
+int64_t split_clusters_export(int d, int64_t k, int64_t n, float* hassign, float* centroids);
 
 struct FlatIndex {
   int d, device;

@@ -37,6 +37,50 @@ def merge_partials_host(D_all: np.ndarray, I_all: np.ndarray, k: int):
     return D, I
 
 
+class DeviceOps:
+    """The per-rank arithmetic of the distributed build, on this rank's GPU through the C ABI.
+    (The gloo CPU tests substitute an oracle-backed object with the same five methods.)"""
+
+    def __init__(self, local):
+        self.local = local
+
+    def to_device(self, a):
+        import torch
+
+        return a if hasattr(a, "is_cuda") else torch.from_numpy(np.ascontiguousarray(a)).cuda(self.local.device)
+
+    def assign(self, x):
+        return self.local.assign(x)
+
+    def centroid_sums(self, x, assign):
+        import torch
+
+        from ._lib import check, current_stream_ptr, lib, ptr
+
+        ix = self.local
+        sums = torch.empty((ix.nlist, ix.d), dtype=torch.float32, device=x.device)
+        counts = torch.empty((ix.nlist,), dtype=torch.float32, device=x.device)
+        check(lib().absb_ivf_centroid_sums_dev(ix._h, x.shape[0], ptr(x), ptr(assign.contiguous()), ptr(sums), ptr(counts),
+                                               current_stream_ptr()))
+        return sums, counts
+
+    def rand_perm(self, n: int, seed: int) -> np.ndarray:
+        from ._lib import check, lib, ptr
+
+        out = np.empty((n,), dtype=np.int32)
+        check(lib().absb_rand_perm(n, seed, ptr(out)))
+        return out.astype(np.int64)
+
+    def split_clusters(self, d: int, k: int, n: int, hassign: np.ndarray, centroids: np.ndarray) -> int:
+        from ctypes import byref, c_int64
+
+        from ._lib import check, lib, ptr
+
+        ns = c_int64()
+        check(lib().absb_kmeans_split_clusters(d, k, n, ptr(hassign), ptr(centroids), byref(ns)))
+        return ns.value
+
+
 class ShardedIndexIVFFlat:
     """`local` is this rank's IndexIVFFlat (already set_shard(rank, world)); `group` a
     torch.distributed process group (None = default)."""
@@ -76,6 +120,123 @@ class ShardedIndexIVFFlat:
 
     def add_core(self, x, ids, list_ids):
         self.local.add_core(x, ids, list_ids)
+
+    # ---- distributed build (`add` = all-to-all of rows, `train` = all-reduce of sums) --
+    def _ops(self, ops):
+        return ops if ops is not None else DeviceOps(self.local)
+
+    def _slice_offsets(self, n_local: int, device):
+        """Rows are spread over ranks in rank order: rank r holds global rows [off[r], off[r+1])."""
+        import torch
+        import torch.distributed as dist
+
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=device)
+        sizes[self.rank] = n_local
+        dist.all_reduce(sizes, group=self.group)
+        off = torch.zeros(self.world + 1, dtype=torch.int64)
+        off[1:] = torch.cumsum(sizes.cpu(), 0)
+        return off
+
+    def add_distributed(self, x_local, ids_local=None, ops=None):
+        """Index.add for rows that are SPREAD over the ranks (rank r holds the r-th contiguous slice
+        of the global batch): every rank assigns only its own rows (1/W of the coarse GEMM), then one
+        all-to-all routes each (vector, id, list) to the rank that owns the list.  The lists end up
+        identical — contents and order — to a single index fed the concatenated batch, and default
+        ids number the rows globally."""
+        import torch
+        import torch.distributed as dist
+
+        ops = self._ops(ops)
+        x = ops.to_device(x_local)
+        n, W = x.shape[0], self.world
+        dev = x.device
+        off = self._slice_offsets(n, dev)
+        base = getattr(self, "_rows_seen", 0)
+        if ids_local is None:
+            ids = torch.arange(base + int(off[self.rank]), base + int(off[self.rank]) + n, dtype=torch.int64, device=dev)
+        else:
+            ids = ops.to_device(np.ascontiguousarray(ids_local, dtype=np.int64) if not hasattr(ids_local, "is_cuda") else ids_local)
+        self._rows_seen = base + int(off[-1])
+        lists = ops.assign(x)
+        lists = lists if hasattr(lists, "device") and not isinstance(lists, np.ndarray) else torch.from_numpy(lists)
+        lists = lists.to(dev).to(torch.int64)
+        owner = owner_of_list(lists, W)
+        order = torch.argsort(owner, stable=True)
+        send = torch.bincount(owner, minlength=W).to(torch.int64)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        s_list, r_list = send.cpu().tolist(), recv.cpu().tolist()
+        nr = int(sum(r_list))
+
+        def exchange(t):
+            out = torch.empty((nr,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            dist.all_to_all_single(out, t[order].contiguous(), r_list, s_list, group=self.group)
+            return out
+
+        xr, idr, lr = exchange(x), exchange(ids), exchange(lists)
+        self.local.add_core(xr if xr.is_cuda else xr.numpy(), idr if idr.is_cuda else idr.numpy(),
+                            lr if lr.is_cuda else lr.numpy())
+        return nr
+
+    def train_distributed(self, x_local, ops=None):
+        """Index.train (faiss Clustering defaults: subsample to 256 x nlist rows with rand_perm(seed),
+        initial centroids = rows rand_perm(seed + 1)[:nlist] of the sample, niter x {assign, mean,
+        split empty clusters}) with the training rows spread over the ranks.  Per iteration every
+        rank assigns its slice and reduces it to per-list sums; ONE all-reduce of [nlist, d] sums +
+        counts follows; mean and split_clusters are replicated (deterministic)."""
+        import torch
+        import torch.distributed as dist
+
+        ops = self._ops(ops)
+        cp = getattr(self.local, "cp", None)
+        niter = cp.niter if cp else 10
+        max_ppc = cp.max_points_per_centroid if cp else 256
+        seed = cp.seed if cp else 1234
+        k, d = self.nlist, self.d
+        x = ops.to_device(x_local)
+        dev = x.device
+        off = self._slice_offsets(x.shape[0], dev)
+        lo, hi, n = int(off[self.rank]), int(off[self.rank + 1]), int(off[-1])
+        if n < k:
+            raise RuntimeError(f"Number of training points ({n}) should be at least as large as number of clusters ({k})")
+        # global sample order -> the rows of it this rank holds, kept in sample order
+        if n > k * max_ppc:
+            perm = ops.rand_perm(n, seed)[: k * max_ppc]
+        else:
+            perm = np.arange(n, dtype=np.int64)
+        ns = len(perm)
+        mine = np.nonzero((perm >= lo) & (perm < hi))[0]  # sample positions held here
+        xs = x[torch.from_numpy(perm[mine] - lo).to(dev)].contiguous()
+        # initial centroids: sample rows perm2[:k]; every rank fills the rows it holds, one all-reduce
+        if ns == k:
+            pick = np.arange(k, dtype=np.int64)
+        else:
+            pick = ops.rand_perm(ns, seed + 1)[:k]
+        pos_of = np.full(ns, -1, dtype=np.int64)
+        pos_of[mine] = np.arange(len(mine))
+        src = pos_of[pick]
+        cent = torch.zeros((k, d), dtype=torch.float32, device=dev)
+        have = np.nonzero(src >= 0)[0]
+        if len(have):
+            cent[torch.from_numpy(have).to(dev)] = xs[torch.from_numpy(src[have]).to(dev)]
+        dist.all_reduce(cent, group=self.group)
+        self.local.set_centroids(cent if cent.is_cuda else cent.numpy())
+        if ns == k:
+            return
+        for _ in range(niter):
+            assign = ops.assign(xs)
+            sums, counts = ops.centroid_sums(xs, assign if hasattr(assign, "device") and not isinstance(assign, np.ndarray)
+                                             else torch.from_numpy(assign).to(dev))
+            dist.all_reduce(sums, group=self.group)
+            dist.all_reduce(counts, group=self.group)
+            inv = torch.where(counts > 0, 1.0 / counts, torch.zeros_like(counts))
+            cent = sums * inv[:, None]
+            hassign = counts.cpu().numpy().astype(np.float32)
+            if (hassign == 0).any():
+                c_h = np.ascontiguousarray(cent.cpu().numpy())
+                ops.split_clusters(d, k, ns, hassign, c_h)
+                cent = torch.from_numpy(c_h).to(dev)
+            self.local.set_centroids(cent if cent.is_cuda else cent.numpy())
 
     def search(self, x, k: int):
         """x: the full query batch on every rank.  Returns the merged (D, I) on every rank.

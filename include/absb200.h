@@ -154,6 +154,18 @@ int absb_ivf_list_sizes(absb_ivf_t h, int64_t* sizes);
  * order (host buffers sized from absb_ivf_list_sizes; either may be NULL). */
 int absb_ivf_get_list(absb_ivf_t h, int64_t list_no, float* codes, int64_t* ids);
 
+/* Building blocks of Index.train when the training rows are spread over ranks (k-means
+ * row): the LOCAL half of Clustering::compute_centroids — per-list fp32 sums of the rows assigned to
+ * each list (ascending row order) and member counts, to be all-reduced by the caller — plus the two
+ * host-side pieces of faiss's Clustering that need a sequential std::mt19937: rand_perm (subsample
+ * and initial centroids) and split_clusters (empty-cluster repair; returns the number of splits). */
+int absb_ivf_centroid_sums_dev(absb_ivf_t h, int64_t n, const float* x_dev, const int64_t* list_ids_dev,
+                               float* sums_dev /* [nlist,d] */, float* counts_dev /* [nlist] */,
+                               void* stream);
+int absb_rand_perm(int64_t n, int64_t seed, int32_t* out);
+int absb_kmeans_split_clusters(int d, int64_t k, int64_t n, float* hassign, float* centroids,
+                               int64_t* nsplit);
+
 /* Sharding by inverted list: this handle keeps only lists l with
  * l % world == rank; add() silently drops rows of other lists but ntotal still counts only kept
  * rows. Must be called before the first add. Coarse quantisation stays replicated. */

@@ -1,0 +1,65 @@
+"""2-GPU (NCCL) check of the distributed index build, launched by torchrun:
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_build_check.py
+train_distributed / add_distributed on the CUDA path must reproduce the single-process oracle
+(k-means exact on the lattice corpus; list contents, ids and search results bit-exact)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{torch.cuda.current_device()}"))
+    P = importlib.import_module("abstracts-search_b200")
+    from oracle import ivf as oivf
+    from oracle import synth as osynth
+
+    d, nlist, n, nq, k, nprobe = 1024, 64, 20000, 16, 10, 8
+    x = osynth.corpus(11, 0, n, d, nlist)
+    cut = np.linspace(0, n, world + 1).astype(int)
+    cut[1] += 333  # uneven slices
+    mine = x[cut[rank]:cut[rank + 1]]
+    local = P.IndexIVFFlat(d, nlist, device=torch.cuda.current_device())
+    local.set_shard(rank, world)
+    local.cp.max_points_per_centroid = 200  # 64 * 200 < 20000: subsampling branch
+    sh = P.ShardedIndexIVFFlat(local)
+    sh.train_distributed(mine)
+    cent = local.get_centroids()
+    ref_cent = oivf.kmeans_train(x, nlist, max_points_per_centroid=200)
+    assert np.array_equal(cent, ref_cent), f"rank {rank}: distributed k-means differs from the oracle"
+    h = len(mine) // 2
+    sh.add_distributed(mine[:h])
+    sh.add_distributed(torch.from_numpy(mine[h:]).cuda())
+    assert sh.ntotal == n
+    order = np.concatenate([np.arange(cut[r], cut[r] + (cut[r + 1] - cut[r]) // 2) for r in range(world)] +
+                           [np.arange(cut[r] + (cut[r + 1] - cut[r]) // 2, cut[r + 1]) for r in range(world)])
+    ref = oivf.IVFFlat(d, nlist)
+    ref.set_centroids(ref_cent)
+    ref.add(x[order])
+    sizes = torch.from_numpy(local.list_sizes()).cuda()
+    dist.all_reduce(sizes)
+    assert np.array_equal(sizes.cpu().numpy(), ref.list_sizes())
+    for l in range(rank, nlist, world):
+        codes, ids = local.get_list(l)
+        assert np.array_equal(ids, ref.ids[l]) and np.array_equal(codes, ref.codes[l]), (rank, l)
+    sh.nprobe = nprobe
+    q = osynth.queries(11, 0, nq, d, nlist, n)
+    D, I = sh.search(torch.from_numpy(q).cuda(), k)
+    Dr, Ir = ref.search(q, k, nprobe=nprobe)
+    assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr)
+    dist.barrier()
+    if rank == 0:
+        print(f"dist_build_check ok: world={world}, k-means exact, lists and search bit-exact")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

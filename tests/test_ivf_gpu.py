@@ -335,3 +335,21 @@ def test_two_million_rows_properties(gpu_pkg):
     assert np.array_equal(Io, In[sel]) and np.array_equal(Do, Dn[sel])
     st = ix.last_stats()
     assert st["vectors"] == sizes[Ic].sum()
+
+
+# ------------------------------------------------------------------ distributed build (NCCL) ---
+def test_distributed_build_two_gpus(gpu_pkg):
+    """train_distributed / add_distributed over NCCL (tests/dist_build_check.py under torchrun).
+    Needs two visible GPUs; the single-GPU driver run skips it, `gpurun --gpus 2` exercises it."""
+    import os
+    import subprocess
+    import sys
+
+    t = _torch()
+    if t.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(root, "tests", "dist_build_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "dist_build_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -46,9 +46,56 @@ class OracleShard:
         self.ix.add(x, ids=ids, list_ids=lists)
         self.rows_seen += n
 
+    def add_core(self, x, ids, lists):
+        lists = np.where(np.asarray(lists) % self.world == self.rank, lists, -1)
+        self.ix.add(np.asarray(x), ids=np.asarray(ids), list_ids=lists)
+
     def search(self, x, k):
         _, Ic = self.ix.coarse(x, min(self.nprobe, self.nlist))
         return self.ix.search_preassigned(x, k, Ic)
+
+
+class OracleOps:
+    """CPU stand-ins (oracle arithmetic) for DeviceOps, so that the distributed build's host logic —
+    slicing, the all-to-all routing, the all-reduce of sums, global ids — runs under gloo."""
+
+    def __init__(self, shard):
+        self.s = shard
+
+    def to_device(self, a):
+        import torch
+
+        return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+
+    def assign(self, x):
+        import torch
+
+        return torch.from_numpy(self.s.ix.assign(x.numpy()))
+
+    def centroid_sums(self, x, assign):
+        import torch
+
+        k, d = self.s.nlist, self.s.d
+        sums = np.zeros((k, d), dtype=np.float32)
+        counts = np.zeros(k, dtype=np.float32)
+        xn, an = x.numpy(), assign.numpy()
+        for i in range(xn.shape[0]):
+            sums[an[i]] += xn[i]
+            counts[an[i]] += 1
+        return torch.from_numpy(sums), torch.from_numpy(counts)
+
+    def rand_perm(self, n, seed):
+        from oracle import ivf as oivf
+
+        return oivf.rand_perm(n, seed)
+
+    def split_clusters(self, d, k, n, hassign, centroids):
+        import ctypes
+
+        from oracle import ivf as oivf
+
+        return int(oivf.clib().orc_split_clusters(ctypes.c_int(d), ctypes.c_int64(k), ctypes.c_int64(n),
+                                                  oivf._p(hassign, ctypes.c_float), oivf._p(centroids, ctypes.c_float)))
 
 
 def _worker(rank, world, port, out_dir):
@@ -77,6 +124,77 @@ def _worker(rank, world, port, out_dir):
     D, I = sh.search(q, k)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), D=D, I=I, total=total, local=local.ntotal)
     dist.destroy_process_group()
+
+
+def _build_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import importlib
+
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = importlib.import_module("abstracts-search_b200")
+    from oracle import synth as osynth
+
+    d, nlist, n, nq, k, nprobe = 64, 16, 5000, 9, 6, 4
+    x = osynth.corpus(11, 0, n, d, nlist)
+    # uneven contiguous slices: rank 0 holds [0, 1800), rank 1 the rest
+    cut = [0, 1800, n]
+    mine = x[cut[rank]:cut[rank + 1]]
+    local = OracleShard(d, nlist, rank, world)
+    local.cp = P.ClusteringParameters()
+    local.cp.max_points_per_centroid = 200  # 16 * 200 = 3200 < 5000: the subsampling branch
+    local.device = "cpu"
+    sh = P.ShardedIndexIVFFlat(local, merge_fn=P.merge_partials_host)
+    ops = OracleOps(local)
+    sh.train_distributed(mine, ops=ops)
+    cent = local.ix.centroids.copy()
+    # two distributed adds (global default ids continue across calls)
+    h = (cut[rank + 1] - cut[rank]) // 2
+    sh.add_distributed(mine[:h], ops=ops)
+    sh.add_distributed(mine[h:], ops=ops)
+    sh.nprobe = nprobe
+    q = osynth.queries(11, 0, nq, d, nlist, n)
+    D, I = sh.search(q, k)
+    sizes = local.ix.list_sizes()
+    np.savez(os.path.join(out_dir, f"b{rank}.npz"), D=D, I=I, cent=cent, sizes=sizes, total=sh.ntotal,
+             ids0=local.ix.ids[rank], h=h)
+    dist.destroy_process_group()
+
+
+def test_distributed_train_and_add_world2_gloo(tmp_path):
+    """train_distributed == single-process k-means (exact on the lattice corpus, where fp32 sums do not
+    depend on order); add_distributed routes every row to its list owner with global ids."""
+    world = 2
+    mp.spawn(_build_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from oracle import ivf as oivf
+    from oracle import synth as osynth
+
+    d, nlist, n, nq, k, nprobe = 64, 16, 5000, 9, 6, 4
+    x = osynth.corpus(11, 0, n, d, nlist)
+    cent = oivf.kmeans_train(x, nlist, max_points_per_centroid=200)
+    res = [np.load(tmp_path / f"b{r}.npz") for r in range(world)]
+    for r in res:
+        assert np.array_equal(r["cent"], cent), "distributed k-means differs from the single-process oracle"
+        assert int(r["total"]) == n
+    # the global batch order of the two add calls: [r0 first half, r1 first half, r0 second half, r1 second half]
+    cut = [0, 1800, n]
+    h = [int(r["h"]) for r in res]
+    order = np.concatenate([np.arange(cut[0], cut[0] + h[0]), np.arange(cut[1], cut[1] + h[1]),
+                            np.arange(cut[0] + h[0], cut[1]), np.arange(cut[1] + h[1], cut[2])])
+    ref = oivf.IVFFlat(d, nlist)
+    ref.set_centroids(cent)
+    ref.add(x[order])  # default ids = position in the global batch order
+    sizes = sum(r["sizes"] for r in res)
+    assert np.array_equal(sizes, ref.list_sizes())
+    for rank, r in enumerate(res):
+        assert np.array_equal(r["ids0"], ref.ids[rank]), "list contents / order differ"
+    D, I = ref.search(osynth.queries(11, 0, nq, d, nlist, n), k, nprobe=nprobe)
+    for r in res:
+        assert np.array_equal(r["I"], I) and np.array_equal(r["D"], D)
 
 
 def test_sharded_search_world2_gloo(tmp_path):
