@@ -435,39 +435,55 @@ class ParameterSpace:
 
 
 # ------------------------------------------------------------------ (de)serialisation ---------
-_MAGIC = b"ABSBIVF1"
+def write_index(index, path: str, ondisk_path: str | None = None) -> None:
+    """faiss.write_index in faiss's own byte format (faiss_io.py): IndexFlatIP -> "IxFI",
+    IndexIVFFlat -> "IwFl" with array inverted lists, or — with `ondisk_path` — the
+    index.faiss + ondisk.ivfdata pair `sidecar-search index fill` leaves (Makefile:11)."""
+    from . import faiss_io as fio
 
-
-def write_index(index: IndexIVFFlat, path: str) -> None:
-    """Self-describing container (centroids + lists in list order).  faiss's own file format is a
-    SURVEY §8(f) row, not part of this slice."""
+    if isinstance(index, IndexFlatIP):
+        with open(path, "wb") as f:
+            fio.write_flat(f, fio.FlatData(index.d, METRIC_INNER_PRODUCT, index.reconstruct_n(0, index.ntotal)))
+        return
     assert isinstance(index, IndexIVFFlat)
-    sizes = index.list_sizes()
-    with open(path, "wb") as f:
-        f.write(_MAGIC)
-        f.write(struct.pack("<qqqqq", index.d, index.nlist, index.nprobe, int(index.is_trained), int(sizes.sum())))
-        if index.is_trained:
-            f.write(index.get_centroids().tobytes())
-        f.write(sizes.tobytes())
-        for l in np.nonzero(sizes)[0]:
-            codes, ids = index.get_list(int(l))
-            f.write(ids.tobytes())
-            f.write(codes.tobytes())
+    data = fio.IVFFlatData(index.d, index.nlist, index.nprobe, METRIC_INNER_PRODUCT, index.is_trained,
+                           index.get_centroids() if index.is_trained else None)
+    fio.write_ivfflat(path, data, ondisk_path, sizes=index.list_sizes(), list_fn=lambda l: index.get_list(int(l)))
 
 
-def read_index(path: str, device: int = 0) -> IndexIVFFlat:
+def read_index(path: str, device: int = 0):
+    """faiss.read_index for the index types on this path."""
+    from . import faiss_io as fio
+
     with open(path, "rb") as f:
-        if f.read(8) != _MAGIC:
-            raise RuntimeError(f"{path}: not an absb200 index file")
-        d, nlist, nprobe, trained, _ = struct.unpack("<qqqqq", f.read(40))
-        index = IndexIVFFlat(d, nlist, METRIC_INNER_PRODUCT, device=device)
-        index.nprobe = nprobe
-        if trained:
-            index.set_centroids(np.frombuffer(f.read(nlist * d * 4), dtype=np.float32).reshape(nlist, d))
-        sizes = np.frombuffer(f.read(nlist * 8), dtype=np.int64)
-        for l in np.nonzero(sizes)[0]:
-            n = int(sizes[l])
-            ids = np.frombuffer(f.read(n * 8), dtype=np.int64)
-            codes = np.frombuffer(f.read(n * d * 4), dtype=np.float32).reshape(n, d)
-            index.add_core(codes, ids, np.full(n, l, dtype=np.int64))
+        cc = f.read(4)
+    if cc in (b"IxFI", b"IxF2", b"IxFl"):
+        flat = fio._r_flat(fio._R(np.memmap(path, dtype=np.uint8, mode="r")))
+        if flat.metric != METRIC_INNER_PRODUCT:
+            raise RuntimeError("only METRIC_INNER_PRODUCT is on the abstracts-search path")
+        ix = IndexFlatIP(flat.d, device=device)
+        ix.add(flat.xb)
+        return ix
+    data = fio.read_ivfflat(path)
+    if data.metric != METRIC_INNER_PRODUCT:
+        raise RuntimeError("only METRIC_INNER_PRODUCT is on the abstracts-search path")
+    index = IndexIVFFlat(data.d, data.nlist, METRIC_INNER_PRODUCT, device=device)
+    index.nprobe = data.nprobe
+    if data.centroids is not None:
+        index.set_centroids(data.centroids)
+    # feed the lists back in bounded batches through add_core (precomputed list numbers)
+    batch_c, batch_i, batch_l, rows = [], [], [], 0
+    def flush():
+        nonlocal batch_c, batch_i, batch_l, rows
+        if rows:
+            index.add_core(np.concatenate(batch_c), np.concatenate(batch_i), np.concatenate(batch_l))
+        batch_c, batch_i, batch_l, rows = [], [], [], 0
+    for l in range(data.nlist):
+        n = len(data.ids[l])
+        if n:
+            batch_c.append(data.codes[l]); batch_i.append(data.ids[l]); batch_l.append(np.full(n, l, dtype=np.int64))
+            rows += n
+            if rows >= 262144:
+                flush()
+    flush()
     return index

@@ -53,8 +53,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="search", choices=["search", "encode"],
-                    help="search = the headline metric (encode+IVF search); encode = BASELINE configs[1], bulk embedding")
+    ap.add_argument("--workload", default="search", choices=["search", "encode", "build"],
+                    help="search = the headline metric (encode+IVF search); encode = BASELINE configs[1], bulk embedding; "
+                         "build = BASELINE configs[4], Index.add / Index.train rates")
+    ap.add_argument("--add-rows", type=int, default=1 << 20, help="build workload: rows per add() per GPU")
+    ap.add_argument("--train-rows", type=int, default=1 << 21, help="build workload: k-means sample rows per GPU")
     ap.add_argument("--encode-batch", type=int, default=32)
     ap.add_argument("--seq-len", type=int, default=256)
     ap.add_argument("--rows-per-gpu", type=int, default=25_875_000)
@@ -588,6 +591,122 @@ def run_encode(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# secondary workload: index build (BASELINE configs[4]) -> rows/s of Index.add, k-means iteration rate
+# ------------------------------------------------------------------------------------------------
+def run_build(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+
+    P = importlib.import_module("abstracts-search_b200")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    device = f"cuda:{dev}"
+    pk = peaks()
+    d, nlist, n_add = 1024, args.nlist, args.add_rows
+    ix = P.index_factory(d, f"IVF{nlist},Flat", P.METRIC_INNER_PRODUCT, device=dev)
+    ix.set_tunables(coarse_impl=args.coarse_impl)
+    sh = None
+    if world > 1:
+        ix.set_shard(rank, world)
+        sh = P.ShardedIndexIVFFlat(ix)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- Index.train: one Lloyd iteration rate on a per-GPU sample (niter = 2 keeps the run short) ----
+    xt = P.synth.corpus(SEED + 1, rank * args.train_rows, args.train_rows, d, nlist, device=dev)
+    ix.cp.niter = 2
+    ix.cp.max_points_per_centroid = 1 << 30
+    barrier()
+    t0 = time.perf_counter()
+    if sh is not None:
+        sh.train_distributed(xt)
+    else:
+        ix.train(xt)
+    barrier()
+    train_s = max_over_ranks(time.perf_counter() - t0)
+    del xt
+    torch.cuda.empty_cache()
+    # the bench index uses the generating centres as centroids (every list gets rows)
+    ix.set_centroids(P.synth.centroids(SEED, nlist, d, device=dev))
+
+    # ---- Index.add: assign (fused arg-max GEMM) + append; rows spread over ranks, all-to-all to owners ----
+    total_steps = max(args.warmup, 3) + args.steps
+    xbuf = [P.synth.corpus(SEED, (s * world + rank) * n_add, n_add, d, nlist, device=dev) for s in range(min(4, total_steps))]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def add_step(i):
+        x = xbuf[i % len(xbuf)]
+        if sh is not None:
+            sh.add_distributed(x)
+        else:
+            ix.add(x)
+
+    for i in range(max(args.warmup, 3)):
+        add_step(i)
+    sampler = ClockSampler(dev) if rank == 0 else None
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        add_step(i)
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    clocks = sampler.stop() if sampler else None
+    # e2e: host rows through the numpy API (H2D of the rows inside the timed region)
+    xh = torch.empty((n_add, d), dtype=torch.float32).pin_memory()
+    xh.copy_(xbuf[0])
+    xnp = xh.numpy()
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        if sh is not None:
+            sh.add_distributed(xnp)
+        else:
+            ix.add(xnp)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    ntotal = sh.ntotal if sh is not None else ix.ntotal
+    if rank != 0:
+        return
+    rows = n_add * world
+    flops_row = 6 * 2.0 * nlist * d  # split-bf16: six bf16 products per fp32-faithful inner product
+    assign_tf = n_add * flops_row / (ms * 1e-3) / 1e12
+    line = {
+        "metric": f"rows/sec (Index.add: coarse assign over {nlist} centroids + list append, d=1024 fp32)",
+        "value": rows / (ms * 1e-3), "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 x3 split (fp32-faithful scores, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[4]: Index.add of {n_add} rows per GPU per step into IVF{nlist},Flat "
+                               f"(rows spread over {world} GPU(s); assign locally, one all-to-all to the list owners)",
+                   "rows_per_step": rows, "ntotal_after": int(ntotal),
+                   "train": {"rows_per_gpu": args.train_rows, "niter": 2, "seconds": train_s,
+                             "rows_x_iters_per_s": args.train_rows * world * 2 / train_s},
+                   "l2": "each step reads 4 GB of fresh rows and 403 MB of split centroids per GPU (L2 = 126 MB)"},
+        "clocks": clocks,
+        "e2e": {"value": rows / e2e_s, "unit": "rows/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": n_add * d * 4,
+                "d2h_bytes_per_step": 0, "api": "IndexIVFFlat.add(numpy) / ShardedIndexIVFFlat.add_distributed(numpy)"},
+        "gpu_launches": None,
+        "roofline": {"kernel": "gemm_bf16_tc_kernel (EPI_ARGMAX, 6 split-bf16 segments)", "bound": "tensor",
+                     "achieved": assign_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": assign_tf / pk["tf_sustained"],
+                     "traffic": None, "note": "whole add() step (assign + sort + scatter) charged to the GEMM"},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def load_traffic(rooflines: dict):
     """dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json), if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -626,6 +745,8 @@ def main():
     try:
         if args.workload == "encode":
             run_encode(args, rank, world, local_rank)
+        elif args.workload == "build":
+            run_build(args, rank, world, local_rank)
         else:
             run_ours(args, rank, world, local_rank)
     finally:

@@ -244,6 +244,21 @@ def test_write_read_roundtrip(gpu_pkg, tmp_path, lattice):
     assert ix2.ntotal == ix.ntotal and ix2.nprobe == ix.nprobe
     D, I = ix2.search(q, int(g["k"]))
     assert np.array_equal(I, g["I"]) and np.array_equal(D, g["D"])
+    assert open(path, "rb").read(4) == b"IwFl"  # faiss's own container (faiss_io.py)
+    # index.faiss + ondisk.ivfdata pair, as `sidecar-search index fill` leaves it (Makefile:11)
+    p3, d3 = str(tmp_path / "index.faiss"), str(tmp_path / "ondisk.ivfdata")
+    gpu_pkg.write_index(ix, p3, ondisk_path=d3)
+    ix3 = gpu_pkg.read_index(p3)
+    assert np.array_equal(ix3.list_sizes(), ix.list_sizes())
+    D, I = ix3.search(q, int(g["k"]))
+    assert np.array_equal(I, g["I"]) and np.array_equal(D, g["D"])
+    # flat index
+    fl = gpu_pkg.IndexFlatIP(x.shape[1])
+    fl.add(x[:777])
+    pf = str(tmp_path / "flat.faiss")
+    gpu_pkg.write_index(fl, pf)
+    fl2 = gpu_pkg.read_index(pf)
+    assert fl2.ntotal == 777 and np.array_equal(fl2.reconstruct_n(0, 777), x[:777])
 
 
 # ------------------------------------------------------------------ shards ---------------------
