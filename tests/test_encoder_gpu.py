@@ -183,3 +183,21 @@ def test_sentence_transformer_surface(gpu_pkg):
         model.encode("x", prompt_name="nope")
     t = model.encode(docs[:2], convert_to_tensor=True)
     assert t.is_cuda and tuple(t.shape) == (2, TINY.embed_dim)
+
+
+def test_baseline_config0_encode_full_size(gpu_pkg):
+    """BASELINE configs[0], encoder half, at a size the fp32 CPU oracle finishes in seconds: 6
+    synthetic 256-token abstracts through the full stella architecture (several key tiles, GQA
+    sharing, CTA-pair GEMM tiles) — cosine within 1e-3 of the oracle (north-star tolerance)."""
+    P = gpu_pkg
+    enc = P.Encoder(config=P.STELLA_1_5B, random_init_seed=0)
+    sd = enc.state_dict()
+    rng = np.random.default_rng(7)
+    ids = rng.integers(0, P.STELLA_1_5B.vocab_size, (6, 256)).astype(np.int64)
+    mask = np.ones_like(ids)
+    mask[2, 200:] = 0
+    mask[5, 17:] = 0
+    emb = enc.encode_tokens(ids, mask, True)
+    ref = oenc.forward_plain(P.STELLA_1_5B, sd, ids, mask, normalize=True)
+    cos = oenc.cosine_rows(emb, ref)
+    assert (1 - cos).max() < COS_TOL, cos

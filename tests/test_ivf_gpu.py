@@ -368,3 +368,53 @@ def test_distributed_build_two_gpus(gpu_pkg):
                         "--master-addr", "127.0.0.1", "--master-port", "29541",
                         os.path.join(root, "tests", "dist_build_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "dist_build_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# ------------------------------------------------------------------ §8f rows on the GPU index --
+def test_parquet_fill_and_tune_on_gpu_index(gpu_pkg, tmp_path, lattice):
+    P = gpu_pkg
+    g, x, q, c = lattice
+    d, nlist, k = int(g["d"]), int(g["nlist"]), int(g["k"])
+    ids = [f"W{i}" for i in range(x.shape[0])]
+    P.store.write_shards(str(tmp_path / "data"), ids, x, shard_size=3000, row_group_size=1024)
+    ix = P.index_factory(d, f"IVF{nlist},Flat", P.METRIC_INNER_PRODUCT)
+    ix.set_centroids(c)
+    assert P.store.fill_index(ix, str(tmp_path / "data"), ids_parquet=str(tmp_path / "ids.parquet")) == x.shape[0]
+    assert np.array_equal(ix.list_sizes(), g["sizes"])
+    ix.nprobe = int(g["nprobe"])
+    D, I = ix.search(q, k)
+    assert np.array_equal(I, g["I"]) and np.array_equal(D, g["D"])
+    names = P.faiss_io.read_ids_parquet(str(tmp_path / "ids.parquet"))
+    assert names[int(I[0, 0])] == f"W{int(I[0, 0])}"
+    # tune: exact ground truth from a flat index; recall grows with nprobe and reaches 1 at nlist
+    flat = P.IndexFlatIP(d)
+    flat.add(x)
+    pts = P.tune.sweep(ix, q, k, nprobes=[1, 4, int(g["nprobe"]), nlist], ground_truth=flat, repeats=1)
+    rec = [p["recall"] for p in pts]
+    assert rec == sorted(rec) and rec[-1] == 1.0
+    choice = P.tune.tune(ix, q, k, min_recall=0.9, nprobes=[1, 4, 16, nlist], ground_truth=flat,
+                         params_path=str(tmp_path / "params.json"))
+    assert choice["recall"] >= 0.9 and ix.nprobe == choice["nprobe"]
+
+
+def test_baseline_config0_flat_10k(gpu_pkg):
+    """BASELINE configs[0], index half: IndexFlatIP k=10 over 10k x 1024 (gaussian unit vectors, the
+    reference's CPU-runnable case) against the oracle's sgemm + top-k.  ids exact where the fp64
+    k/k+1 margin exceeds the fp32 rounding bound, scores within 1e-5."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((10000, 1024)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = rng.standard_normal((64, 1024)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    ix = gpu_pkg.IndexFlatIP(1024)
+    ix.add(x)
+    D, I = ix.search(q, 10)
+    o = oivf.FlatIP(1024)
+    o.add(x)
+    Do, Io = o.search(q, 10)
+    s64 = np.sort(o.scores_f64(q), axis=1)[:, ::-1]
+    margin = (s64[:, :10] - s64[:, 1:11]).min(axis=1)
+    safe = margin > 1e-5
+    assert safe.sum() >= 50
+    assert np.array_equal(I[safe], Io[safe])
+    assert np.abs(D - Do).max() < 1e-5
