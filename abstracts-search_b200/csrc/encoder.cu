@@ -367,6 +367,7 @@ struct Encoder {
   std::vector<Layer> layers;
   DBuf<float2> rope_cs;
   bool weights_ready = false;
+  int attention_impl = 1;  // 1 = tcgen05 kernel for S <= 256 (mma.sync kernel above that), 0 = always mma.sync
 
   // activations (sized for cap_tokens)
   int64_t cap_tokens = 0, cap_batch = 0;
@@ -652,10 +653,15 @@ struct Encoder {
       }
       {
         Span sp(this, st, 1);
-        const int units = (nh / nkv) * (int)ceil_div(S, 16);
-        dim3 grid((unsigned)ceil_div(units, kAttnWarps), (unsigned)nkv, (unsigned)B);
-        attention_kernel<<<grid, kAttnWarps * 32, 0, st>>>(qkv.p, QKV, mask, ao.p, nh * kHD, S, nh, nkv, cfg.causal, scale_log2);
-        ABSB_CUDA(cudaGetLastError());
+        if (attention_impl != 0 && attention_tc_supported(S)) {
+          // tcgen05: S = QK^T and O = PV on the 5th-gen tensor cores, P kept in TMEM
+          attention_tc(qkv.p, QKV, mask, ao.p, nh * kHD, B, S, nh, nkv, cfg.causal, scale_log2, st);
+        } else {
+          const int units = (nh / nkv) * (int)ceil_div(S, 16);
+          dim3 grid((unsigned)ceil_div(units, kAttnWarps), (unsigned)nkv, (unsigned)B);
+          attention_kernel<<<grid, kAttnWarps * 32, 0, st>>>(qkv.p, QKV, mask, ao.p, nh * kHD, S, nh, nkv, cfg.causal, scale_log2);
+          ABSB_CUDA(cudaGetLastError());
+        }
       }
       last_flops += 4.0 * (double)B * S * S * kHD * nh;
       gemm(EPI_F32_ADD, (int)T, H, nh * kHD, ao.p, L.wo.p, h.p, H, nullptr, st);
@@ -807,6 +813,14 @@ int absb_enc_last_stats(absb_enc_t e, double* flops, int64_t* launches) {
   NEED(e);
   if (flops) *flops = e->enc.last_flops;
   if (launches) *launches = e->enc.last_launches;
+  ABSB_API_END
+}
+
+int absb_enc_set_attention_impl(absb_enc_t e, int impl) {
+  ABSB_API_BEGIN
+  NEED(e);
+  ABSB_CHECK(impl == 0 || impl == 1, ABSB_ERR_INVALID, "attention impl %d", impl);
+  e->enc.attention_impl = impl;
   ABSB_API_END
 }
 

@@ -490,6 +490,14 @@ void launch_epi(int epi, const void* A, int64_t a_rows, int64_t a_cols, int64_t 
   }
 }
 
+}  // namespace
+
+CUtensorMap make_tmap_bf16(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  return make_tmap(base, rows, cols, ld, box_rows);
+}
+
+namespace {
+
 int g_gemm_variant = 0;  // 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3 = CTA pair x BN 192
 
 }  // namespace

@@ -1,6 +1,7 @@
 // gemm_tc.cuh — host interface of the tcgen05 GEMM (gemm_tc.cu).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -48,6 +49,15 @@ void gemm_bf16_tc(int epi, int M, int N, int K, const void* A, int64_t lda, cons
 int argmax_partials_per_row(int N);
 void gemm_split3_argmax(int M, int N, int K, const void* A3, const void* B3, float* ws_max, int* ws_idx,
                         long long* out_idx, float* out_score, int sms, cudaStream_t st);
+
+// TMA descriptor of a bf16 row-major matrix [rows, cols] (pitch ld elements): boxes of 64 columns x
+// box_rows rows, SWIZZLE_128B.
+CUtensorMap make_tmap_bf16(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
+// attention_tc.cu: tcgen05 attention for S <= 256 (qkv bf16 [B*S, ld], out bf16 [B*S, ldo])
+bool attention_tc_supported(int S);
+void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, int B, int S, int nh, int nkv,
+                  int causal, float scale_log2, cudaStream_t st);
 
 // test hook: 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3 = CTA pair x BN 192
 void gemm_set_variant(int v);

@@ -313,6 +313,10 @@ class Encoder:
         check(lib().absb_enc_last_stats(self._h, byref(f), byref(l)))
         return {"flops": f.value, "launches": l.value}
 
+    def set_attention_impl(self, impl: int):
+        """1 = tcgen05 attention for S <= 256 (default), 0 = always the mma.sync kernel."""
+        check(lib().absb_enc_set_attention_impl(self._h, int(impl)))
+
     def set_profile(self, on: int):
         check(lib().absb_enc_set_profile(self._h, int(on)))
 

@@ -201,3 +201,31 @@ def test_baseline_config0_encode_full_size(gpu_pkg):
     ref = oenc.forward_plain(P.STELLA_1_5B, sd, ids, mask, normalize=True)
     cos = oenc.cosine_rows(emb, ref)
     assert (1 - cos).max() < COS_TOL, cos
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("S", [1, 7, 16, 33, 64, 100, 128, 129, 200, 256])
+def test_attention_kernels_all_lengths(gpu_pkg, S, impl):
+    """Both attention kernels (tcgen05 for S <= 256, mma.sync) over sequence lengths that exercise every
+    tile shape: several q heads packed into one 128-row tile (S < 128), row tiles past the sequence end,
+    key counts that are not a multiple of 32, ragged padding, GQA with 6 q heads per kv head, causal."""
+    P = gpu_pkg
+    for causal in (False, True):
+        base = TinyCfg(num_heads=6, num_kv_heads=1, hidden_size=256, intermediate_size=256, num_layers=1, causal=causal)
+        sd = oenc.random_state_dict(base, seed=S, std=0.08)
+        enc = _loaded(P, base, sd)
+        enc.set_attention_impl(impl)
+        rng = np.random.default_rng(S)
+        B = 3
+        ids = rng.integers(0, base.vocab_size, (B, S)).astype(np.int64)
+        mask = np.ones((B, S), dtype=np.int64)
+        if S > 2:
+            mask[1, S // 2:] = 0
+            mask[2, S - 1:] = 0
+        emb = enc.encode_tokens(ids, mask, True)
+        ref, hid = oenc.forward_plain(base, sd, ids, mask, normalize=True, return_hidden=True)
+        h = enc.last_hidden_state(B, S)
+        mm = mask.astype(bool)
+        rel = np.abs(h - hid)[mm].max() / np.abs(hid)[mm].max()
+        assert rel < 3e-2, (S, impl, causal, rel)
+        assert (1 - oenc.cosine_rows(emb, ref)).max() < COS_TOL, (S, impl, causal)
