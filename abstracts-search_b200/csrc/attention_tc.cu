@@ -208,13 +208,310 @@ __global__ __launch_bounds__(kThreads) void attention_tc_kernel(const __grid_con
   }
 }
 
+
+// ================================================================================================
+// Persistent, warp-specialised version: one CTA per SM walks a contiguous range of tiles.
+//   warp 0      TMA producer: K/V once per (sequence, kv head) into a 1-2 stage ring (+ the key-valid
+//               bit mask), Q per tile into a 2-stage ring
+//   warp 1      MMA issuer: S = Q K^T of tile i is issued before P V of tile i-1, so the tensor core
+//               works on one tile while the softmax warps work on the other
+//   warps 4-7   softmax + epilogue of even tiles (TMEM slot 0: columns [0, 256))
+//   warps 8-11  softmax + epilogue of odd tiles  (TMEM slot 1: columns [256, 512))
+// ================================================================================================
+constexpr int kPThreads = 384;
+
+struct TileInfo {
+  int unit, b, kvh, h0, p0, nheads;
+  bool first_of_unit, last_of_unit;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const AttnParams& p, int t, int tiles_per_unit, int t_begin, int t_end) {
+  TileInfo ti;
+  ti.unit = t / tiles_per_unit;
+  const int blk = t - ti.unit * tiles_per_unit;
+  ti.b = ti.unit / p.nkv;
+  ti.kvh = ti.unit - ti.b * p.nkv;
+  const int group = p.nh / p.nkv;
+  if (p.heads_per_blk == 1) {
+    ti.h0 = blk / p.blks_per_head;
+    ti.p0 = (blk - ti.h0 * p.blks_per_head) * 128;
+    ti.nheads = 1;
+  } else {
+    ti.h0 = blk * p.heads_per_blk;
+    ti.p0 = 0;
+    ti.nheads = min(p.heads_per_blk, group - ti.h0);
+  }
+  ti.first_of_unit = (t == t_begin) || blk == 0;
+  ti.last_of_unit = (t == t_end - 1) || blk == tiles_per_unit - 1;
+  return ti;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int KVS>
+__global__ __launch_bounds__(kPThreads, 1) void attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                               const __grid_constant__ CUtensorMap tmKV,
+                                                                               const AttnParams p, int total_tiles,
+                                                                               int tiles_per_unit) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int NK = p.NK;
+  const uint32_t kv_half = (uint32_t)NK * 128u;
+  const uint32_t kv_stage = 4 * kv_half;       // K halves, V halves
+  uint8_t* sQ = smem;                           // [2 stages][2 halves][128][128 B]
+  uint8_t* sKV = sQ + 2 * 32768;                // [KVS][K0 K1 V0 V1]
+  uint32_t* kvalid = reinterpret_cast<uint32_t*>(sKV + KVS * kv_stage);  // [KVS][8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kvalid + KVS * 8);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* q_empty = bars + 2;       // [2]
+  uint64_t* kv_full = bars + 4;       // [2]
+  uint64_t* kv_empty = bars + 6;      // [2]
+  uint64_t* s_full = bars + 8;        // [2]
+  uint64_t* p_ready = bars + 10;      // [2]
+  uint64_t* o_full = bars + 12;       // [2]
+  uint64_t* slot_free = bars + 14;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int per = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = min(total_tiles, (int)blockIdx.x * per), t_end = min(total_tiles, t_begin + per);
+  const int group = p.nh / p.nkv;
+  const int S = p.S;
+
+  if (tid == 0) {
+    tc::prefetch_tmap(&tmQ);
+    tc::prefetch_tmap(&tmKV);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(q_full + i, 1);
+      tc::mbar_init(q_empty + i, 1);
+      tc::mbar_init(kv_full + i, 1);
+      tc::mbar_init(kv_empty + i, 1);
+      tc::mbar_init(s_full + i, 1);
+      tc::mbar_init(p_ready + i, 4);
+      tc::mbar_init(o_full + i, 1);
+      tc::mbar_init(slot_free + i, 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc<1>(tmem_slot, 512);
+    tc::tmem_relinquish<1>();
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    int n_unit = -1;  // units seen by this CTA so far - 1
+    for (int t = t_begin; t < t_end; ++t) {
+      const int i = t - t_begin;
+      const TileInfo ti = decode_tile(p, t, tiles_per_unit, t_begin, t_end);
+      const int64_t tok0 = (int64_t)ti.b * S;
+      if (ti.first_of_unit) {
+        ++n_unit;
+        const int ks = n_unit % KVS;
+        const uint32_t kph = (uint32_t)(n_unit / KVS) & 1u;
+        tc::mbar_wait(kv_empty + ks, kph ^ 1);
+        // key-valid bits: real token of this sequence (padding and rows past S are masked out)
+        for (int c = 0; c < NK; c += 32) {
+          const int k = c + lane;
+          const bool ok = k < S && p.mask[tok0 + k] != 0;
+          const unsigned w = __ballot_sync(0xffffffffu, ok);
+          if (lane == 0) kvalid[ks * 8 + (c >> 5)] = w;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          uint8_t* st = sKV + ks * kv_stage;
+          tc::mbar_arrive_expect_tx(kv_full + ks, kv_stage);
+          for (int half = 0; half < 2; ++half) {
+            tc::tma_load_2d(st + half * kv_half, &tmKV, kv_full + ks, (p.nh + ti.kvh) * kHD + half * 64, (int)tok0);
+            tc::tma_load_2d(st + (2 + half) * kv_half, &tmKV, kv_full + ks, (p.nh + p.nkv + ti.kvh) * kHD + half * 64,
+                            (int)tok0);
+          }
+        }
+      }
+      if (lane == 0) {
+        const int qs = i & 1;
+        tc::mbar_wait(q_empty + qs, ((uint32_t)(i >> 1) & 1u) ^ 1);
+        tc::mbar_arrive_expect_tx(q_full + qs, (uint32_t)ti.nheads * 2u * (uint32_t)p.RB * 128u);
+        for (int h = 0; h < ti.nheads; ++h)
+          for (int half = 0; half < 2; ++half)
+            tc::tma_load_2d(sQ + qs * 32768 + half * 16384 + h * p.RB * 128, &tmQ, q_full + qs,
+                            (ti.kvh * group + ti.h0 + h) * kHD + half * 64, (int)(tok0 + ti.p0));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc1 = tc::make_idesc_bf16_f32(128, NK);
+      const uint32_t idesc2 = tc::make_idesc_bf16_f32(128, kHD, 1);
+      int n_unit = -1;
+      int prev_ks = 0;
+      bool prev_last = false;
+      auto issue_pv = [&](int i, int ks, bool last_of_unit) {
+        const int slot = i & 1;
+        const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+        tc::mbar_wait(p_ready + slot, ph);
+        tc::tcgen05_fence_after();
+        const uint32_t sv = tc::smem_u32(sKV + ks * kv_stage + 2 * kv_half);
+        const uint32_t tb = tmem_base + (uint32_t)(slot * 256);
+        for (int j = 0; j < NK / 16; ++j) {
+          const uint64_t db = tc::make_mnmajor_sw128_desc(sv + (uint32_t)j * 2048u, kv_half);
+          tc::umma_bf16_ts(tb + kOCol, tb + (uint32_t)(j * 8), db, idesc2, j != 0 ? 1u : 0u);
+        }
+        tc::umma_commit<1>(o_full + slot);
+        if (last_of_unit) tc::umma_commit<1>(kv_empty + ks);
+      };
+      for (int t = t_begin; t < t_end; ++t) {
+        const int i = t - t_begin;
+        const TileInfo ti = decode_tile(p, t, tiles_per_unit, t_begin, t_end);
+        if (ti.first_of_unit) ++n_unit;
+        const int ks = n_unit % KVS;
+        // a single K/V stage must be drained by the previous tile's P V before it can be refilled
+        const bool pv_first = (KVS == 1) && ti.first_of_unit && i > 0;
+        if (pv_first) issue_pv(i - 1, prev_ks, prev_last);
+        const int qs = i & 1, slot = i & 1;
+        const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+        tc::mbar_wait(q_full + qs, ph);
+        if (ti.first_of_unit) tc::mbar_wait(kv_full + ks, (uint32_t)(n_unit / KVS) & 1u);
+        tc::mbar_wait(slot_free + slot, ph ^ 1);
+        tc::tcgen05_fence_after();
+        const uint32_t sq = tc::smem_u32(sQ + qs * 32768);
+        const uint32_t sk = tc::smem_u32(sKV + ks * kv_stage);
+#pragma unroll
+        for (int j = 0; j < kHD / 16; ++j) {
+          const uint32_t off = (uint32_t)(j >> 2), within = (uint32_t)(j & 3) * 32u;
+          const uint64_t da = tc::make_kmajor_sw128_desc(sq + off * 16384u + within);
+          const uint64_t db = tc::make_kmajor_sw128_desc(sk + off * kv_half + within);
+          tc::umma_bf16<1>(tmem_base + (uint32_t)(slot * 256), da, db, idesc1, j != 0 ? 1u : 0u);
+        }
+        tc::umma_commit<1>(s_full + slot);
+        tc::umma_commit<1>(q_empty + qs);
+        if (i > 0 && !pv_first) issue_pv(i - 1, prev_ks, prev_last);
+        prev_ks = ks;
+        prev_last = ti.last_of_unit;
+      }
+      if (t_end > t_begin) issue_pv(t_end - t_begin - 1, prev_ks, prev_last);
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax + epilogue =====================
+    const int grp = (warp - 4) >> 2;  // tiles with (i & 1) == grp
+    const int row = (warp & 3) * 32 + lane;
+    int n_unit = -1;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int i = t - t_begin;
+      const TileInfo ti = decode_tile(p, t, tiles_per_unit, t_begin, t_end);
+      if (ti.first_of_unit) ++n_unit;
+      if ((i & 1) != grp) continue;
+      const int ks = n_unit % KVS;
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      const int sub = row / p.RB;
+      const int pos = ti.p0 + row - sub * p.RB;
+      const bool row_ok = sub < ti.nheads && pos < S;
+      const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * 256);
+      tc::mbar_wait(s_full + grp, ph);
+      tc::tcgen05_fence_after();
+      // pass A: row maximum of the raw scores over the valid keys
+      float m = -INFINITY;
+      for (int c = 0; c < NK; c += 32) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(t_row + c, v);
+        unsigned km = kvalid[ks * 8 + (c >> 5)];
+        if (p.causal) km &= pos < c ? 0u : (pos - c >= 31 ? 0xffffffffu : ((2u << (pos - c)) - 1u));
+        tc::tmem_ld_wait();
+        if (km == 0xffffffffu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if ((km >> j) & 1u) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+      }
+      const float ms = (m == -INFINITY || !(m == m)) ? 0.f : m * p.scale_log2;
+      // pass B: probabilities -> packed bf16 back into TMEM, row sum
+      float sum = 0.f;
+      for (int c = 0; c < NK; c += 32) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(t_row + c, v);
+        unsigned km = kvalid[ks * 8 + (c >> 5)];
+        if (p.causal) km &= pos < c ? 0u : (pos - c >= 31 ? 0xffffffffu : ((2u << (pos - c)) - 1u));
+        tc::tmem_ld_wait();
+        uint32_t pk[16];
+        if (km == 0xffffffffu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -ms));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -ms));
+            sum += e0 + e1;
+            pk[j] = pack2(e0, e1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -ms));
+            float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -ms));
+            if (!((km >> (2 * j)) & 1u)) e0 = 0.f;
+            if (!((km >> (2 * j + 1)) & 1u)) e1 = 0.f;
+            sum += e0 + e1;
+            pk[j] = pack2(e0, e1);
+          }
+        }
+        tc::tmem_st_32x16(t_row + (c >> 1), pk);
+      }
+      tc::tmem_st_wait();
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(p_ready + grp);
+      // epilogue
+      tc::mbar_wait(o_full + grp, ph);
+      tc::tcgen05_fence_after();
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      __nv_bfloat16* orow =
+          p.out + (size_t)((int64_t)ti.b * S + pos) * p.ldo + (size_t)(ti.kvh * group + ti.h0 + sub) * kHD;
+#pragma unroll 1
+      for (int c = 0; c < kHD; c += 32) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(t_row + kOCol + c, v);
+        tc::tmem_ld_wait();
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(pack2(__uint_as_float(v[j * 8]) * inv, __uint_as_float(v[j * 8 + 1]) * inv),
+                                pack2(__uint_as_float(v[j * 8 + 2]) * inv, __uint_as_float(v[j * 8 + 3]) * inv),
+                                pack2(__uint_as_float(v[j * 8 + 4]) * inv, __uint_as_float(v[j * 8 + 5]) * inv),
+                                pack2(__uint_as_float(v[j * 8 + 6]) * inv, __uint_as_float(v[j * 8 + 7]) * inv));
+        }
+      }
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(slot_free + grp);
+    }
+  }
+
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tcgen05_fence_after();
+    tc::tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 bool attention_tc_supported(int S) { return S >= 1 && S <= 256; }
 
 // qkv: bf16 [B*S, ld] = [q heads | k heads | v heads] x 128; out: bf16 [B*S, ldo] = q heads x 128
 void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, int B, int S, int nh, int nkv,
-                  int causal, float scale_log2, cudaStream_t st) {
+                  int causal, float scale_log2, int sms, bool persistent, cudaStream_t st) {
   ABSB_CHECK(attention_tc_supported(S), ABSB_ERR_INVALID, "attention_tc: S=%d outside [1,256]", S);
   AttnParams p{};
   p.S = S;
@@ -242,6 +539,25 @@ void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, 
   const int64_t T = (int64_t)B * S;
   const CUtensorMap tmQ = make_tmap_bf16(qkv, T, ld, ld, p.RB);
   const CUtensorMap tmKV = make_tmap_bf16(qkv, T, ld, ld, p.NK);
+  if (persistent) {
+    const int tiles_per_unit = blocks;
+    const int total = tiles_per_unit * nkv * B;
+    const int kvs = p.NK <= 128 ? 2 : 1;
+    const size_t smem_p = 1024 + 2 * 32768 + (size_t)kvs * 4 * p.NK * 128 + 2 * 8 * 4 + 16 * 8 + 16;
+    static bool configured_p = false;
+    if (!configured_p) {
+      ABSB_CUDA(cudaFuncSetAttribute(attention_tc_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      ABSB_CUDA(cudaFuncSetAttribute(attention_tc_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      configured_p = true;
+    }
+    const int grid_p = std::max(1, std::min(total, sms));
+    if (kvs == 2)
+      attention_tc_persistent_kernel<2><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
+    else
+      attention_tc_persistent_kernel<1><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
+    ABSB_CUDA(cudaGetLastError());
+    return;
+  }
   const size_t smem = 1024 + 2 * 128 * 128 + 4 * (size_t)p.NK * 128 + 256 * 4 + 4 * 8 + 16;
   static bool configured = false;
   if (!configured) {

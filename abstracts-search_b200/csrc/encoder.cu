@@ -367,7 +367,8 @@ struct Encoder {
   std::vector<Layer> layers;
   DBuf<float2> rope_cs;
   bool weights_ready = false;
-  int attention_impl = 1;  // 1 = tcgen05 kernel for S <= 256 (mma.sync kernel above that), 0 = always mma.sync
+  int attention_impl = 1;  // 1 = persistent tcgen05 kernel for S <= 256 (mma.sync above that), 2 = one-tile-per-CTA
+                           // tcgen05 kernel, 0 = always mma.sync
 
   // activations (sized for cap_tokens)
   int64_t cap_tokens = 0, cap_batch = 0;
@@ -655,7 +656,8 @@ struct Encoder {
         Span sp(this, st, 1);
         if (attention_impl != 0 && attention_tc_supported(S)) {
           // tcgen05: S = QK^T and O = PV on the 5th-gen tensor cores, P kept in TMEM
-          attention_tc(qkv.p, QKV, mask, ao.p, nh * kHD, B, S, nh, nkv, cfg.causal, scale_log2, st);
+          attention_tc(qkv.p, QKV, mask, ao.p, nh * kHD, B, S, nh, nkv, cfg.causal, scale_log2, props.sm_count,
+                       attention_impl == 1, st);
         } else {
           const int units = (nh / nkv) * (int)ceil_div(S, 16);
           dim3 grid((unsigned)ceil_div(units, kAttnWarps), (unsigned)nkv, (unsigned)B);
@@ -819,7 +821,7 @@ int absb_enc_last_stats(absb_enc_t e, double* flops, int64_t* launches) {
 int absb_enc_set_attention_impl(absb_enc_t e, int impl) {
   ABSB_API_BEGIN
   NEED(e);
-  ABSB_CHECK(impl == 0 || impl == 1, ABSB_ERR_INVALID, "attention impl %d", impl);
+  ABSB_CHECK(impl >= 0 && impl <= 2, ABSB_ERR_INVALID, "attention impl %d", impl);
   e->enc.attention_impl = impl;
   ABSB_API_END
 }

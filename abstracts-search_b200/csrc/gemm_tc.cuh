@@ -57,7 +57,7 @@ CUtensorMap make_tmap_bf16(const void* base, int64_t rows, int64_t cols, int64_t
 // attention_tc.cu: tcgen05 attention for S <= 256 (qkv bf16 [B*S, ld], out bf16 [B*S, ldo])
 bool attention_tc_supported(int S);
 void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, int B, int S, int nh, int nkv,
-                  int causal, float scale_log2, cudaStream_t st);
+                  int causal, float scale_log2, int sms, bool persistent, cudaStream_t st);
 
 // test hook: 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3 = CTA pair x BN 192
 void gemm_set_variant(int v);

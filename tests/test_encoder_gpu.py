@@ -203,7 +203,7 @@ def test_baseline_config0_encode_full_size(gpu_pkg):
     assert (1 - cos).max() < COS_TOL, cos
 
 
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [1, 2, 0])
 @pytest.mark.parametrize("S", [1, 7, 16, 33, 64, 100, 128, 129, 200, 256])
 def test_attention_kernels_all_lengths(gpu_pkg, S, impl):
     """Both attention kernels (tcgen05 for S <= 256, mma.sync) over sequence lengths that exercise every
@@ -216,7 +216,7 @@ def test_attention_kernels_all_lengths(gpu_pkg, S, impl):
         enc = _loaded(P, base, sd)
         enc.set_attention_impl(impl)
         rng = np.random.default_rng(S)
-        B = 3
+        B = 3 if S > 64 else 37  # many tiles per CTA: ring phases wrap, units change mid-CTA
         ids = rng.integers(0, base.vocab_size, (B, S)).astype(np.int64)
         mask = np.ones((B, S), dtype=np.int64)
         if S > 2:
