@@ -349,56 +349,65 @@ __global__ __launch_bounds__(kPThreads, 1) void attention_tc_persistent_kernel(c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // Dynamic order: whichever of {P V of the oldest tile whose probabilities are ready, Q K^T of the
+    // next tile whose operands and TMEM slot are ready} can go is issued first, so a finished softmax
+    // never waits behind a Q K^T that is itself waiting for an epilogue.
     if (lane == 0) {
       const uint32_t idesc1 = tc::make_idesc_bf16_f32(128, NK);
       const uint32_t idesc2 = tc::make_idesc_bf16_f32(128, kHD, 1);
+      const int n_tiles = t_end - t_begin;
+      int next_qk = 0, next_pv = 0;
       int n_unit = -1;
-      int prev_ks = 0;
-      bool prev_last = false;
-      auto issue_pv = [&](int i, int ks, bool last_of_unit) {
-        const int slot = i & 1;
-        const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-        tc::mbar_wait(p_ready + slot, ph);
-        tc::tcgen05_fence_after();
-        const uint32_t sv = tc::smem_u32(sKV + ks * kv_stage + 2 * kv_half);
-        const uint32_t tb = tmem_base + (uint32_t)(slot * 256);
-        for (int j = 0; j < NK / 16; ++j) {
-          const uint64_t db = tc::make_mnmajor_sw128_desc(sv + (uint32_t)j * 2048u, kv_half);
-          tc::umma_bf16_ts(tb + kOCol, tb + (uint32_t)(j * 8), db, idesc2, j != 0 ? 1u : 0u);
+      int ks_of[2] = {0, 0};
+      bool last_of[2] = {false, false};
+      while (next_pv < n_tiles) {
+        // ---- P V of tile next_pv ----
+        if (next_pv < next_qk) {
+          const int j = next_pv, slot = j & 1;
+          if (tc::mbar_test_wait(p_ready + slot, (uint32_t)(j >> 1) & 1u)) {
+            tc::tcgen05_fence_after();
+            const int ks = ks_of[slot];
+            const uint32_t sv = tc::smem_u32(sKV + ks * kv_stage + 2 * kv_half);
+            const uint32_t tb = tmem_base + (uint32_t)(slot * 256);
+            for (int k = 0; k < NK / 16; ++k) {
+              const uint64_t db = tc::make_mnmajor_sw128_desc(sv + (uint32_t)k * 2048u, kv_half);
+              tc::umma_bf16_ts(tb + kOCol, tb + (uint32_t)(k * 8), db, idesc2, k != 0 ? 1u : 0u);
+            }
+            tc::umma_commit<1>(o_full + slot);
+            if (last_of[slot]) tc::umma_commit<1>(kv_empty + ks);
+            ++next_pv;
+          }
         }
-        tc::umma_commit<1>(o_full + slot);
-        if (last_of_unit) tc::umma_commit<1>(kv_empty + ks);
-      };
-      for (int t = t_begin; t < t_end; ++t) {
-        const int i = t - t_begin;
-        const TileInfo ti = decode_tile(p, t, tiles_per_unit, t_begin, t_end);
-        if (ti.first_of_unit) ++n_unit;
-        const int ks = n_unit % KVS;
-        // a single K/V stage must be drained by the previous tile's P V before it can be refilled
-        const bool pv_first = (KVS == 1) && ti.first_of_unit && i > 0;
-        if (pv_first) issue_pv(i - 1, prev_ks, prev_last);
-        const int qs = i & 1, slot = i & 1;
-        const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-        tc::mbar_wait(q_full + qs, ph);
-        if (ti.first_of_unit) tc::mbar_wait(kv_full + ks, (uint32_t)(n_unit / KVS) & 1u);
-        tc::mbar_wait(slot_free + slot, ph ^ 1);
-        tc::tcgen05_fence_after();
-        const uint32_t sq = tc::smem_u32(sQ + qs * 32768);
-        const uint32_t sk = tc::smem_u32(sKV + ks * kv_stage);
+        // ---- Q K^T of tile next_qk ----
+        if (next_qk < n_tiles && next_qk - next_pv < 2) {
+          const int i = next_qk, qs = i & 1, slot = i & 1;
+          const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+          const TileInfo ti = decode_tile(p, t_begin + i, tiles_per_unit, t_begin, t_end);
+          const int nu = n_unit + (ti.first_of_unit ? 1 : 0);
+          const int ks = nu % KVS;
+          // a single K/V stage is refilled only after the previous unit's last P V: that one goes first
+          const bool blocked = (KVS == 1) && ti.first_of_unit && i > 0 && next_pv < i;
+          if (!blocked && tc::mbar_test_wait(q_full + qs, ph) && tc::mbar_test_wait(slot_free + slot, ph ^ 1) &&
+              (!ti.first_of_unit || tc::mbar_test_wait(kv_full + ks, (uint32_t)(nu / KVS) & 1u))) {
+            tc::tcgen05_fence_after();
+            const uint32_t sq = tc::smem_u32(sQ + qs * 32768);
+            const uint32_t sk = tc::smem_u32(sKV + ks * kv_stage);
 #pragma unroll
-        for (int j = 0; j < kHD / 16; ++j) {
-          const uint32_t off = (uint32_t)(j >> 2), within = (uint32_t)(j & 3) * 32u;
-          const uint64_t da = tc::make_kmajor_sw128_desc(sq + off * 16384u + within);
-          const uint64_t db = tc::make_kmajor_sw128_desc(sk + off * kv_half + within);
-          tc::umma_bf16<1>(tmem_base + (uint32_t)(slot * 256), da, db, idesc1, j != 0 ? 1u : 0u);
+            for (int k = 0; k < kHD / 16; ++k) {
+              const uint32_t off = (uint32_t)(k >> 2), within = (uint32_t)(k & 3) * 32u;
+              const uint64_t da = tc::make_kmajor_sw128_desc(sq + off * 16384u + within);
+              const uint64_t db = tc::make_kmajor_sw128_desc(sk + off * kv_half + within);
+              tc::umma_bf16<1>(tmem_base + (uint32_t)(slot * 256), da, db, idesc1, k != 0 ? 1u : 0u);
+            }
+            tc::umma_commit<1>(s_full + slot);
+            tc::umma_commit<1>(q_empty + qs);
+            n_unit = nu;
+            ks_of[slot] = ks;
+            last_of[slot] = ti.last_of_unit;
+            ++next_qk;
+          }
         }
-        tc::umma_commit<1>(s_full + slot);
-        tc::umma_commit<1>(q_empty + qs);
-        if (i > 0 && !pv_first) issue_pv(i - 1, prev_ks, prev_last);
-        prev_ks = ks;
-        prev_last = ti.last_of_unit;
       }
-      if (t_end > t_begin) issue_pv(t_end - t_begin - 1, prev_ks, prev_last);
     }
   } else if (warp >= 4) {
     // ===================== softmax + epilogue =====================
@@ -418,77 +427,120 @@ __global__ __launch_bounds__(kPThreads, 1) void attention_tc_persistent_kernel(c
       const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * 256);
       tc::mbar_wait(s_full + grp, ph);
       tc::tcgen05_fence_after();
-      // pass A: row maximum of the raw scores over the valid keys
-      float m = -INFINITY;
-      for (int c = 0; c < NK; c += 32) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(t_row + c, v);
+      auto key_mask = [&](int c) -> unsigned {
         unsigned km = kvalid[ks * 8 + (c >> 5)];
         if (p.causal) km &= pos < c ? 0u : (pos - c >= 31 ? 0xffffffffu : ((2u << (pos - c)) - 1u));
-        tc::tmem_ld_wait();
-        if (km == 0xffffffffu) {
+        return km;
+      };
+      // pass A: row maximum of the raw scores over the valid keys (TMEM loads one chunk ahead)
+      float m = -INFINITY;
+      {
+        uint32_t va[32], vb[32];
+        auto row_max = [&](const uint32_t (&v)[32], int c) {
+          const unsigned km = key_mask(c);
+          if (km == 0xffffffffu) {
+            // four independent chains instead of one 32-deep dependency
+            float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-        } else {
+            for (int j = 0; j < 32; j += 4) {
+              m0 = fmaxf(m0, __uint_as_float(v[j]));
+              m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+              m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+              m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+            }
+            m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if ((km >> j) & 1u) m = fmaxf(m, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j)
+              if ((km >> j) & 1u) m = fmaxf(m, __uint_as_float(v[j]));
+          }
+        };
+        tc::tmem_ld_32x32(t_row, va);
+        for (int c = 0; c < NK; c += 64) {
+          tc::tmem_ld_wait();
+          if (c + 32 < NK) tc::tmem_ld_32x32(t_row + c + 32, vb);
+          row_max(va, c);
+          if (c + 32 < NK) {
+            tc::tmem_ld_wait();
+            if (c + 64 < NK) tc::tmem_ld_32x32(t_row + c + 64, va);
+            row_max(vb, c + 32);
+          }
         }
       }
       const float ms = (m == -INFINITY || !(m == m)) ? 0.f : m * p.scale_log2;
       // pass B: probabilities -> packed bf16 back into TMEM, row sum
       float sum = 0.f;
-      for (int c = 0; c < NK; c += 32) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(t_row + c, v);
-        unsigned km = kvalid[ks * 8 + (c >> 5)];
-        if (p.causal) km &= pos < c ? 0u : (pos - c >= 31 ? 0xffffffffu : ((2u << (pos - c)) - 1u));
-        tc::tmem_ld_wait();
-        uint32_t pk[16];
-        if (km == 0xffffffffu) {
+      {
+        uint32_t va[32], vb[32];
+        auto probs = [&](const uint32_t (&v)[32], int c) {
+          const unsigned km = key_mask(c);
+          uint32_t pk[16];
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          if (km == 0xffffffffu) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -ms));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -ms));
-            sum += e0 + e1;
-            pk[j] = pack2(e0, e1);
+            for (int j = 0; j < 16; j += 2) {
+              const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -ms));
+              const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -ms));
+              const float e2 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 2]), p.scale_log2, -ms));
+              const float e3 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 3]), p.scale_log2, -ms));
+              s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+              pk[j] = pack2(e0, e1);
+              pk[j + 1] = pack2(e2, e3);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -ms));
+              float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -ms));
+              if (!((km >> (2 * j)) & 1u)) e0 = 0.f;
+              if (!((km >> (2 * j + 1)) & 1u)) e1 = 0.f;
+              s0 += e0; s1 += e1;
+              pk[j] = pack2(e0, e1);
+            }
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -ms));
-            float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -ms));
-            if (!((km >> (2 * j)) & 1u)) e0 = 0.f;
-            if (!((km >> (2 * j + 1)) & 1u)) e1 = 0.f;
-            sum += e0 + e1;
-            pk[j] = pack2(e0, e1);
+          sum += (s0 + s1) + (s2 + s3);
+          // P overwrites the (already consumed) low columns of S: keys [c, c+32) -> columns [c/2, c/2+16)
+          tc::tmem_st_32x16(t_row + (c >> 1), pk);
+        };
+        tc::tmem_ld_32x32(t_row, va);
+        for (int c = 0; c < NK; c += 64) {
+          tc::tmem_ld_wait();
+          if (c + 32 < NK) tc::tmem_ld_32x32(t_row + c + 32, vb);
+          probs(va, c);
+          if (c + 32 < NK) {
+            tc::tmem_ld_wait();
+            if (c + 64 < NK) tc::tmem_ld_32x32(t_row + c + 64, va);
+            probs(vb, c + 32);
           }
         }
-        tc::tmem_st_32x16(t_row + (c >> 1), pk);
       }
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(p_ready + grp);
-      // epilogue
+      // epilogue: two 64-column halves, both TMEM loads of a half in flight together
       tc::mbar_wait(o_full + grp, ph);
       tc::tcgen05_fence_after();
       const float inv = sum > 0.f ? 1.f / sum : 0.f;
       __nv_bfloat16* orow =
           p.out + (size_t)((int64_t)ti.b * S + pos) * p.ldo + (size_t)(ti.kvh * group + ti.h0 + sub) * kHD;
 #pragma unroll 1
-      for (int c = 0; c < kHD; c += 32) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(t_row + kOCol + c, v);
+      for (int c = 0; c < kHD; c += 64) {
+        uint32_t v[2][32];
+        tc::tmem_ld_32x32(t_row + kOCol + c, v[0]);
+        tc::tmem_ld_32x32(t_row + kOCol + c + 32, v[1]);
         tc::tmem_ld_wait();
         if (row_ok) {
           uint4* dst = reinterpret_cast<uint4*>(orow + c);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_uint4(pack2(__uint_as_float(v[j * 8]) * inv, __uint_as_float(v[j * 8 + 1]) * inv),
-                                pack2(__uint_as_float(v[j * 8 + 2]) * inv, __uint_as_float(v[j * 8 + 3]) * inv),
-                                pack2(__uint_as_float(v[j * 8 + 4]) * inv, __uint_as_float(v[j * 8 + 5]) * inv),
-                                pack2(__uint_as_float(v[j * 8 + 6]) * inv, __uint_as_float(v[j * 8 + 7]) * inv));
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[h * 4 + j] =
+                  make_uint4(pack2(__uint_as_float(v[h][j * 8]) * inv, __uint_as_float(v[h][j * 8 + 1]) * inv),
+                             pack2(__uint_as_float(v[h][j * 8 + 2]) * inv, __uint_as_float(v[h][j * 8 + 3]) * inv),
+                             pack2(__uint_as_float(v[h][j * 8 + 4]) * inv, __uint_as_float(v[h][j * 8 + 5]) * inv),
+                             pack2(__uint_as_float(v[h][j * 8 + 6]) * inv, __uint_as_float(v[h][j * 8 + 7]) * inv));
         }
       }
       tc::tcgen05_fence_before();
