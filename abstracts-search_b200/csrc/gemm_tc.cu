@@ -19,7 +19,8 @@
 //   warp 2   allocates / frees the 512 TMEM columns (double-buffered accumulator);
 //   warps 4-11 epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused epilogue straight from
 //            registers (each thread owns one output row: 64-128 contiguous bytes per burst; the
-//            residual add is a red.global.add.v4.f32), then release the accumulator (`tmem_empty`,
+//            residual add goes through a swizzled shared-memory box and ONE cp.reduce.async.bulk.tensor
+//            per 32 x 32 block), then release the accumulator (`tmem_empty`,
 //            remote arrive from the peer CTA) so the next tile's MMAs overlap.
 #include <mutex>
 
@@ -37,15 +38,27 @@ constexpr int kThreads = 384;  // TMA, MMA, TMEM-alloc, spare + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;
 constexpr int kTmemCols = 512;   // two accumulator stages at column 0 and 256
 constexpr int kAccStride = 256;
+// Residual-add epilogue: false = red.global.add.v4.f32 straight from the tcgen05.ld registers, true = bulk
+// tensor reduction (cp.reduce.async.bulk.tensor) of 32 x 32 boxes staged in shared memory.  Measured on
+// B200 (tools/gemm_bench.py, T = 16384): O-proj 99 us (red) vs 91 us (bulk reduction), FFN-down 356 vs 364 us;
+// a second staging buffer per warp changed nothing.
+#ifndef ABSB_TMA_REDUCE
+#define ABSB_TMA_REDUCE 1
+#endif
+constexpr bool kTmaReduce = ABSB_TMA_REDUCE != 0;
 
-template <int BN, int NCTA>
+template <int BN, int NCTA, int EPI = EPI_BF16_BIAS>
 struct SmemLayout {
   static constexpr int kBRows = BN / NCTA;  // B rows this CTA stages (a pair splits the N tile)
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (216 * 1024) / kStageBytes;
-  static constexpr int kBarOff = kStages * kStageBytes;
+  // residual-add epilogue: one 32 x 32 fp32 box (4 KB, SWIZZLE_128B) per epilogue warp, the source of
+  // its cp.reduce.async.bulk.tensor
+  static constexpr int kEpiBytes = (EPI == EPI_F32_ADD && kTmaReduce) ? 8 * 4096 : 0;
+  static constexpr int kStages = (216 * 1024 - kEpiBytes) / kStageBytes;
+  static constexpr int kEpiOff = kStages * kStageBytes;
+  static constexpr int kBarOff = kEpiOff + kEpiBytes;
   // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr
   static constexpr int kTotal = kBarOff + (2 * kStages + 4) * 8 + 16;
   static constexpr int kDyn = kTotal + 1024;  // slack for manual 1024-byte alignment
@@ -89,8 +102,9 @@ __device__ __forceinline__ void tile_coords(const KernelParams& p, int tile, int
 template <int BN, int EPI, int NCTA>
 __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                   const __grid_constant__ CUtensorMap tmC,
                                                                    const KernelParams p) {
-  using L = SmemLayout<BN, NCTA>;
+  using L = SmemLayout<BN, NCTA, EPI>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -202,8 +216,8 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
     // ===================== epilogue (every CTA drains its own 128 accumulator rows) ===============
     // 8 warps: warp w reads TMEM lane quarter w % 4 (hardware restriction) and column half (w - 4) / 4.
     // Each thread owns one output row: 32 consecutive columns per tcgen05.ld, written as 64-128
-    // contiguous bytes.  The residual add is a fire-and-forget red.global.add.v4.f32 (every element is
-    // touched by exactly one thread, so the result does not depend on timing).
+    // contiguous bytes.  The residual add is a bulk tensor reduction (every element is added exactly once,
+    // so the result does not depend on timing).
     const int q = warp & 3;
     const int chalf = (warp - kEpiWarp0) >> 2;
     const uint32_t tmem_empty_addr0 = NCTA == 1 ? 0u : tc::map_to_cta(tc::smem_u32(tmem_empty), 0);
@@ -329,7 +343,38 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
           tc::tmem_ld_32x32(t_base + c, v);
           tc::tmem_ld_wait();
           const int col = col0 + c;
-          if (row_ok && col < p.N) {
+          if constexpr (EPI == EPI_F32_ADD && !kTmaReduce) {
+            // fire-and-forget vector reductions: every element is added exactly once, so the result does
+            // not depend on timing
+            if (row_ok && col < p.N) {
+              float* dst = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldc + col;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j * 4),
+                             "f"(__uint_as_float(v[j * 4])), "f"(__uint_as_float(v[j * 4 + 1])),
+                             "f"(__uint_as_float(v[j * 4 + 2])), "f"(__uint_as_float(v[j * 4 + 3]))
+                             : "memory");
+            }
+          } else if constexpr (EPI == EPI_F32_ADD) {
+            // h += acc as ONE bulk tensor reduction per 32 x 32 box: registers -> swizzled shared-memory
+            // box -> cp.reduce.async.bulk.tensor (.add, fp32).  Rows past M are clipped by the tensor map;
+            // every element is added exactly once, so the result does not depend on timing.
+            if (col < p.N) {  // warp-uniform
+              uint8_t* stg = smem + L::kEpiOff + (warp - kEpiWarp0) * 4096;
+              if (lane == 0) tc::bulk_wait_read_all();  // the previous box has left this buffer
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                    make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+              tc::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tc::tma_reduce_add_2d(&tmC, stg, col, (tm * NCTA + cta_rank) * BM + q * 32);
+                tc::bulk_commit_group();
+              }
+            }
+          } else if (row_ok && col < p.N) {
             if constexpr (EPI == EPI_BF16_BIAS) {
               __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
               uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * p.ldc + col);
@@ -353,17 +398,11 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
               for (int j = 0; j < 8; ++j) {
                 float4 f = make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]),
                                        __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
-                if constexpr (EPI == EPI_F32_ADD) {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j * 4), "f"(f.x), "f"(f.y),
-                               "f"(f.z), "f"(f.w)
-                               : "memory");
-                } else {
-                  if (p.bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j * 4));
-                    f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
-                  }
-                  reinterpret_cast<float4*>(dst)[j] = f;
+                if (p.bias) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j * 4));
+                  f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
                 }
+                reinterpret_cast<float4*>(dst)[j] = f;
               }
             }
           }
@@ -380,6 +419,9 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
         acc = 0;
         acc_phase ^= 1;
       }
+    }
+    if constexpr (EPI == EPI_F32_ADD && kTmaReduce) {
+      if (lane == 0) tc::bulk_wait_all();  // reductions performed before the CTA (and its smem) goes away
     }
   }
 
@@ -427,10 +469,26 @@ CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, 
   return m;
 }
 
+// fp32 matrix [rows, cols] with row pitch ld (elements): 32 x 32 boxes, SWIZZLE_128B (the residual stream)
+CUtensorMap make_tmap_f32_box32(const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  ABSB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 4) % 16 == 0, ABSB_ERR_INVALID,
+             "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (ld=%lld)", (long long)ld);
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ABSB_CHECK(r == CUDA_SUCCESS, ABSB_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with %d", (int)r);
+  return m;
+}
+
 template <int BN, int EPI, int NCTA>
 void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const void* B, int64_t b_rows, int64_t b_cols,
             int64_t ldb, KernelParams p, int sms, cudaStream_t st) {
-  using L = SmemLayout<BN, NCTA>;
+  using L = SmemLayout<BN, NCTA, EPI>;
   auto kern = gemm_bf16_tc_kernel<BN, EPI, NCTA>;
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -445,6 +503,7 @@ void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const vo
   p.n_fast = p.tiles_n <= 16 ? 1 : 0;
   const CUtensorMap tmA = make_tmap(A, a_rows, a_cols, lda, BM);
   const CUtensorMap tmB = make_tmap(B, b_rows, b_cols, ldb, L::kBRows);
+  const CUtensorMap tmC = EPI == EPI_F32_ADD ? make_tmap_f32_box32(p.out, p.M, p.N, p.ldc) : tmA;
   const int workers = std::max(1, std::min(p.tiles_m * p.tiles_n, sms / NCTA));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(workers * NCTA));
@@ -458,7 +517,7 @@ void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const vo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ABSB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  ABSB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
 }
 
 template <int BN, int NCTA>
@@ -690,6 +749,20 @@ extern "C" int absb_gemm_set_variant(int variant) {
   ABSB_API_BEGIN
   ABSB_CHECK(variant >= 0 && variant <= 3, ABSB_ERR_INVALID, "GEMM variant %d outside [0,3]", variant);
   absb::gemm_set_variant(variant);
+  ABSB_API_END
+}
+
+extern "C" int absb_gemm_bf16_epi_dev(int device, int epi, int M, int N, int K, const void* A_dev, const void* B_dev,
+                                      void* out_dev, int64_t ldc, const float* bias_dev, void* stream) {
+  ABSB_API_BEGIN
+  using namespace absb;
+  ABSB_CHECK(M >= 0 && N >= 0 && K > 0 && A_dev && B_dev && out_dev, ABSB_ERR_INVALID, "bad GEMM arguments");
+  ABSB_CHECK(epi == EPI_BF16_BIAS || epi == EPI_F32_BIAS || epi == EPI_F32_ADD || epi == EPI_SWIGLU_BF16, ABSB_ERR_INVALID,
+             "epilogue %d is not available through this entry", epi);
+  DeviceGuard g(device);
+  const DeviceProps pr = device_props(device);
+  ABSB_CHECK(pr.cc_major == 10, ABSB_ERR_UNSUPPORTED, "tcgen05 GEMM needs an sm_100 device");
+  gemm_bf16_tc(epi, M, N, K, A_dev, K, B_dev, K, out_dev, ldc, bias_dev, nullptr, pr.sm_count, (cudaStream_t)stream);
   ABSB_API_END
 }
 

@@ -335,6 +335,21 @@ def gemm_set_variant(variant: int = 0):
     check(lib().absb_gemm_set_variant(int(variant)))
 
 
+def gemm_bf16_epi(A, B, epi: int, out=None, bias=None):
+    """The tcgen05 GEMM with a fused epilogue (0 bf16, 1 f32, 2 f32 +=, 3 SwiGLU bf16) — test hook."""
+    import torch
+
+    A, B = A.contiguous(), B.contiguous()
+    M, K = A.shape
+    N = B.shape[0]
+    if out is None:
+        out = torch.empty((M, N // 2 if epi == 3 else N), dtype=torch.bfloat16 if epi in (0, 3) else torch.float32,
+                          device=A.device)
+    check(lib().absb_gemm_bf16_epi_dev(A.device.index or 0, epi, M, N, K, ptr(A), ptr(B), ptr(out), out.shape[1],
+                                       ptr(bias), _lib.current_stream_ptr()))
+    return out
+
+
 def gemm_bf16(A, B):
     """C[M,N] fp32 = A[M,K] @ B[N,K]^T on tcgen05 (CUDA bf16 tensors) — test / micro-benchmark hook."""
     import torch

@@ -259,6 +259,11 @@ int absb_enc_get_profile(absb_enc_t e, double* gemm_ms, double* gemm_flops, doub
 /* Test hook: force the tile shape of the tcgen05 GEMM (0 = automatic; 1 = one CTA, 128x256 tiles;
  * 2 = CTA pair (cta_group::2), 256x256 tiles; 3 = CTA pair, 256x192 tiles). Process-wide. */
 int absb_gemm_set_variant(int variant);
+/* Same GEMM with one of the fused epilogues (gemm_tc.cuh): 0 = bf16 out (+bias), 1 = f32 out (+bias),
+ * 2 = f32 out += acc (residual stream), 3 = bf16 SwiGLU (B rows interleaved per 256-row tile, out
+ * [M, N/2]).  Test / micro-benchmark hook. */
+int absb_gemm_bf16_epi_dev(int device, int epi, int M, int N, int K, const void* A_dev, const void* B_dev,
+                           void* out_dev, int64_t ldc, const float* bias_dev, void* stream);
 int absb_gemm_bf16_dev(int device, int M, int N, int K, const void* A_dev, const void* B_dev,
                        float* C_dev, void* stream);
 

@@ -229,3 +229,35 @@ def test_attention_kernels_all_lengths(gpu_pkg, S, impl):
         rel = np.abs(h - hid)[mm].max() / np.abs(hid)[mm].max()
         assert rel < 3e-2, (S, impl, causal, rel)
         assert (1 - oenc.cosine_rows(emb, ref)).max() < COS_TOL, (S, impl, causal)
+
+
+def test_gemm_fused_epilogues(gpu_pkg):
+    """bias / residual-add (bulk tensor reduction) / SwiGLU epilogues against torch, ragged M."""
+    import torch
+    from importlib import import_module
+
+    enc = import_module("abstracts-search_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for M, N, K in [(300, 1536, 512), (4100, 768, 256), (129, 512, 1024)]:
+        A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+        B = (torch.randn((N, K), device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+        bias = torch.randn((N,), device="cuda", generator=g)
+        ref = A.float() @ B.float().T
+        o1 = enc.gemm_bf16_epi(A, B, 1, bias=bias)
+        assert (o1 - (ref + bias)).abs().max().item() < 2e-3 * max(1.0, K / 256)
+        o0 = enc.gemm_bf16_epi(A, B, 0, bias=bias)
+        assert (o0.float() - (ref + bias)).abs().max().item() < 0.05
+        h = torch.randn((M, N), device="cuda", generator=g)
+        h2 = h.clone()
+        enc.gemm_bf16_epi(A, B, 2, out=h2)
+        enc.gemm_bf16_epi(A, B, 2, out=h2)  # twice: += really accumulates
+        assert (h2 - (h + 2 * ref)).abs().max().item() < 4e-3 * max(1.0, K / 256)
+    # SwiGLU: B rows interleaved per 256-row tile [128 gate | 128 up]
+    M, I, K = 260, 512, 256
+    A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    Wg = (torch.randn((I, K), device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    Wu = (torch.randn((I, K), device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    W = torch.stack([Wg.view(I // 128, 128, K), Wu.view(I // 128, 128, K)], dim=1).reshape(2 * I, K).contiguous()
+    o3 = enc.gemm_bf16_epi(A, W, 3)
+    ref3 = torch.nn.functional.silu(A.float() @ Wg.float().T) * (A.float() @ Wu.float().T)
+    assert (o3.float() - ref3).abs().max().item() < 0.05 * max(1.0, ref3.abs().max().item())

@@ -44,5 +44,18 @@ def main():
         print(" | ".join(row), flush=True)
 
 
+def epilogues():
+    """The four fused epilogues on their encoder shapes, as they run inside a layer."""
+    T = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+    for name, epi, N, K in [("qkv bf16", 0, 2048, 1536), ("o  f32+=", 2, 1536, 1536), ("ffn swiglu", 3, 17920, 1536),
+                            ("down f32+=", 2, 1536, 8960)]:
+        A = torch.randn((T, K), device="cuda").to(torch.bfloat16)
+        B = (torch.randn((N, K), device="cuda") * 0.02).to(torch.bfloat16)
+        out = torch.zeros((T, N // 2 if epi == 3 else N), dtype=torch.bfloat16 if epi in (0, 3) else torch.float32, device="cuda")
+        ms = timeit(lambda: enc.gemm_bf16_epi(A, B, epi, out=out))
+        print(f"epi {name:11s} M={T} N={N} K={K}: {ms*1e3:7.1f} us {2.0*T*N*K/ms/1e9:7.0f} TF", flush=True)
+
+
 if __name__ == "__main__":
     main()
+    epilogues()
