@@ -587,6 +587,14 @@ int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int sca
   ABSB_API_END
 }
 
+int absb_ivf_set_scan_order(absb_ivf_t h, int list_major) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(list_major == 0 || list_major == 1, ABSB_ERR_INVALID, "scan order %d", list_major);
+  h->ix.scan_order = list_major;
+  ABSB_API_END
+}
+
 int absb_ivf_last_stats(absb_ivf_t h, int64_t* vectors_scanned, int64_t* bytes_scanned,
                         int64_t* work_items, int64_t* launches) {
   ABSB_API_BEGIN

@@ -741,9 +741,17 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
       ws_pair_counts.reserve(npairs_max + 1);
       ws_pair_offs.reserve(npairs_max + 1);
       ws_plan_tmp.reserve(plan_scan_tmp_bytes((int)npairs_max) + 16);
+      PlanOrderWs ow{};
+      if (scan_order == 1) {
+        ws_okeys.reserve(npairs_max + 1); ws_okeys_sorted.reserve(npairs_max + 1);
+        ws_ovals.reserve(npairs_max + 1); ws_ovals_sorted.reserve(npairs_max + 1);
+        ws_ocounts.reserve(npairs_max + 1); ws_oqoffs.reserve(npairs_max + 1);
+        ws_order.reserve((size_t)max_items);
+        ow = PlanOrderWs{ws_okeys.p, ws_okeys_sorted.p, ws_ovals.p, ws_ovals_sorted.p, ws_ocounts.p, ws_oqoffs.p, ws_order.p};
+      }
       launch_plan(table(), coarse + q0 * nprobe, nb, nprobe, scan_chunk, (int)max_items, ws_items.p,
                   ws_q_begin.p, ws_counters.p, ws_counters.p + 1, ws_stats.p, ws_pair_counts.p, ws_pair_offs.p,
-                  ws_plan_tmp.p, ws_plan_tmp.cap, st);
+                  ws_plan_tmp.p, ws_plan_tmp.cap, scan_order == 1 ? &ow : nullptr, st);
     }
     ScanLaunch a;
     a.Q = q + q0 * d;
@@ -752,6 +760,7 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
     a.items = ws_items.p;
     a.n_items = ws_counters.p;
     a.queue_counter = ws_counters.p + 1;
+    a.order = scan_order == 1 ? ws_order.p : nullptr;
     a.part_s = ws_part_s.p;
     a.part_id = ws_part_id.p;
     a.sm_count = props.sm_count;
@@ -767,7 +776,7 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
     last_scan = a;
     have_last_scan = true;
     stats_pending = true;
-    stats.launches += 5;
+    stats.launches += scan_order == 1 ? 11 : 5;
     if (q0 + nb_max < nq) fold_stats();
   }
 }

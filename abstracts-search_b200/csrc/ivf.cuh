@@ -70,6 +70,7 @@ struct IvfIndex {
   int scan_chunk = 128;
   int coarse_impl = 1;  // 1 = tcgen05 split-bf16 (falls back to the FFMA GEMM for shapes it cannot take)
   int scan_ctas_per_sm = 0;
+  int scan_order = 1;  // 1 = list-major work queue (probes of one list scanned together: L2 reuse), 0 = query-major
 
   // workspaces (single stream at a time)
   DBuf<float> ws_scores;
@@ -81,6 +82,8 @@ struct IvfIndex {
   DBuf<int> ws_q_begin;
   DBuf<int> ws_pair_counts, ws_pair_offs;  // plan: items per (query, probe) pair and their prefix sums
   DBuf<unsigned char> ws_plan_tmp;
+  DBuf<unsigned> ws_okeys, ws_okeys_sorted;  // list-major queue order (scan_order = 1)
+  DBuf<int> ws_ovals, ws_ovals_sorted, ws_ocounts, ws_oqoffs, ws_order;
   DBuf<int> ws_counters;  // [0] n_items, [1] queue counter
   DBuf<unsigned long long> ws_stats;
   DBuf<unsigned char> ws_cub;

@@ -77,10 +77,19 @@ __device__ __forceinline__ int walk_list(const ListTable& lt, long long l, int c
 // Pass 1: one thread per (query, probe) pair counts the work items of that list.
 __global__ void plan_count_kernel(ListTable lt, const long long* __restrict__ coarse, int npairs, int chunk,
                                   int* __restrict__ counts /* [npairs + 1] */,
+                                  unsigned* __restrict__ keys /* [npairs] list number, or nullptr */,
+                                  int* __restrict__ vals /* [npairs] pair index */,
                                   unsigned long long* __restrict__ stats) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   long long vec = 0;
-  if (i < npairs) counts[i] = walk_list(lt, coarse[i], chunk, 0, nullptr, &vec);
+  if (i < npairs) {
+    const long long l = coarse[i];
+    counts[i] = walk_list(lt, l, chunk, 0, nullptr, &vec);
+    if (keys) {
+      keys[i] = (l >= 0 && l < lt.nlist) ? (unsigned)l : (unsigned)lt.nlist;
+      vals[i] = i;
+    }
+  }
   if (i == npairs) counts[i] = 0;
   // vectors scanned = sum of probed list sizes (statistics only)
 #pragma unroll
@@ -139,16 +148,18 @@ __device__ __forceinline__ ScanItem load_item(const ScanItem* p) {
 template <int SLOTS, int D4, int U>
 __global__ __launch_bounds__(kScanThreads) void ivf_scan_kernel(
     const float* __restrict__ Q, const ScanItem* __restrict__ items, const int* __restrict__ n_items_ptr,
-    int* __restrict__ queue_counter, int k, float* __restrict__ part_s, long long* __restrict__ part_id) {
+    int* __restrict__ queue_counter, const int* __restrict__ order, int k, float* __restrict__ part_s,
+    long long* __restrict__ part_id) {
   constexpr int d4 = D4 * 32;  // float4 per vector
   const int lane = threadIdx.x & 31;
   const int n_items = *n_items_ptr;
-  int item = 0;
-  if (lane == 0) item = atomicAdd(queue_counter, 1);
-  item = __shfl_sync(kFullMask, item, 0);
-  while (item < n_items) {
+  int pos = 0;
+  if (lane == 0) pos = atomicAdd(queue_counter, 1);
+  pos = __shfl_sync(kFullMask, pos, 0);
+  while (pos < n_items) {
     int next = 0;
     if (lane == 0) next = atomicAdd(queue_counter, 1);  // latency hidden behind this item's scan
+    const int item = order ? __ldg(order + pos) : pos;  // queue position -> item (list-major order)
     const ScanItem it = load_item(items + item);
     const float4* qp = reinterpret_cast<const float4*>(Q) + (size_t)it.q * d4 + lane;
     float4 qv[D4];
@@ -193,7 +204,7 @@ __global__ __launch_bounds__(kScanThreads) void ivf_scan_kernel(
       }
     }
     tk.store(part_s + (size_t)item * k, part_id + (size_t)item * k);
-    item = __shfl_sync(kFullMask, next, 0);
+    pos = __shfl_sync(kFullMask, next, 0);
   }
 }
 
@@ -201,19 +212,20 @@ __global__ __launch_bounds__(kScanThreads) void ivf_scan_kernel(
 template <int SLOTS>
 __global__ __launch_bounds__(kScanThreads) void ivf_scan_generic_kernel(
     const float* __restrict__ Q, int d, const ScanItem* __restrict__ items,
-    const int* __restrict__ n_items_ptr, int* __restrict__ queue_counter, int k,
+    const int* __restrict__ n_items_ptr, int* __restrict__ queue_counter, const int* __restrict__ order, int k,
     float* __restrict__ part_s, long long* __restrict__ part_id) {
   extern __shared__ __align__(16) float sm_q[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = d / 4;
   float4* myq = reinterpret_cast<float4*>(sm_q) + (size_t)warp * d4;
   const int n_items = *n_items_ptr;
-  int item = 0;
-  if (lane == 0) item = atomicAdd(queue_counter, 1);
-  item = __shfl_sync(kFullMask, item, 0);
-  while (item < n_items) {
+  int pos = 0;
+  if (lane == 0) pos = atomicAdd(queue_counter, 1);
+  pos = __shfl_sync(kFullMask, pos, 0);
+  while (pos < n_items) {
     int next = 0;
     if (lane == 0) next = atomicAdd(queue_counter, 1);
+    const int item = order ? __ldg(order + pos) : pos;
     const ScanItem it = load_item(items + item);
     const float4* qp = reinterpret_cast<const float4*>(Q) + (size_t)it.q * d4;
     __syncwarp();
@@ -232,7 +244,7 @@ __global__ __launch_bounds__(kScanThreads) void ivf_scan_generic_kernel(
       }
     }
     tk.store(part_s + (size_t)item * k, part_id + (size_t)item * k);
-    item = __shfl_sync(kFullMask, next, 0);
+    pos = __shfl_sync(kFullMask, next, 0);
   }
 }
 
@@ -243,20 +255,53 @@ int resident_ctas(Kern kern, size_t smem) {
   return n < 1 ? 1 : n;
 }
 
+// List-major queue order: pairs sorted by list number, so that the probes of different queries into the
+// same inverted list are scanned at the same time and the later ones hit L2 instead of HBM.
+__global__ void plan_gather_counts_kernel(int npairs, const int* __restrict__ pair_sorted, const int* __restrict__ counts,
+                                          int* __restrict__ counts_sorted /* [npairs + 1] */) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < npairs) counts_sorted[s] = counts[pair_sorted[s]];
+  if (s == npairs) counts_sorted[s] = 0;
+}
+
+__global__ void plan_order_kernel(int npairs, int max_items, const int* __restrict__ pair_sorted,
+                                  const int* __restrict__ offs /* item offsets, pair order */,
+                                  const int* __restrict__ qoffs /* queue offsets, sorted order */,
+                                  int* __restrict__ order) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= npairs || offs[npairs] > max_items) return;
+  const int pi = pair_sorted[s];
+  const int b = offs[pi], n = offs[pi + 1] - b, q = qoffs[s];
+  for (int c = 0; c < n; ++c) order[q + c] = b + c;
+}
+
 }  // namespace
 
 void launch_plan(const ListTable& lt, const long long* coarse, int nq, int nprobe, int chunk,
                  int max_items, ScanItem* items, int* q_begin, int* n_items, int* queue_counter,
                  unsigned long long* stats, int* pair_counts, int* pair_offs, void* scan_tmp,
-                 size_t scan_tmp_bytes, cudaStream_t st) {
+                 size_t scan_tmp_bytes, const PlanOrderWs* ow, cudaStream_t st) {
   ABSB_CHECK(nq >= 1 && nq <= kMaxPlanQueries, ABSB_ERR_INVALID, "plan: nq=%d", nq);
   const int npairs = nq * nprobe;
   ABSB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), st));
   const int threads = 256;
-  plan_count_kernel<<<(npairs + 1 + threads - 1) / threads, threads, 0, st>>>(lt, coarse, npairs, chunk, pair_counts,
-                                                                             stats);
+  const int pair_blocks = (npairs + 1 + threads - 1) / threads;
+  plan_count_kernel<<<pair_blocks, threads, 0, st>>>(lt, coarse, npairs, chunk, pair_counts, ow ? ow->keys : nullptr,
+                                                     ow ? ow->vals : nullptr, stats);
   ABSB_CUDA(cudaGetLastError());
   ABSB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_tmp_bytes, pair_counts, pair_offs, npairs + 1, st));
+  if (ow) {
+    int bits = 1;
+    while ((1ll << bits) < (long long)lt.nlist + 1) ++bits;
+    size_t tb = scan_tmp_bytes;
+    ABSB_CUDA(cub::DeviceRadixSort::SortPairs(scan_tmp, tb, ow->keys, ow->keys_sorted, ow->vals, ow->vals_sorted, npairs, 0,
+                                              bits, st));
+    plan_gather_counts_kernel<<<pair_blocks, threads, 0, st>>>(npairs, ow->vals_sorted, pair_counts, ow->counts_sorted);
+    ABSB_CUDA(cudaGetLastError());
+    ABSB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_tmp_bytes, ow->counts_sorted, ow->qoffs, npairs + 1, st));
+    plan_order_kernel<<<pair_blocks, threads, 0, st>>>(npairs, max_items, ow->vals_sorted, pair_offs, ow->qoffs, ow->order);
+    ABSB_CUDA(cudaGetLastError());
+  }
   const int work = std::max(npairs, nq + 1);
   plan_emit_kernel<<<(work + threads - 1) / threads, threads, 0, st>>>(lt, coarse, nq, nprobe, chunk, max_items,
                                                                       pair_offs, items, q_begin, n_items,
@@ -265,9 +310,11 @@ void launch_plan(const ListTable& lt, const long long* coarse, int nq, int nprob
 }
 
 size_t plan_scan_tmp_bytes(int max_pairs) {
-  size_t bytes = 0;
+  size_t bytes = 0, b2 = 0;
   ABSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int*)nullptr, (int*)nullptr, max_pairs + 1));
-  return bytes;
+  ABSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b2, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr,
+                                            max_pairs, 0, 32));
+  return std::max(bytes, b2);
 }
 
 void launch_scan(const ScanLaunch& a, cudaStream_t st) {
@@ -277,7 +324,7 @@ void launch_scan(const ScanLaunch& a, cudaStream_t st) {
     ABSB_DISPATCH_SLOTS(a.k, {
       auto kern = ivf_scan_kernel<SLOTS, D4, kScanUnroll>;
       const int per_sm = a.ctas_per_sm > 0 ? a.ctas_per_sm : resident_ctas(kern, 0);
-      kern<<<sms * per_sm, kScanThreads, 0, st>>>(a.Q, a.items, a.n_items, a.queue_counter, a.k,
+      kern<<<sms * per_sm, kScanThreads, 0, st>>>(a.Q, a.items, a.n_items, a.queue_counter, a.order, a.k,
                                                   a.part_s, a.part_id);
     });
   } else {
@@ -289,7 +336,7 @@ void launch_scan(const ScanLaunch& a, cudaStream_t st) {
       if (smem > 48 * 1024)
         ABSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int per_sm = a.ctas_per_sm > 0 ? a.ctas_per_sm : resident_ctas(kern, smem);
-      kern<<<sms * per_sm, kScanThreads, smem, st>>>(a.Q, a.d, a.items, a.n_items, a.queue_counter,
+      kern<<<sms * per_sm, kScanThreads, smem, st>>>(a.Q, a.d, a.items, a.n_items, a.queue_counter, a.order,
                                                      a.k, a.part_s, a.part_id);
     });
   }

@@ -43,16 +43,22 @@ struct ScanLaunch {
   const ScanItem* items;
   const int* n_items;
   int* queue_counter;
+  const int* order;    // queue position -> item index (list-major order), or nullptr = identity
   float* part_s;       // [max_items, k]
   long long* part_id;  // [max_items, k]
   int sm_count;
   int ctas_per_sm;  // <= 0: occupancy query
 };
 
+// Scratch of the list-major queue order (all [npairs + 1] except order [max_items]).
+struct PlanOrderWs {
+  unsigned *keys, *keys_sorted;
+  int *vals, *vals_sorted, *counts_sorted, *qoffs, *order;
+};
 void launch_plan(const ListTable& lt, const long long* coarse, int nq, int nprobe, int chunk,
                  int max_items, ScanItem* items, int* q_begin, int* n_items, int* queue_counter,
                  unsigned long long* stats, int* pair_counts, int* pair_offs, void* scan_tmp,
-                 size_t scan_tmp_bytes, cudaStream_t st);
+                 size_t scan_tmp_bytes, const PlanOrderWs* order_ws, cudaStream_t st);
 size_t plan_scan_tmp_bytes(int max_pairs);
 void launch_scan(const ScanLaunch& a, cudaStream_t st);
 

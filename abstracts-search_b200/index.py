@@ -242,6 +242,10 @@ class IndexIVFFlat:
     def set_tunables(self, scan_chunk: int = -1, coarse_impl: int = -1, scan_ctas_per_sm: int = -1):
         check(lib().absb_ivf_set_tunables(self._h, scan_chunk, coarse_impl, scan_ctas_per_sm))
 
+    def set_scan_order(self, list_major: bool = True):
+        """Work-queue order of the fine scan: list-major (default, L2 reuse across queries) or query-major."""
+        check(lib().absb_ivf_set_scan_order(self._h, 1 if list_major else 0))
+
     # ---- train ---------------------------------------------------------------------------
     def train(self, x):
         x = _as_f32_matrix(x, self.d)

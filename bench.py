@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--query-tokens", type=int, default=32)
     ap.add_argument("--coarse-impl", type=int, default=1, help="0 fp32 FFMA GEMM, 1 tcgen05 split-bf16 GEMM")
     ap.add_argument("--scan-chunk", type=int, default=-1)
+    ap.add_argument("--scan-order", type=int, default=1, help="1 list-major work queue (default), 0 query-major")
     ap.add_argument("--gemm-variant", type=int, default=0, help="tcgen05 GEMM tile shape (0 auto; see absb_gemm_set_variant)")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not time individual kernels in the timed region")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
@@ -261,6 +262,7 @@ def build_shard(P, torch, args, rank: int, world: int, dev: int):
     total = args.rows_per_gpu * world
     ix = P.index_factory(d, f"IVF{nlist},Flat", P.METRIC_INNER_PRODUCT, device=dev)
     ix.set_tunables(scan_chunk=args.scan_chunk, coarse_impl=args.coarse_impl)
+    ix.set_scan_order(bool(args.scan_order))
     if world > 1:
         ix.set_shard(rank, world)
     ix.set_centroids(P.synth.centroids(SEED, nlist, d, device=dev))

@@ -182,6 +182,10 @@ int absb_merge_shards_dev(int device, int world, int64_t n, int k, const float* 
 /* Tunables (chunk = vectors per scan work item; coarse_impl 0 = fp32 SIMT, 1 = tcgen05
  * split-bf16). Values < 0 leave a setting unchanged. */
 int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int scan_ctas_per_sm);
+/* Order of the scan work queue: 1 (default) = list-major — the (query, probe) pairs are sorted by list
+ * number, so probes of several queries into one list are scanned at the same time and the repeats hit
+ * L2; 0 = query-major.  Results are identical. */
+int absb_ivf_set_scan_order(absb_ivf_t h, int list_major);
 /* Statistics of the most recent search call on this handle: number of list vectors scanned,
  * algorithmic bytes (vectors * (4d+8)), number of scan work items, number of kernel launches. */
 int absb_ivf_last_stats(absb_ivf_t h, int64_t* vectors_scanned, int64_t* bytes_scanned,

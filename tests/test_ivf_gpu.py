@@ -86,6 +86,11 @@ def test_ivf_matches_golden_lattice(gpu_pkg, lattice, coarse_impl):
     assert np.array_equal(Id.cpu().numpy(), g["I"]) and np.array_equal(Dd.cpu().numpy(), g["D"])
     Dp, Ip = ix.search_preassigned(q, k, g["Ic"])
     assert np.array_equal(Ip, g["I"]) and np.array_equal(Dp, g["D"])
+    # work-queue order (list-major with L2 reuse vs query-major) must not change anything
+    ix.set_scan_order(False)
+    Dq, Iq = ix.search(q, k)
+    ix.set_scan_order(True)
+    assert np.array_equal(Iq, g["I"]) and np.array_equal(Dq, g["D"])
     # probing every list == exact flat search
     ix.nprobe = nlist
     Da, Ia = ix.search(q, k)
