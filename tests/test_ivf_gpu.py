@@ -423,3 +423,28 @@ def test_baseline_config0_flat_10k(gpu_pkg):
     assert safe.sum() >= 50
     assert np.array_equal(I[safe], Io[safe])
     assert np.abs(D - Do).max() < 1e-5
+
+
+def test_large_query_batch_splits_internally(gpu_pkg):
+    """2,500 queries in one call: more than one plan/scan launch (1,024 queries each) and more than one
+    host staging chunk must give the same answer as the oracle, for host and device entry points."""
+    P = gpu_pkg
+    t = _torch()
+    d, nlist, n, nq, k, nprobe = 64, 32, 6000, 2500, 5, 3
+    x = osynth.corpus(21, 0, n, d, nlist)
+    q = osynth.queries(21, 0, nq, d, nlist, n)
+    c = osynth.centroids(21, nlist, d)
+    ix = P.IndexIVFFlat(d, nlist)
+    ix.set_centroids(c)
+    ix.add(x)
+    ix.nprobe = nprobe
+    o = oivf.IVFFlat(d, nlist)
+    o.set_centroids(c)
+    o.add(x)
+    Do, Io = o.search(q, k, nprobe=nprobe, impl="c")
+    D, I = ix.search(q, k)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+    Dd, Id = ix.search(t.from_numpy(q).cuda(), k)
+    assert np.array_equal(Id.cpu().numpy(), Io) and np.array_equal(Dd.cpu().numpy(), Do)
+    st = ix.last_stats()
+    assert st["vectors"] == o.last_nscanned
