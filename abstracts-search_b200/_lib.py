@@ -10,7 +10,7 @@ import ctypes
 import os
 import re
 import subprocess
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libabsb200.so")
@@ -132,6 +132,10 @@ _SIGS = {
     "absb_gemm_set_variant": ([c_int], c_int),
     "absb_gemm_bf16_epi_dev": ([c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "absb_gemm_bf16_dev": ([c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    # OpenAlex JSON-lines front end (host only)
+    "absb_oa_jsonl_convert": ([c_char_p, c_size_t, c_int, c_int, POINTER(c_char_p), POINTER(c_size_t),
+                               POINTER(c_size_t), _PI64], c_int),
+    "absb_oa_jsonl_free": ([c_char_p], c_int),
 }
 
 _lib = None

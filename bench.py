@@ -53,9 +53,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="search", choices=["search", "encode", "build"],
+    ap.add_argument("--workload", default="search", choices=["search", "encode", "build", "oa_jsonl"],
                     help="search = the headline metric (encode+IVF search); encode = BASELINE configs[1], bulk embedding; "
-                         "build = BASELINE configs[4], Index.add / Index.train rates")
+                         "build = BASELINE configs[4], Index.add / Index.train rates; oa_jsonl = the host-side OpenAlex "
+                         "JSON-lines front end (SURVEY 8f row 4), MB/s next to the reference program itself")
+    ap.add_argument("--oa-records", type=int, default=40000, help="oa_jsonl workload: synthetic records per step")
     ap.add_argument("--add-rows", type=int, default=1 << 20, help="build workload: rows per add() per GPU")
     ap.add_argument("--train-rows", type=int, default=1 << 21, help="build workload: k-means sample rows per GPU")
     ap.add_argument("--encode-batch", type=int, default=32)
@@ -709,6 +711,60 @@ def run_build(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
 
 
+def run_oa_jsonl(args):
+    """Host-only secondary workload: OpenAlex works JSONL -> {"id","document"} JSONL.
+    A step converts one resident block of synthetic records on all host threads; the baseline arm is
+    the REFERENCE PROGRAM ITSELF (oracle/_ref/oa_jsonl, compiled from /root/reference/oa_jsonl.c) fed
+    the same block through a pipe, as in the reference's Makefile:60-65 pipeline."""
+    from oracle import oa_jsonl as O
+
+    P = importlib.import_module("abstracts-search_b200")
+    data = P.oa_jsonl.synth_records(SEED, args.oa_records)
+    mb = len(data) / 1e6
+    cores = os.cpu_count() or 1
+
+    def ours():
+        return P.oa_jsonl.convert(data, threads=0)
+
+    def ref():
+        return O.convert_reference(data)
+
+    def rate(fn, steps, warmup):
+        for _ in range(warmup):
+            out = fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn()
+        return (time.perf_counter() - t0) / steps, out
+
+    have_ref = O.reference_available()
+    line = {"metric": "MB/s of OpenAlex works JSONL converted to {id, document} JSONL", "unit": "MB/s", "n_gpus": 0,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "oa_jsonl: %d synthetic OpenAlex works records (%.1f MB) per step, resident in host memory"
+                                   % (args.oa_records, mb), "records": args.oa_records, "bytes": len(data)},
+            "gpu_launches": 0}
+    if args.impl == "reference":
+        if not have_ref:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/oa_jsonl is not built (needs /root/reference)"}))
+            return
+        dt, out = rate(ref, max(1, args.steps), max(1, args.warmup))
+        line.update({"impl": "reference", "value": mb / dt, "ms_per_step": dt * 1e3,
+                     "cpu_baseline": {"value": mb / dt, "unit": "MB/s", "cores": 1, "kind": "reference",
+                                      "sample": "the whole block through a pipe into oracle/_ref/oa_jsonl"}})
+    else:
+        dt, out = rate(ours, args.steps, args.warmup)
+        dt1, _ = rate(lambda: P.oa_jsonl.convert(data, threads=1), max(1, args.steps // 2), 1)
+        line.update({"value": mb / dt, "ms_per_step": dt * 1e3, "threads": cores, "single_thread_mb_s": mb / dt1,
+                     "records_kept": out.count(b"\n")})
+        if have_ref:
+            dtr, out_ref = rate(ref, 2, 1)
+            line["cpu_baseline"] = {"value": mb / dtr, "unit": "MB/s", "cores": 1, "kind": "reference",
+                                    "sample": "the whole block through a pipe into oracle/_ref/oa_jsonl (the reference program)"}
+            line["matches_reference_bytes"] = bool(out_ref == out)
+    print(json.dumps(line))
+
+
 def load_traffic(rooflines: dict):
     """dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json), if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -732,6 +788,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "oa_jsonl":
+        if rank == 0:
+            run_oa_jsonl(args)
+        return
     if args.impl == "reference":
         if args.workload == "encode":
             run_encode(args, rank, world, local_rank)

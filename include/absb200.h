@@ -271,6 +271,25 @@ int absb_gemm_bf16_epi_dev(int device, int epi, int M, int N, int K, const void*
 int absb_gemm_bf16_dev(int device, int M, int N, int K, const void* A_dev, const void* B_dev,
                        float* C_dev, void* stream);
 
+/* ---------------------------------------------------------------- OpenAlex front end -------- */
+/* The stage in front of bulk encode.  Replaces the reference's `./oa_jsonl`
+ * executable — /root/reference/Makefile:64, main loop /root/reference/oa_jsonl.c:351-414 — which
+ * turns OpenAlex `works` JSON lines into {"id","document"} JSON lines (English records with a
+ * non-empty abstract_inverted_index; document = title + ' ' + un-inverted abstract, strings left
+ * JSON-escaped).  HOST code only, no GPU needed; bytes out are identical to the reference
+ * program's on well-formed input.
+ *   in[0:in_len)  one block of the stream.  final_chunk = 0: only its complete lines are
+ *                 converted and *consumed tells where the unfinished tail starts; final_chunk = 1:
+ *                 a last line without '\n' is converted too (oa_jsonl.c:333-349).
+ *   threads       line ranges converted concurrently (0 = all hardware threads).
+ *   *out          malloc'ed result of *out_len bytes (+ a NUL), released with absb_oa_jsonl_free.
+ *   stats[4]      optional: lines read, records written, records dropped, 1 if an empty line
+ *                 ended the conversion (oa_jsonl.c:363-366; *consumed = in_len then).
+ * A malformed record returns ABSB_ERR_INVALID naming the line (the reference assert()s). */
+int absb_oa_jsonl_convert(const char* in, size_t in_len, int final_chunk, int threads, char** out,
+                          size_t* out_len, size_t* consumed, int64_t* stats);
+int absb_oa_jsonl_free(char* out);
+
 #ifdef __cplusplus
 }
 #endif
