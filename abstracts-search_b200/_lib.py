@@ -96,6 +96,8 @@ _SIGS = {
     "absb_ivf_add_preassigned": ([_H, c_int64, c_void_p, c_void_p, c_void_p], c_int),
     "absb_ivf_add_preassigned_dev": ([_H, c_int64, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "absb_ivf_compact": ([_H], c_int),
+    "absb_ivf_compact_scratch": ([_H, c_int64], c_int),
+    "absb_plan_page_compaction": ([c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, _PI64, _PI64], c_int),
     "absb_ivf_coarse": ([_H, c_int64, c_void_p, c_int, c_void_p, c_void_p], c_int),
     "absb_ivf_coarse_dev": ([_H, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "absb_ivf_assign": ([_H, c_int64, c_void_p, c_void_p], c_int),

@@ -399,7 +399,37 @@ int absb_ivf_add_preassigned(absb_ivf_t h, int64_t n, const float* x, const int6
 int absb_ivf_compact(absb_ivf_t h) {
   ABSB_API_BEGIN
   NEED(h);
-  fail(ABSB_ERR_UNSUPPORTED, "compact is not implemented yet");
+  DeviceGuard g(h->ix.device);
+  h->ix.compact(0, h->ix.own_stream);
+  ABSB_API_END
+}
+
+int absb_ivf_compact_scratch(absb_ivf_t h, int64_t scratch_pages) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(scratch_pages >= 1, ABSB_ERR_INVALID, "scratch_pages=%lld", (long long)scratch_pages);
+  DeviceGuard g(h->ix.device);
+  h->ix.compact(scratch_pages, h->ix.own_stream);
+  ABSB_API_END
+}
+
+int absb_plan_page_compaction(int64_t n, const int32_t* src, int64_t scratch_pages, int32_t* moves,
+                              int64_t moves_cap, int64_t* phase_end, int64_t phases_cap, int64_t* n_moves,
+                              int64_t* n_phases) {
+  ABSB_API_BEGIN
+  ABSB_CHECK(n >= 0 && (n == 0 || src) && n_moves && n_phases, ABSB_ERR_INVALID, "bad arguments");
+  std::vector<PageMove> mv;
+  std::vector<int64_t> pe;
+  plan_page_compaction(std::vector<int>(src, src + n), scratch_pages, mv, pe);
+  *n_moves = (int64_t)mv.size();
+  *n_phases = (int64_t)pe.size();
+  ABSB_CHECK((int64_t)mv.size() <= moves_cap && (int64_t)pe.size() <= phases_cap, ABSB_ERR_INVALID,
+             "output too small: %lld moves, %lld phases", (long long)mv.size(), (long long)pe.size());
+  for (size_t i = 0; i < mv.size(); ++i) {
+    moves[2 * i] = mv[i].from;
+    moves[2 * i + 1] = mv[i].to;
+  }
+  std::copy(pe.begin(), pe.end(), phase_end);
   ABSB_API_END
 }
 

@@ -136,6 +136,38 @@ __global__ void copy_list_kernel(ListTable lt, long long l, float* __restrict__ 
   }
 }
 
+// One CTA per page copy; `from`/`to` >= 0 name pool pages, < 0 scratch slots (-1 - v).
+__global__ void move_pages_kernel(int64_t n_moves, const PageMove* __restrict__ moves, int P, int d4,
+                                  int slab_shift, float* const* __restrict__ code_slabs,
+                                  long long* const* __restrict__ id_slabs, float* __restrict__ scratch_codes,
+                                  long long* __restrict__ scratch_ids) {
+  const long long mask = (1ll << slab_shift) - 1;
+  const size_t page_f4 = (size_t)P * d4;
+  for (int64_t m = blockIdx.x; m < n_moves; m += gridDim.x) {
+    const PageMove mv = moves[m];
+    const float4* src_c;
+    const long long* src_i;
+    float4* dst_c;
+    long long* dst_i;
+    if (mv.from >= 0) {
+      src_c = reinterpret_cast<const float4*>(code_slabs[mv.from >> slab_shift]) + (size_t)(mv.from & mask) * page_f4;
+      src_i = id_slabs[mv.from >> slab_shift] + (size_t)(mv.from & mask) * P;
+    } else {
+      src_c = reinterpret_cast<const float4*>(scratch_codes) + (size_t)(-1 - mv.from) * page_f4;
+      src_i = scratch_ids + (size_t)(-1 - mv.from) * P;
+    }
+    if (mv.to >= 0) {
+      dst_c = reinterpret_cast<float4*>(code_slabs[mv.to >> slab_shift]) + (size_t)(mv.to & mask) * page_f4;
+      dst_i = id_slabs[mv.to >> slab_shift] + (size_t)(mv.to & mask) * P;
+    } else {
+      dst_c = reinterpret_cast<float4*>(scratch_codes) + (size_t)(-1 - mv.to) * page_f4;
+      dst_i = scratch_ids + (size_t)(-1 - mv.to) * P;
+    }
+    for (size_t j = threadIdx.x; j < page_f4; j += blockDim.x) __stcs(dst_c + j, __ldcs(src_c + j));
+    for (int j = threadIdx.x; j < P; j += blockDim.x) dst_i[j] = src_i[j];
+  }
+}
+
 int grid_for(int64_t work, int threads, int sms) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, threads), (int64_t)sms * 16));
 }
@@ -496,6 +528,106 @@ void IvfIndex::get_list(int64_t l, float* codes, long long* ids) {
   if (codes) ABSB_CUDA(cudaMemcpyAsync(codes, dc.p, sizeof(float) * (size_t)size * d, cudaMemcpyDeviceToHost, st));
   if (ids) ABSB_CUDA(cudaMemcpyAsync(ids, di.p, sizeof(long long) * (size_t)size, cudaMemcpyDeviceToHost, st));
   ABSB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---------------------------------------------------------------- compact ------------------
+// Target layout: list l owns pool pages [pt_off[l], pt_off[l+1]) in order, i.e. pt_pages becomes the
+// identity and the plan kernel can merge a whole list into scan_chunk-sized work items.  The pages
+// are permuted IN PLACE, window by window, because a 106 GB shard leaves no room for a second copy:
+// for the window W = [w, w+S) of target positions
+//   phase 1  scratch[i] <- page src[w+i]                  (the S pages that belong in W)
+//   phase 2  pages of W still wanted by a later target move into the slots phase 1 just freed
+//            outside W (|W minus sources| == |sources minus W|, paired up in order)
+//   phase 3  page w+i <- scratch[i]
+// After the round every target >= w+S again has its source >= w+S.  Pages already in place are
+// skipped.  Traffic: every page is read and written at most twice (+ once if it is displaced).
+void plan_page_compaction(std::vector<int> src, int64_t S, std::vector<PageMove>& moves,
+                          std::vector<int64_t>& phase_end) {
+  const int64_t n = (int64_t)src.size();
+  moves.clear();
+  phase_end.clear();
+  if (n == 0) return;
+  ABSB_CHECK(S >= 1, ABSB_ERR_INVALID, "compaction needs at least one scratch page");
+  std::vector<int> where((size_t)n, -1);  // where[p] = the target that wants pool page p
+  for (int64_t t = 0; t < n; ++t) {
+    ABSB_CHECK(src[t] >= 0 && src[t] < n && where[src[t]] < 0, ABSB_ERR_STATE, "page table is not a permutation");
+    where[src[t]] = (int)t;
+  }
+  std::vector<int> displaced, freed;
+  for (int64_t w = 0; w < n; w += S) {
+    const int64_t e = std::min(n, w + S);
+    const size_t before = moves.size();
+    for (int64_t t = w; t < e; ++t)
+      if (src[t] != t) moves.push_back({src[t], (int)(-1 - (t - w))});
+    if (moves.size() == before) continue;  // window already in place
+    phase_end.push_back((int64_t)moves.size());
+    displaced.clear();
+    freed.clear();
+    for (int64_t t = w; t < e; ++t) {
+      if (where[t] < w || where[t] >= e) displaced.push_back((int)t);  // page t is wanted later
+      if (src[t] < w || src[t] >= e) freed.push_back(src[t]);          // its slot was read in phase 1
+    }
+    ABSB_CHECK(displaced.size() == freed.size(), ABSB_ERR_STATE, "compaction bookkeeping broke");
+    for (size_t k = 0; k < displaced.size(); ++k) {
+      const int p = displaced[k], f = freed[k], u = where[p];
+      moves.push_back({p, f});
+      src[u] = f;
+      where[f] = u;
+    }
+    if (!displaced.empty()) phase_end.push_back((int64_t)moves.size());
+    for (int64_t t = w; t < e; ++t) {
+      if (src[t] != t) moves.push_back({(int)(-1 - (t - w)), (int)t});
+      src[t] = (int)t;
+      where[t] = (int)t;
+    }
+    phase_end.push_back((int64_t)moves.size());
+  }
+}
+
+void IvfIndex::compact(int64_t scratch_pages, cudaStream_t st) {
+  const int64_t n = pt_total_pages;
+  if (n == 0) return;
+  ABSB_CHECK(n == pool.pages_used, ABSB_ERR_STATE, "page table (%lld) and pool (%lld) disagree", (long long)n,
+             (long long)pool.pages_used);
+  std::vector<int> src((size_t)n);
+  ABSB_CUDA(cudaMemcpyAsync(src.data(), pt_pages.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+  ABSB_CUDA(cudaStreamSynchronize(st));
+  const int P = pool.page_vecs;
+  const size_t page_bytes = (size_t)P * d * sizeof(float) + (size_t)P * sizeof(long long);
+  if (scratch_pages <= 0) {
+    size_t free_b = 0, total_b = 0;
+    ABSB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    scratch_pages = (int64_t)std::min<size_t>(free_b / 2 / page_bytes, (size_t)1 << 16);  // <= 4 GB of fp32 d=1024
+  }
+  scratch_pages = std::max<int64_t>(1, std::min(scratch_pages, n));
+  std::vector<PageMove> moves;
+  std::vector<int64_t> phase_end;
+  plan_page_compaction(std::move(src), scratch_pages, moves, phase_end);
+  if (!moves.empty()) {
+    DBuf<float> sc_codes;
+    DBuf<long long> sc_ids;
+    DBuf<PageMove> d_moves;
+    sc_codes.alloc_exact((size_t)scratch_pages * P * d);
+    sc_ids.alloc_exact((size_t)scratch_pages * P);
+    d_moves.alloc_exact(moves.size());
+    ABSB_CUDA(cudaMemcpyAsync(d_moves.p, moves.data(), sizeof(PageMove) * moves.size(), cudaMemcpyHostToDevice, st));
+    int64_t begin = 0;
+    for (int64_t end : phase_end) {
+      const int64_t cnt = end - begin;
+      if (cnt > 0) {
+        const int grid = (int)std::min<int64_t>(cnt, (int64_t)props.sm_count * 8);
+        move_pages_kernel<<<grid, 256, 0, st>>>(cnt, d_moves.p + begin, P, d / 4, pool.slab_shift, pool.d_code_slabs.p,
+                                                pool.d_id_slabs.p, sc_codes.p, sc_ids.p);
+        ABSB_CUDA(cudaGetLastError());
+      }
+      begin = end;
+    }
+    std::vector<int> iota((size_t)n);
+    std::iota(iota.begin(), iota.end(), 0);
+    ABSB_CUDA(cudaMemcpyAsync(pt_pages.p, iota.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    ABSB_CUDA(cudaStreamSynchronize(st));  // scratch and host vectors die with this frame
+  }
+  have_last_scan = false;
 }
 
 // ---------------------------------------------------------------- train --------------------

@@ -149,9 +149,21 @@ struct IvfIndex {
   void fold_stats();
   void coarse_scores(int M, const float* q, float* S, cudaStream_t st);
   void get_list(int64_t list_no, float* codes, long long* ids);
+  // Physically reorders the pages so that every list's pages are consecutive (in place, through a
+  // bounded scratch of `scratch_pages` pages; <= 0 picks a size from the free memory).
+  void compact(int64_t scratch_pages, cudaStream_t st);
   int64_t items_bound_per_query(int nprobe) const;
   void refresh_host_sizes(cudaStream_t st);
 };
+
+// One page copy of the in-place compaction: locations >= 0 are pool pages, < 0 scratch slot -1 - v.
+struct PageMove {
+  int from, to;
+};
+// Plans content_new[t] = content_old[src[t]] (src a permutation of [0, n)) as phases of mutually
+// independent page copies that run in order, using at most `scratch_pages` scratch pages.
+void plan_page_compaction(std::vector<int> src, int64_t scratch_pages, std::vector<PageMove>& moves,
+                          std::vector<int64_t>& phase_end);
 
 void rand_perm_export(int64_t n, int64_t seed, int* out);
 int64_t split_clusters_export(int d, int64_t k, int64_t n, float* hassign, float* centroids);

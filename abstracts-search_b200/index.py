@@ -383,6 +383,15 @@ class IndexIVFFlat:
         check(lib().absb_ivf_get_list(self._h, l, ptr(codes), ptr(ids)))
         return codes, ids
 
+    def compact(self, scratch_pages: int = 0) -> None:
+        """Make every list's pages physically consecutive, in place (bounded scratch).  Results are
+        unchanged; after an index was filled by many small add() calls the scan needs far fewer
+        work items.  No faiss counterpart is needed there (its lists are one array each)."""
+        if scratch_pages > 0:
+            check(lib().absb_ivf_compact_scratch(self._h, int(scratch_pages)))
+        else:
+            check(lib().absb_ivf_compact(self._h))
+
     # ---- measurement ---------------------------------------------------------------------
     def last_stats(self) -> dict:
         v, b, w, l = c_int64(), c_int64(), c_int64(), c_int64()

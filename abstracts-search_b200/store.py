@@ -85,6 +85,8 @@ def fill_index(index, dir_path: str, ids_parquet: str | None = None) -> int:
         n += x.shape[0]
         if ids_parquet is not None:
             all_ids.extend(ids)
+    if hasattr(index, "compact"):
+        index.compact()  # row-group-sized add() calls leave every list scattered over the page pool
     if ids_parquet is not None:
         write_ids_parquet(ids_parquet, all_ids)
     return n

@@ -125,9 +125,20 @@ int absb_ivf_add_preassigned(absb_ivf_t h, int64_t n, const float* x, const int6
 int absb_ivf_add_preassigned_dev(absb_ivf_t h, int64_t n, const float* x_dev,
                                  const int64_t* ids_dev, const int64_t* list_ids_dev,
                                  void* stream);
-/* Merge all add() segments into one contiguous list arena (optional; halves nothing in the
- * result, only the number of scan work items). Needs room for a second copy of the codes. */
+/* Make every list's pages physically consecutive (optional; changes no result, only the number of
+ * scan work items after an index was filled by many small add() calls, e.g. streamed row groups
+ * of `sidecar-search index fill`, /root/reference/Makefile:24-25).  In place: the pages are permuted
+ * window by window through a bounded scratch (<= 4 GB, or `scratch_pages` pages), so a 106 GB
+ * shard compacts inside 180 GB.  Synchronises. */
 int absb_ivf_compact(absb_ivf_t h);
+int absb_ivf_compact_scratch(absb_ivf_t h, int64_t scratch_pages);
+/* Test hook (host only): the compaction schedule for a page table `src` [n] (a permutation;
+ * content_new[t] = content_old[src[t]]).  moves [n_moves, 2] = (from, to), >= 0 pool page, < 0
+ * scratch slot -1 - v; phase_end [n_phases] = exclusive end of each phase in `moves`; the copies
+ * of one phase are independent, phases run in order. */
+int absb_plan_page_compaction(int64_t n, const int32_t* src, int64_t scratch_pages, int32_t* moves,
+                              int64_t moves_cap, int64_t* phase_end, int64_t phases_cap,
+                              int64_t* n_moves, int64_t* n_phases);
 
 /* quantizer.search(x, nprobe): Dc [n,nprobe] f32, Ic [n,nprobe] i64, best first. */
 int absb_ivf_coarse(absb_ivf_t h, int64_t n, const float* q, int nprobe, float* Dc, int64_t* Ic);

@@ -152,3 +152,70 @@ def test_safetensors_reader(tmp_path, P):
     t = enc.read_safetensors(str(path))
     assert np.array_equal(t["w"][0], a) and t["w"][1] == "F32"
     assert np.array_equal(t["v"][0], b) and t["v"][1] == "BF16"
+
+
+# ---------------------------------------------------------------------------------------------
+# in-place page compaction schedule (absb_ivf_compact): host-side planner, simulated here
+# ---------------------------------------------------------------------------------------------
+def _plan(src, scratch):
+    import ctypes
+
+    import numpy as np
+
+    L = load_pkg().lib()
+    n = len(src)
+    src = np.ascontiguousarray(src, dtype=np.int32)
+    moves = np.empty((3 * n + 1, 2), dtype=np.int32)
+    phases = np.empty(3 * n + 3, dtype=np.int64)
+    nm, nph = ctypes.c_int64(), ctypes.c_int64()
+    rc = L.absb_plan_page_compaction(n, src.ctypes.data, scratch, moves.ctypes.data, len(moves), phases.ctypes.data,
+                                     len(phases), ctypes.byref(nm), ctypes.byref(nph))
+    assert rc == 0, L.absb_last_error()
+    return moves[: nm.value], phases[: nph.value]
+
+
+@pytest.mark.parametrize("n,scratch,seed", [(1, 1, 0), (2, 1, 1), (17, 1, 2), (64, 5, 3), (1000, 64, 4), (1000, 1000, 5),
+                                            (4096, 100, 6), (333, 7, 7)])
+def test_compaction_plan_permutes_pages_in_place(n, scratch, seed):
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    src = rng.permutation(n).astype(np.int32)
+    if seed % 2:  # a partly ordered table, as left by a few large add() calls
+        src[: n // 2] = np.sort(src[: n // 2])
+    moves, phases = _plan(src, scratch)
+    pool = np.arange(n, dtype=np.int64) + 1000  # page p holds content 1000 + p
+    sc = np.full(scratch, -1, dtype=np.int64)
+    begin = 0
+    for end in phases:
+        ph = moves[begin:end]
+        begin = end
+        reads, writes = set(ph[:, 0].tolist()), ph[:, 1].tolist()
+        assert len(set(writes)) == len(writes), "two copies of one phase write the same page"
+        assert not reads & set(writes), "a phase reads a page it also writes"
+        vals = [pool[f] if f >= 0 else sc[-1 - f] for f in ph[:, 0]]
+        for (f, t), v in zip(ph, vals):
+            assert -scratch <= min(f, t) and max(f, t) < n
+            if t >= 0:
+                pool[t] = v
+            else:
+                sc[-1 - t] = v
+    assert begin == len(moves)
+    assert np.array_equal(pool, src.astype(np.int64) + 1000), "content_new[t] must equal content_old[src[t]]"
+    assert len(moves) <= 3 * n
+
+
+def test_compaction_plan_skips_an_ordered_table_and_rejects_garbage():
+    import numpy as np
+
+    moves, phases = _plan(np.arange(100), 8)
+    assert len(moves) == 0 and len(phases) == 0
+    L = load_pkg().lib()
+    import ctypes
+
+    bad = np.array([0, 0, 1], dtype=np.int32)
+    out = np.empty((16, 2), dtype=np.int32)
+    ph = np.empty(16, dtype=np.int64)
+    a, b = ctypes.c_int64(), ctypes.c_int64()
+    assert L.absb_plan_page_compaction(3, bad.ctypes.data, 2, out.ctypes.data, 16, ph.ctypes.data, 16,
+                                       ctypes.byref(a), ctypes.byref(b)) != 0

@@ -120,6 +120,44 @@ def test_list_contents_keep_insertion_order_across_adds(gpu_pkg, lattice):
     assert ix.ntotal == 0 and ix.is_trained and ix.list_sizes().sum() == 0
 
 
+@pytest.mark.parametrize("scratch_pages", [0, 1, 37])
+def test_compact_after_many_small_adds_changes_nothing_but_the_work_items(gpu_pkg, lattice, scratch_pages):
+    """Streaming fill (row-group-sized add() calls) scatters every list over the page pool; compact()
+    permutes the pages in place.  List contents, ids and search results must stay bit-identical; the
+    scan must need fewer work items afterwards; later add() calls must still work."""
+    g, x, q, c = lattice
+    d, nlist, nprobe, k = int(g["d"]), int(g["nlist"]), int(g["nprobe"]), int(g["k"])
+    ix = gpu_pkg.IndexIVFFlat(d, nlist)
+    ix.set_centroids(c)
+    o = oivf.IVFFlat(d, nlist)
+    o.set_centroids(c)
+    n0 = 7000
+    for a in range(0, n0, 250):
+        ix.add(x[a:a + 250])
+    o.add(x[:n0])
+    ix.nprobe = nprobe
+    D0, I0 = ix.search(q, k)
+    items_before = ix.last_stats()["items"]
+    Do, Io = o.search(q, k, nprobe=nprobe)
+    assert np.array_equal(I0, Io) and np.array_equal(D0, Do)
+    ix.compact(scratch_pages)
+    assert np.array_equal(ix.list_sizes(), o.list_sizes())
+    for l in range(0, nlist, max(1, nlist // 16)):
+        codes, ids = ix.get_list(l)
+        assert np.array_equal(ids, o.ids[l]) and np.array_equal(codes, o.codes[l])
+    D1, I1 = ix.search(q, k)
+    assert np.array_equal(I1, I0) and np.array_equal(D1, D0)
+    assert ix.last_stats()["items"] < items_before
+    ix.compact(scratch_pages)  # already compact: a no-op
+    ix.add(x[n0:])
+    o.add(x[n0:])
+    D2, I2 = ix.search(q, k)
+    assert np.array_equal(I2, g["I"]) and np.array_equal(D2, g["D"])
+    for l in (0, nlist - 1):
+        codes, ids = ix.get_list(l)
+        assert np.array_equal(ids, o.ids[l]) and np.array_equal(codes, o.codes[l])
+
+
 # ------------------------------------------------------------------ golden: gaussian -----------
 def test_ivf_gauss_search_and_train(gpu_pkg):
     g = golden("ivf_gauss_d64.npz")
