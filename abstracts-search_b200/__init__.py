@@ -12,4 +12,5 @@ from .index import (METRIC_INNER_PRODUCT, METRIC_L2, ClusteringParameters, Index
                     index_factory, read_index, write_index)
 from .sharded import DeviceOps, ShardedIndexIVFFlat, merge_partials_host, owner_of_list  # noqa: F401
 from .encoder import STELLA_1_5B, Encoder, EncoderConfig, SentenceTransformer  # noqa: F401
-from . import faiss_io, oa_jsonl, store, synth, tune  # noqa: F401
+from .peer import PeerExchange  # noqa: F401
+from . import faiss_io, oa_jsonl, peer, store, synth, tune  # noqa: F401

@@ -134,6 +134,19 @@ _SIGS = {
     "absb_gemm_set_variant": ([c_int], c_int),
     "absb_gemm_bf16_epi_dev": ([c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "absb_gemm_bf16_dev": ([c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    # NVLink peer exchange
+    "absb_peer_create": ([c_int, c_int, c_int, c_size_t, POINTER(_H)], c_int),
+    "absb_peer_destroy": ([_H], c_int),
+    "absb_peer_ipc_handle": ([_H, c_void_p], c_int),
+    "absb_peer_local_ptr": ([_H, POINTER(c_void_p)], c_int),
+    "absb_peer_connect": ([_H, c_void_p], c_int),
+    "absb_peer_connect_ptrs": ([_H, c_void_p], c_int),
+    "absb_peer_allgather_dev": ([_H, c_void_p, c_size_t, POINTER(c_void_p), c_void_p], c_int),
+    "absb_peer_push_dev": ([_H, c_void_p, c_size_t, c_void_p], c_int),
+    "absb_peer_wait_dev": ([_H, POINTER(c_void_p), c_void_p], c_int),
+    "absb_peer_status": ([_H, POINTER(c_int)], c_int),
+    "absb_ivf_search_push_dev": ([_H, _H, c_int64, c_void_p, c_int, c_int, c_void_p], c_int),
+    "absb_peer_merge_shards_dev": ([_H, c_int64, c_int, c_void_p, c_void_p, c_void_p], c_int),
     # OpenAlex JSON-lines front end (host only)
     "absb_oa_jsonl_convert": ([c_char_p, c_size_t, c_int, c_int, POINTER(c_char_p), POINTER(c_size_t),
                                POINTER(c_size_t), _PI64], c_int),

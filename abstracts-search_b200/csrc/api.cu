@@ -71,6 +71,11 @@ struct absb_flat_s {
   absb_flat_s(int d, int device) : ix(d, device) {}
 };
 
+struct absb_peer_s {
+  PeerExchange px;
+  absb_peer_s(int device, int rank, int world, size_t slot_bytes) : px(device, rank, world, slot_bytes) {}
+};
+
 #define NEED(p) ABSB_CHECK((p) != nullptr, ABSB_ERR_INVALID, "null argument: " #p)
 
 extern "C" {
@@ -602,6 +607,134 @@ int absb_merge_shards_dev(int device, int world, int64_t n, int k, const float* 
   const int64_t is = rank_stride_bytes ? rank_stride_bytes : n * k * (int64_t)sizeof(long long);
   merge_shards(world, n, k, D_all_dev, reinterpret_cast<const long long*>(I_all_dev), ds, is, D_dev,
                reinterpret_cast<long long*>(I_dev), (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+// ------------------------------------------------------------------ peer exchange ----------
+int absb_peer_create(int device, int rank, int world, size_t slot_bytes, absb_peer_t* out) {
+  ABSB_API_BEGIN
+  NEED(out);
+  require_sm100(device);
+  DeviceGuard g(device);
+  *out = new absb_peer_s(device, rank, world, slot_bytes);
+  ABSB_API_END
+}
+
+int absb_peer_destroy(absb_peer_t p) {
+  ABSB_API_BEGIN
+  if (p) {
+    DeviceGuard g(p->px.device);
+    delete p;
+  }
+  ABSB_API_END
+}
+
+int absb_peer_ipc_handle(absb_peer_t p, void* handle64) {
+  ABSB_API_BEGIN
+  NEED(p);
+  NEED(handle64);
+  DeviceGuard g(p->px.device);
+  p->px.ipc_handle(handle64);
+  ABSB_API_END
+}
+
+int absb_peer_local_ptr(absb_peer_t p, void** ptr_dev) {
+  ABSB_API_BEGIN
+  NEED(p);
+  NEED(ptr_dev);
+  *ptr_dev = p->px.local;
+  ABSB_API_END
+}
+
+int absb_peer_connect(absb_peer_t p, const void* handles) {
+  ABSB_API_BEGIN
+  NEED(p);
+  NEED(handles);
+  DeviceGuard g(p->px.device);
+  p->px.connect_ipc(handles);
+  ABSB_API_END
+}
+
+int absb_peer_connect_ptrs(absb_peer_t p, void* const* ptrs_dev) {
+  ABSB_API_BEGIN
+  NEED(p);
+  NEED(ptrs_dev);
+  DeviceGuard g(p->px.device);
+  p->px.connect_ptrs(ptrs_dev);
+  ABSB_API_END
+}
+
+int absb_peer_allgather_dev(absb_peer_t p, const void* src_dev, size_t bytes, void** gathered_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(p);
+  NEED(src_dev);
+  NEED(gathered_dev);
+  DeviceGuard g(p->px.device);
+  *gathered_dev = p->px.allgather(src_dev, bytes, (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_peer_push_dev(absb_peer_t p, const void* src_dev, size_t bytes, void* stream) {
+  ABSB_API_BEGIN
+  NEED(p);
+  NEED(src_dev);
+  DeviceGuard g(p->px.device);
+  p->px.push(src_dev, bytes, (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_peer_wait_dev(absb_peer_t p, void** gathered_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(p);
+  NEED(gathered_dev);
+  DeviceGuard g(p->px.device);
+  p->px.wait((cudaStream_t)stream);
+  *gathered_dev = p->px.local_entry(p->px.epoch);
+  ABSB_API_END
+}
+
+int absb_peer_status(absb_peer_t p, int* status) {
+  ABSB_API_BEGIN
+  NEED(p);
+  NEED(status);
+  DeviceGuard g(p->px.device);
+  *status = p->px.read_status(nullptr);
+  ABSB_API_END
+}
+
+int absb_ivf_search_push_dev(absb_ivf_t h, absb_peer_t p, int64_t n, const float* q_dev, int k, int nprobe,
+                             void* stream) {
+  ABSB_API_BEGIN
+  NEED(h);
+  NEED(p);
+  ABSB_CHECK(n >= 1 && q_dev, ABSB_ERR_INVALID, "bad search arguments");
+  ABSB_CHECK(k >= 1 && k <= ABSB_MAX_K, ABSB_ERR_INVALID, "k=%d outside [1,%d]", k, ABSB_MAX_K);
+  ABSB_CHECK(p->px.device == h->ix.device, ABSB_ERR_INVALID, "index and exchange live on different devices");
+  const size_t i_bytes = ((size_t)n * k * sizeof(long long) + 15) & ~(size_t)15;
+  ABSB_CHECK(i_bytes + (size_t)n * k * sizeof(float) <= p->px.slot_bytes, ABSB_ERR_INVALID,
+             "record of %lld x %d results does not fit the exchange slot (%zu bytes)", (long long)n, k, p->px.slot_bytes);
+  DeviceGuard g(h->ix.device);
+  h->ix.reset_stats();
+  SearchPush sp{p->px.begin_push(0, (long long)i_bytes), 0, n};
+  h->ix.search_dev(n, q_dev, k, nprobe, nullptr, nullptr, (cudaStream_t)stream, &sp);
+  p->px.commit();
+  p->px.rec_n = n;
+  p->px.rec_k = k;
+  ABSB_API_END
+}
+
+int absb_peer_merge_shards_dev(absb_peer_t p, int64_t n, int k, float* D_dev, int64_t* I_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(p);
+  ABSB_CHECK(n >= 1 && D_dev && I_dev, ABSB_ERR_INVALID, "bad merge arguments");
+  PeerExchange& px = p->px;
+  ABSB_CHECK(px.epoch > 0 && px.rec_n == n && px.rec_k == k, ABSB_ERR_STATE,
+             "no pushed search record of %lld x %d results to merge", (long long)n, k);
+  DeviceGuard g(px.device);
+  const size_t i_bytes = ((size_t)n * k * sizeof(long long) + 15) & ~(size_t)15;
+  merge_shards_wait(px.world, n, k, px.local_entry(px.epoch), (int64_t)px.slot_bytes, 0, (int64_t)i_bytes,
+                    px.local_flags(), px.epoch, px.status.p, D_dev, reinterpret_cast<long long*>(I_dev),
+                    (cudaStream_t)stream);
   ABSB_API_END
 }
 

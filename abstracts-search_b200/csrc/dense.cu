@@ -7,6 +7,7 @@
 // The fp32 FFMA GEMM is the ranking-faithful baseline implementation of the coarse step
 // (coarse_impl = 0).  The tcgen05 split-bf16 GEMM in gemm_tc.cu replaces it when enabled.
 #include "common.cuh"
+#include "peer.cuh"
 #include "topk.cuh"
 
 namespace absb {
@@ -202,6 +203,56 @@ __global__ __launch_bounds__(128) void merge_partials_kernel(
   }
 }
 
+// merge_partials fused with the shard exchange (peer.cuh): the merged k-best of every query is
+// stored straight into slot [rank] of EVERY rank's ring entry over NVLink instead of a local
+// (D, I); the last CTA of the launch that completes the record raises this rank's flag everywhere.
+template <int SLOTS>
+__global__ __launch_bounds__(128) void merge_partials_push_kernel(
+    int nq, int k, const int* __restrict__ q_begin, const float* __restrict__ part_s,
+    const long long* __restrict__ part_id, PeerPush pp) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q < nq) {
+    WarpTopK<SLOTS> tk;
+    tk.init(k, lane);
+    const int64_t b = (int64_t)q_begin[q] * k, e = (int64_t)q_begin[q + 1] * k;
+    for (int64_t c0 = b; c0 < e; c0 += 32) {
+      const int64_t c = c0 + lane;
+      const bool valid = c < e;
+      const float v = valid ? part_s[c] : 0.f;
+      const long long id = valid ? part_id[c] : 0;
+      tk.offer_lanes(v, id, valid && id != kIdSentinel);
+    }
+#pragma unroll
+    for (int i = 0; i < SLOTS; ++i) {
+      const int r = lane * SLOTS + i;
+      if (r < k) {
+        float s = tk.s[i];
+        long long id = tk.id[i];
+        if (id == kIdSentinel) { s = -3.4028234663852886e38f; id = -1; }
+        const int64_t o = (pp.q_off + q) * k + r;
+        for (int w = 0; w < pp.world; ++w) {
+          char* rec = pp.slot_ptrs[w];
+          reinterpret_cast<long long*>(rec + pp.i_off)[o] = id;
+          reinterpret_cast<float*>(rec + pp.d_off)[o] = s;
+        }
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(pp.done_counter, 1u) == gridDim.x - 1) {
+      *pp.done_counter = 0;
+      if (pp.epoch) {
+        __threadfence_system();
+        for (int w = 0; w < pp.world; ++w)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flag_ptrs[w]), "l"(pp.epoch) : "memory");
+      }
+    }
+  }
+}
+
 // Shard merge: candidates of query q live at [w, q, :] for w < world.
 template <int SLOTS>
 __global__ __launch_bounds__(128) void merge_shards_kernel(int world, int64_t nq, int k,
@@ -210,7 +261,27 @@ __global__ __launch_bounds__(128) void merge_shards_kernel(int world, int64_t nq
                                                            int64_t d_stride /* bytes per rank */,
                                                            int64_t i_stride /* bytes per rank */,
                                                            float* __restrict__ D,
-                                                           long long* __restrict__ I) {
+                                                           long long* __restrict__ I,
+                                                           const unsigned long long* __restrict__ flags,
+                                                           unsigned long long epoch, int* __restrict__ status) {
+  if (flags != nullptr) {
+    // fused with the peer exchange: acquire the arrival flag of every rank before reading its record
+    if ((int)threadIdx.x < world) {
+      unsigned long long t0, t1, v;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+        if (v >= epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) {  // a dead peer must not hang the GPU
+          *status = 1;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq) return;
@@ -265,7 +336,27 @@ void merge_shards(int world, int64_t nq, int k, const float* D_all, const long l
                   int64_t d_stride, int64_t i_stride, float* D, long long* I, cudaStream_t st) {
   if (nq == 0) return;
   ABSB_DISPATCH_SLOTS(k, (merge_shards_kernel<SLOTS><<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(
-                             world, nq, k, D_all, I_all, d_stride, i_stride, D, I)));
+                             world, nq, k, D_all, I_all, d_stride, i_stride, D, I, nullptr, 0ull, nullptr)));
+  ABSB_CUDA(cudaGetLastError());
+}
+
+void merge_partials_push(int nq, int k, const int* q_begin, const float* part_s, const long long* part_id,
+                         const PeerPush& pp, cudaStream_t st) {
+  if (nq == 0) return;
+  ABSB_DISPATCH_SLOTS(k, (merge_partials_push_kernel<SLOTS><<<(nq + 3) / 4, 128, 0, st>>>(nq, k, q_begin, part_s,
+                                                                                         part_id, pp)));
+  ABSB_CUDA(cudaGetLastError());
+}
+
+void merge_shards_wait(int world, int64_t nq, int k, const char* entry, int64_t slot_bytes, int64_t i_off,
+                       int64_t d_off, const unsigned long long* flags, unsigned long long epoch, int* status,
+                       float* D, long long* I, cudaStream_t st) {
+  if (nq == 0) return;
+  ABSB_CHECK(world <= 128, ABSB_ERR_INVALID, "world=%d", world);
+  ABSB_DISPATCH_SLOTS(k, (merge_shards_kernel<SLOTS><<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(
+                             world, nq, k, reinterpret_cast<const float*>(entry + d_off),
+                             reinterpret_cast<const long long*>(entry + i_off), slot_bytes, slot_bytes, D, I, flags,
+                             epoch, status)));
   ABSB_CUDA(cudaGetLastError());
 }
 

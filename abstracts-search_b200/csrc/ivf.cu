@@ -850,7 +850,7 @@ void IvfIndex::fold_stats() {
 
 void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int nprobe,
                                       const long long* coarse, float* D, long long* I,
-                                      cudaStream_t st) {
+                                      cudaStream_t st, const SearchPush* push) {
   ABSB_CHECK(trained, ABSB_ERR_STATE, "index is not trained");
   ABSB_CHECK(k >= 1 && k <= ABSB_MAX_K, ABSB_ERR_INVALID, "k=%d outside [1,%d]", k, ABSB_MAX_K);
   ABSB_CHECK(nprobe >= 1, ABSB_ERR_INVALID, "nprobe=%d", nprobe);
@@ -903,7 +903,14 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
     }
     {
       Span sp(this, st, 2);
-      merge_partials(nb, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, D + q0 * k, I + q0 * k, st);
+      if (push) {
+        PeerPush pp = push->pp;
+        pp.q_off = push->q_base + q0;
+        if (push->q_base + q0 + nb != push->nq_total) pp.epoch = 0;  // record not complete yet
+        merge_partials_push(nb, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, pp, st);
+      } else {
+        merge_partials(nb, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, D + q0 * k, I + q0 * k, st);
+      }
     }
     last_scan = a;
     have_last_scan = true;
@@ -914,7 +921,7 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
 }
 
 void IvfIndex::search_dev(int64_t nq, const float* q, int k, int nprobe, float* D, long long* I,
-                          cudaStream_t st) {
+                          cudaStream_t st, const SearchPush* push) {
   ABSB_CHECK(trained, ABSB_ERR_STATE, "index is not trained");
   const int np = std::min(nprobe, nlist);
   ABSB_CHECK(np >= 1 && np <= ABSB_MAX_K, ABSB_ERR_INVALID, "nprobe=%d outside [1,%d]", nprobe, ABSB_MAX_K);
@@ -924,7 +931,13 @@ void IvfIndex::search_dev(int64_t nq, const float* q, int k, int nprobe, float* 
   for (int64_t q0 = 0; q0 < nq; q0 += step) {
     const int64_t nb = std::min(step, nq - q0);
     coarse_dev(nb, q + q0 * d, np, ws_coarse_s.p, ws_coarse_i.p, true, st);
-    search_preassigned_dev(nb, q + q0 * d, k, np, ws_coarse_i.p, D + q0 * k, I + q0 * k, st);
+    if (push) {
+      SearchPush sub = *push;
+      sub.q_base = push->q_base + q0;
+      search_preassigned_dev(nb, q + q0 * d, k, np, ws_coarse_i.p, nullptr, nullptr, st, &sub);
+    } else {
+      search_preassigned_dev(nb, q + q0 * d, k, np, ws_coarse_i.p, D + q0 * k, I + q0 * k, st);
+    }
   }
 }
 

@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "ivf_scan.cuh"
+#include "peer.cuh"
 
 namespace absb {
 
@@ -34,6 +35,13 @@ struct ClusteringParams {
   int max_points_per_centroid = 256;
   int min_points_per_centroid = 39;
   int64_t seed = 1234;
+};
+
+// Where a search sends its merged top-k when it feeds the peer exchange instead of a local (D, I).
+struct SearchPush {
+  PeerPush pp;       // this epoch's descriptor (PeerExchange::begin_push)
+  int64_t q_base;    // first query of the current call within the record
+  int64_t nq_total;  // queries of the whole record: the launch that completes it raises the flags
 };
 
 struct SearchStats {
@@ -143,9 +151,9 @@ struct IvfIndex {
                     cudaStream_t st);
   void add_dev(int64_t n, const float* x, const long long* ids, cudaStream_t st);
   void search_preassigned_dev(int64_t nq, const float* q, int k, int nprobe, const long long* coarse,
-                              float* D, long long* I, cudaStream_t st);
+                              float* D, long long* I, cudaStream_t st, const SearchPush* push = nullptr);
   void search_dev(int64_t nq, const float* q, int k, int nprobe, float* D, long long* I,
-                  cudaStream_t st);
+                  cudaStream_t st, const SearchPush* push = nullptr);
   void fold_stats();
   void coarse_scores(int M, const float* q, float* S, cudaStream_t st);
   void get_list(int64_t list_no, float* codes, long long* ids);

@@ -97,6 +97,21 @@ class ShardedIndexIVFFlat:
         self.nprobe = getattr(local, "nprobe", 1)
         self._merge_fn = merge_fn  # injected by the CPU (gloo) tests; None = device merge
         self._gD = self._gI = None
+        self._px = None  # NVLink peer exchange (peer.py); None = one NCCL all-gather
+
+    def use_peer_exchange(self, px=None, max_results: int = 512 * 10, strict: bool = True) -> bool:
+        """Route the exchange of the search path over NVLink peer memory instead of NCCL (collective
+        when `px` is None: creates and connects a PeerExchange sized for n*k <= max_results).
+        strict=False keeps the NCCL all-gather (returns False) where peer mapping is unavailable."""
+        from .peer import PeerExchange
+
+        if px is None:
+            px = PeerExchange.over_group(self.local.device, max_results * 12 + 16, self.group, strict=strict)
+            if px is None:
+                return False
+        assert px.world == self.world and px.rank == self.rank
+        self._px = px
+        return True
 
     @property
     def ntotal(self) -> int:
@@ -238,6 +253,26 @@ class ShardedIndexIVFFlat:
                 cent = torch.from_numpy(c_h).to(dev)
             self.local.set_centroids(cent if cent.is_cuda else cent.numpy())
 
+    def _search_peer(self, x, k: int):
+        """search() with the exchange fused into the kernels on both sides (csrc/peer.cuh): no
+        NCCL call, no packed staging buffer, no separate copies."""
+        import torch
+
+        from ._lib import check, current_stream_ptr, lib, ptr
+
+        px = self._px
+        n = x.shape[0]
+        assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == self.d
+        if ((n * k * 8 + 15) & ~15) + n * k * 4 > px.slot_bytes:
+            raise ValueError(f"{n} x {k} results exceed the exchange slot ({px.slot_bytes} bytes); call use_peer_exchange(max_results=...)")
+        with torch.cuda.device(x.device):
+            st = current_stream_ptr()
+            check(lib().absb_ivf_search_push_dev(self.local._h, px._h, n, ptr(x), k, self.nprobe, st))
+            Dm = torch.empty((n, k), dtype=torch.float32, device=x.device)
+            Im = torch.empty((n, k), dtype=torch.int64, device=x.device)
+            check(lib().absb_peer_merge_shards_dev(px._h, n, k, ptr(Dm), ptr(Im), st))
+        return Dm, Im
+
     def search(self, x, k: int):
         """x: the full query batch on every rank.  Returns the merged (D, I) on every rank.
 
@@ -247,6 +282,8 @@ class ShardedIndexIVFFlat:
         import torch.distributed as dist
 
         self.local.nprobe = self.nprobe
+        if self._px is not None and self.world > 1 and hasattr(x, "is_cuda") and x.is_cuda:
+            return self._search_peer(x, k)
         D, I = self.local.search(x, k)
         if self.world == 1:
             return D, I

@@ -72,6 +72,9 @@ def parse_args():
     ap.add_argument("--scan-chunk", type=int, default=-1)
     ap.add_argument("--scan-order", type=int, default=1, help="1 list-major work queue (default), 0 query-major")
     ap.add_argument("--gemm-variant", type=int, default=0, help="tcgen05 GEMM tile shape (0 auto; see absb_gemm_set_variant)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: all-gathers of the query path as NVLink peer-memory stores fused into our kernels "
+                         "(default) or as NCCL calls")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not time individual kernels in the timed region")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -309,8 +312,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ix, build_s = build_shard(P, torch, args, rank, world, dev)
     ix.nprobe = args.nprobe
     sh = P.ShardedIndexIVFFlat(ix) if world > 1 else None
+    exchange = "none (single GPU)"
+    px_emb = None
     if sh is not None:
         sh.nprobe = args.nprobe
+        exchange = "nccl all-gather x2"
+        if args.exchange == "peer" and sh.use_peer_exchange(max_results=args.batch * args.k, strict=False):
+            px_emb = P.PeerExchange.over_group(dev, (args.batch // world) * 1024 * 4, strict=False)
+            exchange = ("NVLink peer-memory stores fused into the merge kernels (no NCCL on the query path)"
+                        if px_emb is not None else "peer-memory top-k exchange + nccl embedding all-gather")
 
     # inputs: pinned host token ids (e2e) and their device copies (value)
     g = torch.Generator().manual_seed(4321)
@@ -324,6 +334,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     def step_dev():
         e = enc.encode_tokens(ids_d[lo:hi], mask_d[lo:hi], normalize_embeddings=True)
         if world > 1:
+            if px_emb is not None:
+                return sh.search(px_emb.allgather(e).view(nq, 1024), k)
             dist.all_gather_into_tensor(emb_all, e)
             return sh.search(emb_all, k)
         return ix.search(e, k)
@@ -331,8 +343,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     def step_e2e():
         e = enc.encode_tokens(ids_np[lo:hi], mask_np[lo:hi], normalize_embeddings=True)  # host in, host out
         if world > 1:
-            dist.all_gather_into_tensor(emb_all, torch.from_numpy(e).to(device, non_blocking=True))
-            D, I = sh.search(emb_all, k)
+            e_d = torch.from_numpy(e).to(device, non_blocking=True)
+            if px_emb is not None:
+                D, I = sh.search(px_emb.allgather(e_d).view(nq, 1024), k)
+            else:
+                dist.all_gather_into_tensor(emb_all, e_d)
+                D, I = sh.search(emb_all, k)
             return D.cpu().numpy(), I.cpu().numpy()
         return ix.search(e, k)  # numpy in, numpy out
 
@@ -359,7 +375,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     assert (Iw >= 0).all() and Iw.shape == (nq, k), "search returned missing results on a full index"
     _, Ic = ix.coarse(emb_all if world > 1 else enc.encode_tokens(ids_d, mask_d, True), args.nprobe)
     distinct_lists = int(torch.unique(Ic).numel())
-    launches_per_step = int(es["launches"] + st["launches"] + (1 if world > 1 else 0))
+    launches_per_step = int(es["launches"] + st["launches"] + ((3 if px_emb is not None else 1) if world > 1 else 0))
 
     # ---- timed region: value -------------------------------------------------------------------
     # Pass A (clean): K steps, CUDA events around the whole region on the launching stream -> value.
@@ -449,7 +465,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         cpu = {"value": qps, "unit": UNIT, "cores": cp.cores, "kind": "port", "sample": cp.describe()}
 
     cfg = workload_config(args, world)
-    cfg.update({"index_build_s": build_s, "distinct_probed_lists_per_step": distinct_lists,
+    cfg.update({"exchange": exchange, "index_build_s": build_s, "distinct_probed_lists_per_step": distinct_lists,
                 "scan_work_items_per_step": st["items"], "ms_per_step_with_kernel_events": ms_instrumented, "coarse_impl": "tcgen05 split-bf16 (6 bf16 products, fp32-faithful)"
                 if args.coarse_impl == 1 else "fp32 FFMA", "kernel_events": "second timed pass of the same K steps" if kernel_events else "off"})
     line = {

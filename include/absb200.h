@@ -50,6 +50,7 @@ extern "C" {
 typedef struct absb_ivf_s* absb_ivf_t;
 typedef struct absb_flat_s* absb_flat_t;
 typedef struct absb_enc_s* absb_enc_t;
+typedef struct absb_peer_s* absb_peer_t;
 
 /* ---------------------------------------------------------------- library ------------------ */
 int absb_version(void);
@@ -281,6 +282,46 @@ int absb_gemm_bf16_epi_dev(int device, int epi, int M, int N, int K, const void*
                            void* out_dev, int64_t ldc, const float* bias_dev, void* stream);
 int absb_gemm_bf16_dev(int device, int M, int N, int K, const void* A_dev, const void* B_dev,
                        float* C_dev, void* stream);
+
+/* ---------------------------------------------------------------- NVLink peer exchange ------ */
+/* The exchange step of the list-sharded search without NCCL: every rank of one
+ * box owns a small device buffer — a two-deep ring of [world] records plus [world] arrival flags —
+ * and maps every other rank's buffer (CUDA IPC over NVLink/NVSwitch).  An all-gather is remote
+ * stores by the producing kernel into slot [rank] of every rank's buffer, a system-scope release
+ * of flag [rank] everywhere, and an acquire of the local flags by the consuming kernel.  This
+ * replaces faiss IndexShards' host-side merge for /root/reference/README.md:16,28 (app.py query
+ * loop) at 8 GPUs.  All calls of one exchange must use one stream; every rank must issue the same
+ * sequence of exchanges.
+ *   create:    slot_bytes = capacity of one rank's record.  Collective by convention: every rank
+ *              creates its exchange, publishes absb_peer_ipc_handle (64 bytes) to all ranks (any
+ *              host channel), then calls absb_peer_connect with the [world][64] handle table.
+ *   connect_ptrs: same-process variant taking raw device pointers (absb_peer_local_ptr of the
+ *              other exchanges) — several ranks emulated on one GPU, for tests.
+ *   allgather: push `bytes` (multiple of 16) from src_dev, wait for all ranks, return the local
+ *              [world][slot_bytes] entry of this epoch (valid until the next-but-one exchange).
+ *              push / wait are its two halves.
+ *   status:    1 after a wait gave up on a dead peer (20 s), else 0.  Synchronises the stream. */
+int absb_peer_create(int device, int rank, int world, size_t slot_bytes, absb_peer_t* out);
+int absb_peer_destroy(absb_peer_t p);
+int absb_peer_ipc_handle(absb_peer_t p, void* handle64);
+int absb_peer_local_ptr(absb_peer_t p, void** ptr_dev);
+int absb_peer_connect(absb_peer_t p, const void* handles /* [world][64] */);
+int absb_peer_connect_ptrs(absb_peer_t p, void* const* ptrs_dev /* [world] */);
+int absb_peer_allgather_dev(absb_peer_t p, const void* src_dev, size_t bytes, void** gathered_dev,
+                            void* stream);
+int absb_peer_push_dev(absb_peer_t p, const void* src_dev, size_t bytes, void* stream);
+int absb_peer_wait_dev(absb_peer_t p, void** gathered_dev, void* stream);
+int absb_peer_status(absb_peer_t p, int* status);
+/* Index.search fused with the exchange: the kernel that merges this shard's partial k-best lists
+ * stores the result straight into every rank's buffer and raises the flags (no local D, I, no
+ * separate copy or collective).  Record = I [n,k] i64 then D [n,k] f32 (16-byte aligned). */
+int absb_ivf_search_push_dev(absb_ivf_t h, absb_peer_t p, int64_t n, const float* q_dev, int k,
+                             int nprobe, void* stream);
+/* The consuming half: waits (inside the kernel) for every rank's record of the last
+ * absb_ivf_search_push_dev and merges world x k candidates per query with the single-index order
+ * (score desc, id asc) -> D_dev [n,k], I_dev [n,k] on this rank. */
+int absb_peer_merge_shards_dev(absb_peer_t p, int64_t n, int k, float* D_dev, int64_t* I_dev,
+                               void* stream);
 
 /* ---------------------------------------------------------------- OpenAlex front end -------- */
 /* The stage in front of bulk encode.  Replaces the reference's `./oa_jsonl`

@@ -66,9 +66,24 @@ def main():
     D, I = sh.search(torch.from_numpy(q).cuda(), k)
     Dr, Ir = ref.search(q, k, nprobe=nprobe)
     assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr)
+    # the same search with the exchange over NVLink peer memory (CUDA IPC between the two processes)
+    # instead of the NCCL all-gather: identical results, repeated to cycle the two-deep ring
+    sh.use_peer_exchange(max_results=nq * k)
+    qd = torch.from_numpy(q).cuda()
+    for _ in range(5):
+        Dp, Ip = sh.search(qd, k)
+        assert np.array_equal(Ip.cpu().numpy(), Ir) and np.array_equal(Dp.cpu().numpy(), Dr), f"rank {rank}: peer exchange"
+    emb = torch.full((nq // world, d), float(rank + 1), device="cuda")
+    px = P.PeerExchange.over_group(torch.cuda.current_device(), emb.numel() * 4)
+    for it in range(3):
+        got = px.allgather(emb + it)
+        want = torch.stack([torch.full_like(emb, float(r + 1 + it)) for r in range(world)])
+        assert torch.equal(got, want), f"rank {rank}: peer all-gather"
+    torch.cuda.synchronize()
+    assert sh._px.status() == 0 and px.status() == 0
     dist.barrier()
     if rank == 0:
-        print(f"dist_build_check ok: world={world}, k-means matches, lists and search bit-exact")
+        print(f"dist_build_check ok: world={world}, k-means matches, lists and search bit-exact, NVLink peer exchange bit-exact")
     dist.destroy_process_group()
 
 

@@ -343,6 +343,62 @@ def test_sharded_by_list_equals_single_index(gpu_pkg, lattice):
     assert np.array_equal(Ih, g["I"]) and np.array_equal(Dh, g["D"])
 
 
+def test_peer_exchange_allgather_emulated_ranks(gpu_pkg):
+    """csrc/peer.cuh protocol with 4 ranks emulated on one GPU (buffers wired by raw pointer): every
+    rank pushes into every buffer, then every rank waits and reads its own ring entry.  Five epochs
+    exercise the two-deep ring; an early wait on a missing push is not tested (it would spin)."""
+    t = _torch()
+    world, n = 4, 1024
+    pxs = gpu_pkg.PeerExchange.emulate(0, world, n * 4)
+    for epoch in range(5):
+        src = [t.full((n,), float(100 * epoch + r), device="cuda") + t.arange(n, device="cuda") for r in range(world)]
+        for r in range(world):
+            pxs[r].push(src[r])
+        for r in range(world):
+            got = pxs[r].wait(n * 4).contiguous().view(t.float32).view(world, n)
+            assert t.equal(got, t.stack(src)), (epoch, r)
+    assert all(p.status() == 0 for p in pxs)
+    with pytest.raises(gpu_pkg.AbsbError):
+        pxs[0].push(t.zeros(n * 2, device="cuda"))  # larger than the slot
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_search_through_peer_exchange_equals_single_index(gpu_pkg, lattice, world):
+    """Fused exchange: absb_ivf_search_push_dev stores every shard's merged top-k into all ranks'
+    buffers, absb_peer_merge_shards_dev waits inside the kernel and merges.  Ranks are emulated on
+    one GPU (all pushes are issued before the first wait); ids and scores must be bit-exact to the
+    single-index golden result on every rank, for repeated batches (ring reuse) and a ragged one."""
+    P = gpu_pkg
+    t = _torch()
+    g, x, q, c = lattice
+    d, nlist, nprobe, k = int(g["d"]), int(g["nlist"]), int(g["nprobe"]), int(g["k"])
+    nq = q.shape[0]
+    parts = []
+    for r in range(world):
+        ix = P.IndexIVFFlat(d, nlist)
+        ix.set_shard(r, world)
+        ix.set_centroids(c)
+        ix.add(x)
+        parts.append(ix)
+    pxs = P.PeerExchange.emulate(0, world, nq * k * 12 + 16)
+    L = P.lib()
+    qd = t.from_numpy(q).cuda()
+    for n_use in (nq, nq, 7, nq):
+        for r in range(world):
+            assert L.absb_ivf_search_push_dev(parts[r]._h, pxs[r]._h, n_use, ctypes.c_void_p(qd.data_ptr()), k, nprobe, None) == 0
+        for r in range(world):
+            Dm = t.empty((n_use, k), dtype=t.float32, device="cuda")
+            Im = t.empty((n_use, k), dtype=t.int64, device="cuda")
+            assert L.absb_peer_merge_shards_dev(pxs[r]._h, n_use, k, ctypes.c_void_p(Dm.data_ptr()),
+                                                ctypes.c_void_p(Im.data_ptr()), None) == 0
+            t.cuda.synchronize()
+            assert np.array_equal(Im.cpu().numpy(), g["I"][:n_use]) and np.array_equal(Dm.cpu().numpy(), g["D"][:n_use]), (n_use, r)
+    assert all(p.status() == 0 for p in pxs)
+    # a record that does not fit the slot is refused, not truncated
+    small = P.PeerExchange.emulate(0, 1, 64)[0]
+    assert L.absb_ivf_search_push_dev(parts[0]._h, small._h, nq, ctypes.c_void_p(qd.data_ptr()), k, nprobe, None) != 0
+
+
 # ------------------------------------------------------------------ larger, property-based -----
 def test_two_million_rows_properties(gpu_pkg):
     """2M x 1024 built from the device generator with precomputed list ids (the faiss add_core
