@@ -190,7 +190,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world: int):
@@ -476,7 +476,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "roofline": dict(rooflines[dominant], kernel=dominant) if dominant else None,
         "rooflines": rooflines, "phases_ms_per_step": phases, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -511,13 +511,13 @@ def run_encode(args, rank: int, world: int, local_rank: int):
         if rank == 0:
             nb = 4
             v = cpu_encode_rate(nb, args.seq_len, max(1, args.steps))
-            print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "embeddings/s", "n_gpus": args.gpus,
+            emit({"impl": "reference", "metric": metric, "value": v, "unit": "embeddings/s", "n_gpus": args.gpus,
                               "steps": args.steps, "warmup": 1, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
                               "data": "synthetic", "config": {"workload": "BASELINE configs[1] bulk encode"},
                               "cpu_baseline": {"value": v, "unit": "embeddings/s", "cores": os.cpu_count(), "kind": "port",
                                                "sample": f"{nb} x {args.seq_len}-token sequences per step, torch-CPU fp32"},
                               "e2e": {"value": v, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                              "gpu_launches": 0}), flush=True)
+                              "gpu_launches": 0})
         return
     import torch
     import torch.distributed as dist
@@ -608,7 +608,7 @@ def run_encode(args, rank: int, world: int, local_rank: int):
                                "encode_other_ms": prof["other_ms"] / args.steps},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -724,7 +724,7 @@ def run_build(args, rank: int, world: int, local_rank: int):
                      "traffic": None, "note": "whole add() step (assign + sort + scatter) charged to the GEMM"},
         "cpu_baseline": None,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_oa_jsonl(args):
@@ -762,7 +762,7 @@ def run_oa_jsonl(args):
             "gpu_launches": 0}
     if args.impl == "reference":
         if not have_ref:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/oa_jsonl is not built (needs /root/reference)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/oa_jsonl is not built (needs /root/reference)"})
             return
         dt, out = rate(ref, max(1, args.steps), max(1, args.warmup))
         line.update({"impl": "reference", "value": mb / dt, "ms_per_step": dt * 1e3,
@@ -778,7 +778,7 @@ def run_oa_jsonl(args):
             line["cpu_baseline"] = {"value": mb / dtr, "unit": "MB/s", "cores": 1, "kind": "reference",
                                     "sample": "the whole block through a pipe into oracle/_ref/oa_jsonl (the reference program)"}
             line["matches_reference_bytes"] = bool(out_ref == out)
-    print(json.dumps(line))
+    emit(line)
 
 
 def load_traffic(rooflines: dict):
@@ -796,10 +796,27 @@ def load_traffic(rooflines: dict):
             r["traffic_source"] = t[name].get("source")
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
-    # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the JSON line only
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries the JSON line and nothing else: native libraries (NCCL prints its version banner
+    # on stdout at NCCL_DEBUG=VERSION/WARN/INFO) and stray prints are sent to stderr by pointing fd 1
+    # at fd 2 for the whole run; emit() writes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
