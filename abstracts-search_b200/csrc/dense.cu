@@ -126,7 +126,7 @@ namespace {
 
 constexpr int kSelectWarps = 8;
 
-template <int SLOTS>
+template <int SLOTS, bool VEC>
 __global__ __launch_bounds__(kSelectWarps * 32) void select_rows_kernel(
     const float* __restrict__ S, int64_t ld, int ncols, long long id_offset, int k,
     float* __restrict__ out_s, long long* __restrict__ out_id, int64_t out_ld, int finalize) {
@@ -139,11 +139,36 @@ __global__ __launch_bounds__(kSelectWarps * 32) void select_rows_kernel(
 
   WarpTopK<SLOTS> tk;
   tk.init(k, lane);
-  for (int c0 = warp * 32; c0 < ncols; c0 += kSelectWarps * 32) {
-    const int c = c0 + lane;
-    const bool valid = c < ncols;
-    const float v = valid ? __ldcs(srow + c) : 0.f;
-    tk.offer_lanes(v, id_offset + c, valid);
+  if (VEC) {
+    // 128-bit loads, four columns per lane; one warp vote rejects the whole 128-column group when no
+    // score reaches the current k-th best (the common case once the threshold has settled).  The
+    // container's total order (score desc, id asc) makes the result independent of the offer order.
+    const int ngroups = ncols / 128;
+#pragma unroll 2
+    for (int g = warp; g < ngroups; g += kSelectWarps) {
+      const int c = g * 128 + lane * 4;
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(srow + c));
+      const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+      if (__any_sync(kFullMask, tk.may_enter(mx))) {
+        tk.offer_lanes(v.x, id_offset + c, true);
+        tk.offer_lanes(v.y, id_offset + c + 1, true);
+        tk.offer_lanes(v.z, id_offset + c + 2, true);
+        tk.offer_lanes(v.w, id_offset + c + 3, true);
+      }
+    }
+    for (int c0 = ngroups * 128 + warp * 32; c0 < ncols; c0 += kSelectWarps * 32) {
+      const int c = c0 + lane;
+      const bool valid = c < ncols;
+      const float v = valid ? __ldcs(srow + c) : 0.f;
+      tk.offer_lanes(v, id_offset + c, valid);
+    }
+  } else {
+    for (int c0 = warp * 32; c0 < ncols; c0 += kSelectWarps * 32) {
+      const int c = c0 + lane;
+      const bool valid = c < ncols;
+      const float v = valid ? __ldcs(srow + c) : 0.f;
+      tk.offer_lanes(v, id_offset + c, valid);
+    }
   }
   const int kk = (k + 1) & ~1;
   tk.store(sm_s + warp * kk, sm_id + warp * k);
@@ -319,8 +344,14 @@ void select_rows(const float* S, int64_t ld, int64_t nrows, int ncols, long long
   if (nrows == 0) return;
   ABSB_CHECK(k >= 1 && k <= ABSB_MAX_K, ABSB_ERR_INVALID, "k=%d outside [1,%d]", k, ABSB_MAX_K);
   const size_t smem = sizeof(float) * kSelectWarps * ((k + 1) & ~1) + sizeof(long long) * kSelectWarps * k;
-  ABSB_DISPATCH_SLOTS(k, (select_rows_kernel<SLOTS><<<(unsigned)nrows, kSelectWarps * 32, smem, st>>>(
-                             S, ld, ncols, id_offset, k, out_s, out_id, out_ld, finalize ? 1 : 0)));
+  const bool vec = ld % 4 == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0;
+  if (vec) {
+    ABSB_DISPATCH_SLOTS(k, (select_rows_kernel<SLOTS, true><<<(unsigned)nrows, kSelectWarps * 32, smem, st>>>(
+                               S, ld, ncols, id_offset, k, out_s, out_id, out_ld, finalize ? 1 : 0)));
+  } else {
+    ABSB_DISPATCH_SLOTS(k, (select_rows_kernel<SLOTS, false><<<(unsigned)nrows, kSelectWarps * 32, smem, st>>>(
+                               S, ld, ncols, id_offset, k, out_s, out_id, out_ld, finalize ? 1 : 0)));
+  }
   ABSB_CUDA(cudaGetLastError());
 }
 

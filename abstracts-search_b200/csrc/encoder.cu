@@ -50,6 +50,25 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // One warp per token: y = x * rsqrt(mean(x^2) + eps) * w.  OUT = bf16 (GEMM operand) or float.
+// Rows of up to 32 * 4 * kRmsRegs floats (1536 = stella's hidden size) are held in registers: all
+// loads of a row are in flight at once and the row is read only once.
+constexpr int kRmsRegs = 12;
+
+template <typename OUT>
+__device__ __forceinline__ void rms_store(OUT* __restrict__ y, size_t t, int H, int j, const float4& v, float rinv,
+                                          const float4& g) {
+  const float o0 = v.x * rinv * g.x, o1 = v.y * rinv * g.y, o2 = v.z * rinv * g.z, o3 = v.w * rinv * g.w;
+  if constexpr (sizeof(OUT) == 2) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(o0, o1), b = __floats2bfloat162_rn(o2, o3);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(y + t * H)[j] = pk;
+  } else {
+    reinterpret_cast<float4*>(y + t * H)[j] = make_float4(o0, o1, o2, o3);
+  }
+}
+
 template <typename OUT>
 __global__ void rmsnorm_kernel(int64_t T, int H, float eps, const float* __restrict__ x,
                                const float* __restrict__ w, OUT* __restrict__ y, float* __restrict__ rinv_out) {
@@ -57,8 +76,34 @@ __global__ void rmsnorm_kernel(int64_t T, int H, float eps, const float* __restr
   const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (t >= T) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)t * H);
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  const int n4 = H / 4;
+  if (n4 <= 32 * kRmsRegs) {
+    float4 v[kRmsRegs];
+#pragma unroll
+    for (int i = 0; i < kRmsRegs; ++i) {
+      const int j = lane + 32 * i;
+      v[i] = j < n4 ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // same summation order as the streaming path below: per lane ascending j, then the warp tree
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRmsRegs; ++i) ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    ss = warp_sum(ss);
+    const float rinv = rsqrtf(ss / (float)H + eps);
+    if (rinv_out) {
+      if (lane == 0) rinv_out[t] = rinv;
+      if (!y) return;
+    }
+#pragma unroll
+    for (int i = 0; i < kRmsRegs; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n4) rms_store(y, (size_t)t, H, j, v[i], rinv, __ldg(wr + j));
+    }
+    return;
+  }
   float ss = 0.f;
-  for (int j = lane; j < H / 4; j += 32) {
+  for (int j = lane; j < n4; j += 32) {
     const float4 v = xr[j];
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
@@ -68,21 +113,7 @@ __global__ void rmsnorm_kernel(int64_t T, int H, float eps, const float* __restr
     if (lane == 0) rinv_out[t] = rinv;
     if (!y) return;
   }
-  const float4* wr = reinterpret_cast<const float4*>(w);
-  for (int j = lane; j < H / 4; j += 32) {
-    const float4 v = xr[j];
-    const float4 g = __ldg(wr + j);
-    const float o0 = v.x * rinv * g.x, o1 = v.y * rinv * g.y, o2 = v.z * rinv * g.z, o3 = v.w * rinv * g.w;
-    if constexpr (sizeof(OUT) == 2) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(o0, o1), b = __floats2bfloat162_rn(o2, o3);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&a);
-      pk.y = *reinterpret_cast<uint32_t*>(&b);
-      reinterpret_cast<uint2*>(y + (size_t)t * H)[j] = pk;
-    } else {
-      reinterpret_cast<float4*>(y + (size_t)t * H)[j] = make_float4(o0, o1, o2, o3);
-    }
-  }
+  for (int j = lane; j < n4; j += 32) rms_store(y, (size_t)t, H, j, xr[j], rinv, __ldg(wr + j));
 }
 
 // Masked mean pool of the final-normed hidden states: pooled[b, j] = w[j] * sum_s m[b,s] *

@@ -75,6 +75,7 @@ def parse_args():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: all-gathers of the query path as NVLink peer-memory stores fused into our kernels "
                          "(default) or as NCCL calls")
+    ap.add_argument("--no-compact", action="store_true", help="skip Index.compact() after the synthetic fill")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not time individual kernels in the timed region")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -289,6 +290,10 @@ def build_shard(P, torch, args, rank: int, world: int, dev: int):
     torch.cuda.synchronize()
     del xbuf
     torch.cuda.empty_cache()
+    if not args.no_compact:
+        # 1M-row adds leave every list one page per add, scattered over the pool: make lists contiguous
+        # (in place) so that the scan's work items are scan_chunk vectors long instead of one page
+        ix.compact()
     return ix, time.time() - t0
 
 
