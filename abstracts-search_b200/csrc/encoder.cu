@@ -453,7 +453,7 @@ struct Encoder {
       for (int i = 0; i < half; ++i) {
         const float inv_freq = 1.0f / powf(c.rope_theta, (float)(2 * i) / (float)kHD);
         const float ang = (float)p * inv_freq;
-        cs[(size_t)p * half + i] = make_float2(cosf(ang), sinf(ang));
+        cs[(size_t)i * c.max_seq_len + p] = make_float2(cosf(ang), sinf(ang));  // pair-major (gemm_tc.cuh)
       }
     rope_cs.alloc_exact(cs.size());
     ABSB_CUDA(cudaMemcpy(rope_cs.p, cs.data(), cs.size() * sizeof(float2), cudaMemcpyHostToDevice));
@@ -681,6 +681,7 @@ struct Encoder {
         rope.cs = rope_cs.p;
         rope.S = S;
         rope.cols = (nh + nkv) * kHD;
+        rope.ld = cfg.max_seq_len;
         gemm(EPI_BF16_BIAS_ROPE, (int)T, QKV, H, xn.p, L.wqkv.p, qkv.p, QKV, L.bqkv.p, st, &rope);
       }
       {

@@ -78,7 +78,7 @@ struct KernelParams {
   int64_t ldc;
   const float* bias;
   const float2* rope_cs;  // EPI_BF16_BIAS_ROPE only
-  int rope_S, rope_cols;
+  int rope_S, rope_cols, rope_ld;
   int* arg_idx;  // EPI_ARGMAX only: [M, ldc] next to out = float [M, ldc]
 };
 
@@ -290,7 +290,8 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
         const int hc = tn * BN + chalf * 128;  // first column of the head
         const bool rotate = hc < p.rope_cols;
-        const float2* cs = p.rope_cs + (size_t)(row_ok ? row % p.rope_S : 0) * 64;
+        // pair-major table: consecutive lanes (= consecutive positions) read consecutive float2
+        const float2* cs = p.rope_cs + (row_ok ? row % p.rope_S : 0);
 #pragma unroll 1
         for (int c = 0; c < 64; c += 32) {
           uint32_t v1[32], v2[32];
@@ -319,13 +320,11 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
               }
               if (rotate) {
 #pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                  const float4 t = __ldg(reinterpret_cast<const float4*>(cs + c + j * 8 + e));  // cos0 sin0 cos1 sin1
-                  const float x0 = a[e], y0 = b[e], x1 = a[e + 1], y1 = b[e + 1];
+                for (int e = 0; e < 8; ++e) {
+                  const float2 t = __ldg(cs + (size_t)(c + j * 8 + e) * p.rope_ld);  // (cos, sin) of pair c+j*8+e
+                  const float x0 = a[e], y0 = b[e];
                   a[e] = x0 * t.x - y0 * t.y;
                   b[e] = y0 * t.x + x0 * t.y;
-                  a[e + 1] = x1 * t.z - y1 * t.w;
-                  b[e + 1] = y1 * t.z + x1 * t.w;
                 }
               }
               dst1[j] = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]),
@@ -576,7 +575,7 @@ void gemm_bf16_tc_ex(int epi, int M, int N, int K, const void* A, int64_t lda, c
                      int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st, const GemmRope* rope,
                      int* arg_idx) {
   if (M == 0 || N == 0) return;
-  ABSB_CHECK(epi != EPI_BF16_BIAS_ROPE || (rope && rope->cs && rope->S >= 1 && rope->cols % 128 == 0 && N % 128 == 0),
+  ABSB_CHECK(epi != EPI_BF16_BIAS_ROPE || (rope && rope->cs && rope->S >= 1 && rope->ld >= rope->S && rope->cols % 128 == 0 && N % 128 == 0),
              ABSB_ERR_INVALID, "RoPE epilogue needs a table, S >= 1 and 128-wide heads");
   ABSB_CHECK(K > 0 && K % 8 == 0, ABSB_ERR_INVALID, "tcgen05 GEMM needs K %% 8 == 0 (K=%d)", K);
   ABSB_CHECK(N % 32 == 0, ABSB_ERR_INVALID, "tcgen05 GEMM needs N %% 32 == 0 (N=%d)", N);
@@ -611,6 +610,7 @@ void gemm_bf16_tc_ex(int epi, int M, int N, int K, const void* A, int64_t lda, c
     p.rope_cs = rope->cs;
     p.rope_S = rope->S;
     p.rope_cols = rope->cols;
+    p.rope_ld = rope->ld;
   }
   p.arg_idx = arg_idx;
   ABSB_CHECK(epi != EPI_ARGMAX || arg_idx, ABSB_ERR_INVALID, "arg-max epilogue needs an index buffer");
@@ -618,6 +618,10 @@ void gemm_bf16_tc_ex(int epi, int M, int N, int K, const void* A, int64_t lda, c
 
   // Tile shape: CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row block;
   // 192-column tiles when they cut the work into fewer, fuller waves (N = 1536: 8 x 192 instead of 6 x 256).
+  // A 192-column tile keeps the tensor pipe ~0.85 as busy as a 256-column one (72% vs 90% active in
+  // profiles/r01m_ncu_summary.md), so its column count is charged at 1/0.85: measured on N = 1536,
+  // K = 8960 the model then picks 192 at M = 2048 / 4096 and 256 at M = 8192 / 16384, which is the
+  // faster variant in all four cases (profiles/r01n_gemm_residual_variants.log).
   int variant = g_gemm_variant;
   if (variant == 0) {
     if (M <= BM) {
@@ -629,7 +633,7 @@ void gemm_bf16_tc_ex(int epi, int M, int N, int K, const void* A, int64_t lda, c
         const int64_t tm = ceil_div(M, 2 * BM);
         const int64_t cost256 = ceil_div(tm * ceil_div(N, 256), workers) * 256;
         const int64_t cost192 = ceil_div(tm * ceil_div(N, 192), workers) * 192;
-        if (cost192 < cost256) variant = 3;
+        if (cost192 * 100 < cost256 * 85) variant = 3;
       }
     }
   }

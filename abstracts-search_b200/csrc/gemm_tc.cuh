@@ -22,9 +22,10 @@ enum GemmEpilogue {
 // RoPE side input of EPI_BF16_BIAS_ROPE: cs[pos, i] = (cos, sin) of pos * inv_freq[i], i < 64;
 // the position of GEMM row r is r % S.
 struct GemmRope {
-  const float2* cs = nullptr;
-  int S = 1;
-  int cols = 0;
+  const float2* cs = nullptr;  // (cos, sin) table, PAIR-major: cs[i * ld + pos], i < head_dim / 2
+  int S = 1;                   // sequence length: position of GEMM row r is r % S
+  int cols = 0;                // leading output columns that are rotated (q and k heads)
+  int ld = 0;                  // positions per table row (>= S)
 };
 
 constexpr int kMaxGemmSegs = 8;

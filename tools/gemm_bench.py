@@ -53,9 +53,17 @@ def epilogues():
         B = (torch.randn((N, K), device="cuda") * 0.02).to(torch.bfloat16)
         out = torch.zeros((T, N // 2 if epi == 3 else N), dtype=torch.bfloat16 if epi in (0, 3) else torch.float32, device="cuda")
         ms = timeit(lambda: enc.gemm_bf16_epi(A, B, epi, out=out))
-        print(f"epi {name:11s} M={T} N={N} K={K}: {ms*1e3:7.1f} us {2.0*T*N*K/ms/1e9:7.0f} TF", flush=True)
+        row = f"epi {name:11s} M={T} N={N} K={K}: auto {ms*1e3:7.1f} us {2.0*T*N*K/ms/1e9:7.0f} TF"
+        if epi == 2:  # the residual-add GEMMs may take 256- or 192-column tiles
+            for v in (2, 3):
+                enc.gemm_set_variant(v)
+                ms = timeit(lambda: enc.gemm_bf16_epi(A, B, epi, out=out))
+                row += f" | v{v} {ms*1e3:7.1f} us {2.0*T*N*K/ms/1e9:7.0f} TF"
+            enc.gemm_set_variant(0)
+        print(row, flush=True)
 
 
 if __name__ == "__main__":
-    main()
+    if "--epi-only" not in sys.argv:
+        main()
     epilogues()
