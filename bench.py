@@ -75,6 +75,10 @@ def parse_args():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: all-gathers of the query path as NVLink peer-memory stores fused into our kernels "
                          "(default) or as NCCL calls")
+    ap.add_argument("--pipeline", type=int, default=0,
+                    help="1: software-pipeline consecutive batches on two streams (encode of batch i+1 on a high-priority "
+                         "stream overlaps the HBM-bound search of batch i); the timed region covers fill and drain")
+    ap.add_argument("--scan-ctas", type=int, default=-1, help="resident scan CTAs per SM (<= 0: occupancy query)")
     ap.add_argument("--no-compact", action="store_true", help="skip Index.compact() after the synthetic fill")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not time individual kernels in the timed region")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
@@ -267,7 +271,7 @@ def build_shard(P, torch, args, rank: int, world: int, dev: int):
     d, nlist = 1024, args.nlist
     total = args.rows_per_gpu * world
     ix = P.index_factory(d, f"IVF{nlist},Flat", P.METRIC_INNER_PRODUCT, device=dev)
-    ix.set_tunables(scan_chunk=args.scan_chunk, coarse_impl=args.coarse_impl)
+    ix.set_tunables(scan_chunk=args.scan_chunk, coarse_impl=args.coarse_impl, scan_ctas_per_sm=args.scan_ctas)
     ix.set_scan_order(bool(args.scan_order))
     if world > 1:
         ix.set_shard(rank, world)
@@ -345,6 +349,50 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             return sh.search(emb_all, k)
         return ix.search(e, k)
 
+    # ---- optional two-stream software pipeline over consecutive batches ---------------------------
+    if args.pipeline:
+        s_enc = torch.cuda.Stream(priority=-1)  # tensor-bound encoder first in line for SM slots
+        s_srch = torch.cuda.Stream(priority=0)
+        emb_ring = [torch.empty((nq, 1024), dtype=torch.float32, device=device) for _ in range(2)]
+        ev_enc = [torch.cuda.Event() for _ in range(2)]
+        ev_srch = [torch.cuda.Event() for _ in range(2)]
+        pipe_state = {"i": 0, "last": None}
+
+        def pipe_encode(i):
+            with torch.cuda.stream(s_enc):
+                s_enc.wait_event(ev_srch[i & 1])  # the search that read this ring entry two batches ago is done
+                e = enc.encode_tokens(ids_d[lo:hi], mask_d[lo:hi], normalize_embeddings=True)
+                if world > 1:
+                    if px_emb is not None:
+                        emb_ring[i & 1].copy_(px_emb.allgather(e).view(nq, 1024))
+                    else:
+                        dist.all_gather_into_tensor(emb_ring[i & 1], e)
+                else:
+                    emb_ring[i & 1].copy_(e)
+                ev_enc[i & 1].record(s_enc)
+
+        def pipe_search(j):
+            with torch.cuda.stream(s_srch):
+                s_srch.wait_event(ev_enc[j & 1])
+                out = sh.search(emb_ring[j & 1], k) if world > 1 else ix.search(emb_ring[j & 1], k)
+                ev_srch[j & 1].record(s_srch)
+            return out
+
+        def run_pipelined(steps):
+            """`steps` batches end to end: steps + 1 iterations, encode(i) || search(i - 1)."""
+            out = None
+            cur = torch.cuda.current_stream()
+            s_enc.wait_stream(cur)
+            s_srch.wait_stream(cur)
+            for i in range(steps + 1):
+                if i < steps:
+                    pipe_encode(i)
+                if i > 0:
+                    out = pipe_search(i - 1)
+            cur.wait_stream(s_enc)
+            cur.wait_stream(s_srch)
+            return out
+
     def step_e2e():
         e = enc.encode_tokens(ids_np[lo:hi], mask_np[lo:hi], normalize_embeddings=True)  # host in, host out
         if world > 1:
@@ -387,18 +435,25 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # Pass B (instrumented): the same K steps again with the library recording a CUDA-event pair
     # around every kernel on that stream -> per-kernel durations for the roofline.  The ~230 extra
     # event records per step cost up to 8% at N=8 (short kernels), so they stay out of `value`.
-    def timed(steps):
+    def timed(steps, pipelined=False):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
-        for _ in range(steps):
-            step_dev()
+        if pipelined:
+            Dp, Ip = run_pipelined(steps)  # both side streams are joined into the current one before ev1
+        else:
+            for _ in range(steps):
+                step_dev()
         ev1.record()
         barrier()
+        if pipelined:
+            assert np.array_equal(Ip.cpu().numpy(), Iw), "pipelined result differs from the serial result"
         return max_over_ranks(ev0.elapsed_time(ev1))
 
     sampler = ClockSampler(dev) if rank == 0 else None
-    ms_total = timed(args.steps)
+    if args.pipeline:
+        timed(3, pipelined=True)  # warm the side streams
+    ms_total = timed(args.steps, pipelined=bool(args.pipeline))
     kernel_events = not args.no_kernel_events
     enc_prof = ix_prof = None
     ms_instrumented = None
@@ -470,7 +525,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         cpu = {"value": qps, "unit": UNIT, "cores": cp.cores, "kind": "port", "sample": cp.describe()}
 
     cfg = workload_config(args, world)
-    cfg.update({"exchange": exchange, "index_build_s": build_s, "distinct_probed_lists_per_step": distinct_lists,
+    cfg.update({"pipeline": ("two streams: encode of batch i+1 overlaps search of batch i; K batches timed over K+1 iterations "
+                             "including fill and drain" if args.pipeline else "none: encode then search, one stream"),
+                "exchange": exchange, "index_build_s": build_s, "distinct_probed_lists_per_step": distinct_lists,
                 "scan_work_items_per_step": st["items"], "ms_per_step_with_kernel_events": ms_instrumented, "coarse_impl": "tcgen05 split-bf16 (6 bf16 products, fp32-faithful)"
                 if args.coarse_impl == 1 else "fp32 FFMA", "kernel_events": "second timed pass of the same K steps" if kernel_events else "off"})
     line = {
