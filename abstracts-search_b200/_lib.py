@@ -114,7 +114,6 @@ _SIGS = {
     "absb_merge_shards_dev": ([c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p], c_int),
     "absb_ivf_set_tunables": ([_H, c_int, c_int, c_int], c_int),
     "absb_ivf_set_scan_order": ([_H, c_int], c_int),
-    "absb_ivf_set_scan_prefetch": ([_H, c_int], c_int),
     "absb_ivf_last_stats": ([_H, _PI64, _PI64, _PI64, _PI64], c_int),
     "absb_ivf_set_profile": ([_H, c_int], c_int),
     "absb_ivf_get_profile": ([_H, _PD, _PD, _PD, _PI64], c_int),

@@ -738,14 +738,6 @@ int absb_peer_merge_shards_dev(absb_peer_t p, int64_t n, int k, float* D_dev, in
   ABSB_API_END
 }
 
-int absb_ivf_set_scan_prefetch(absb_ivf_t h, int vectors_ahead) {
-  ABSB_API_BEGIN
-  NEED(h);
-  ABSB_CHECK(vectors_ahead >= 0 && vectors_ahead <= 64, ABSB_ERR_INVALID, "prefetch distance %d outside [0,64]", vectors_ahead);
-  h->ix.scan_prefetch = vectors_ahead;
-  ABSB_API_END
-}
-
 int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int scan_ctas_per_sm) {
   ABSB_API_BEGIN
   NEED(h);

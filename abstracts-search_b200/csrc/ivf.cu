@@ -897,7 +897,6 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
     a.part_id = ws_part_id.p;
     a.sm_count = props.sm_count;
     a.ctas_per_sm = scan_ctas_per_sm;
-    a.prefetch_vecs = scan_prefetch;
     {
       Span sp(this, st, 0);
       launch_scan(a, st);

@@ -78,7 +78,6 @@ struct IvfIndex {
   int scan_chunk = 128;
   int coarse_impl = 1;  // 1 = tcgen05 split-bf16 (falls back to the FFMA GEMM for shapes it cannot take)
   int scan_ctas_per_sm = 0;
-  int scan_prefetch = 0;  // L2 prefetch distance of the fine scan, in vectors (0 = off)
   int scan_order = 1;  // 1 = list-major work queue (probes of one list scanned together: L2 reuse), 0 = query-major
 
   // workspaces (single stream at a time)

@@ -144,22 +144,12 @@ __device__ __forceinline__ ScanItem load_item(const ScanItem* p) {
   return it;
 }
 
-// Pulls `bytes` (multiple of 16) at a 16-byte-aligned global address into L2 without occupying
-// registers or shared memory (TMA prefetch, no completion tracking).
-__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 // Fast path: d = 128 * D4, query in registers, U vectors in flight per warp.
-// pf > 0: lane 0 keeps an L2 prefetch running `pf` vectors ahead of the register loads, so that a
-// warp's two in-flight vectors pay L2 instead of DRAM latency: the kernel then reaches HBM bandwidth
-// from far fewer resident warps, which is what lets it share the SMs with the encoder's GEMM CTAs
-// (profiles/r01r_pipeline_experiment.md).
 template <int SLOTS, int D4, int U>
 __global__ __launch_bounds__(kScanThreads) void ivf_scan_kernel(
     const float* __restrict__ Q, const ScanItem* __restrict__ items, const int* __restrict__ n_items_ptr,
     int* __restrict__ queue_counter, const int* __restrict__ order, int k, float* __restrict__ part_s,
-    long long* __restrict__ part_id, int pf) {
+    long long* __restrict__ part_id) {
   constexpr int d4 = D4 * 32;  // float4 per vector
   const int lane = threadIdx.x & 31;
   const int n_items = *n_items_ptr;
@@ -179,12 +169,8 @@ __global__ __launch_bounds__(kScanThreads) void ivf_scan_kernel(
     WarpTopK<SLOTS> tk;
     tk.init(k, lane);
     const float4* cp = reinterpret_cast<const float4*>(it.codes) + lane;
-    constexpr unsigned kVecBytes = (unsigned)d4 * 16u;
-    if (pf > 0 && lane == 0) l2_prefetch(it.codes, (unsigned)min(it.len, pf) * kVecBytes);
     int v = 0;
     for (; v + U <= it.len; v += U) {
-      if (pf > 0 && lane == 0 && v + pf < it.len)
-        l2_prefetch(it.codes + (size_t)(v + pf) * (d4 * 4), (unsigned)min(U, it.len - v - pf) * kVecBytes);
       float4 x[U][D4];
 #pragma unroll
       for (int u = 0; u < U; ++u)
@@ -339,7 +325,7 @@ void launch_scan(const ScanLaunch& a, cudaStream_t st) {
       auto kern = ivf_scan_kernel<SLOTS, D4, kScanUnroll>;
       const int per_sm = a.ctas_per_sm > 0 ? a.ctas_per_sm : resident_ctas(kern, 0);
       kern<<<sms * per_sm, kScanThreads, 0, st>>>(a.Q, a.items, a.n_items, a.queue_counter, a.order, a.k,
-                                                  a.part_s, a.part_id, a.prefetch_vecs);
+                                                  a.part_s, a.part_id);
     });
   } else {
     ABSB_CHECK(a.d % 4 == 0, ABSB_ERR_UNSUPPORTED, "IVF scan needs d %% 4 == 0 (d=%d)", a.d);

@@ -48,7 +48,6 @@ struct ScanLaunch {
   long long* part_id;  // [max_items, k]
   int sm_count;
   int ctas_per_sm;  // <= 0: occupancy query
-  int prefetch_vecs = 0;  // d = 1024 fast path: L2 prefetch distance in vectors (0 = off)
 };
 
 // Scratch of the list-major queue order (all [npairs + 1] except order [max_items]).

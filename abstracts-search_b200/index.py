@@ -242,10 +242,6 @@ class IndexIVFFlat:
     def set_tunables(self, scan_chunk: int = -1, coarse_impl: int = -1, scan_ctas_per_sm: int = -1):
         check(lib().absb_ivf_set_tunables(self._h, scan_chunk, coarse_impl, scan_ctas_per_sm))
 
-    def set_scan_prefetch(self, vectors_ahead: int = 0):
-        """L2 prefetch distance of the fine scan (vectors ahead of each warp's loads; 0 = off)."""
-        check(lib().absb_ivf_set_scan_prefetch(self._h, int(vectors_ahead)))
-
     def set_scan_order(self, list_major: bool = True):
         """Work-queue order of the fine scan: list-major (default, L2 reuse across queries) or query-major."""
         check(lib().absb_ivf_set_scan_order(self._h, 1 if list_major else 0))

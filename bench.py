@@ -78,7 +78,6 @@ def parse_args():
     ap.add_argument("--pipeline", type=int, default=0,
                     help="1: software-pipeline consecutive batches on two streams (encode of batch i+1 on a high-priority "
                          "stream overlaps the HBM-bound search of batch i); the timed region covers fill and drain")
-    ap.add_argument("--scan-prefetch", type=int, default=0, help="fine scan: L2 prefetch distance in vectors (0 = off)")
     ap.add_argument("--scan-ctas", type=int, default=-1, help="resident scan CTAs per SM (<= 0: occupancy query)")
     ap.add_argument("--no-compact", action="store_true", help="skip Index.compact() after the synthetic fill")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not time individual kernels in the timed region")
@@ -274,7 +273,6 @@ def build_shard(P, torch, args, rank: int, world: int, dev: int):
     ix = P.index_factory(d, f"IVF{nlist},Flat", P.METRIC_INNER_PRODUCT, device=dev)
     ix.set_tunables(scan_chunk=args.scan_chunk, coarse_impl=args.coarse_impl, scan_ctas_per_sm=args.scan_ctas)
     ix.set_scan_order(bool(args.scan_order))
-    ix.set_scan_prefetch(args.scan_prefetch)
     if world > 1:
         ix.set_shard(rank, world)
     ix.set_centroids(P.synth.centroids(SEED, nlist, d, device=dev))

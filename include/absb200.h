@@ -191,10 +191,6 @@ int absb_merge_shards_dev(int device, int world, int64_t n, int k, const float* 
                           const int64_t* I_all_dev, int64_t rank_stride_bytes, float* D_dev,
                           int64_t* I_dev, void* stream);
 
-/* Fine scan: keep a TMA prefetch into L2 running `vectors_ahead` vectors in front of every warp's
- * register loads (0 = off, the default).  Lets the scan reach HBM bandwidth at low occupancy, e.g.
- * capped at 1-2 CTAs per SM next to the encoder's GEMM CTAs.  Changes no result. */
-int absb_ivf_set_scan_prefetch(absb_ivf_t h, int vectors_ahead);
 /* Tunables (chunk = vectors per scan work item; coarse_impl 0 = fp32 SIMT, 1 = tcgen05
  * split-bf16). Values < 0 leave a setting unchanged. */
 int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int scan_ctas_per_sm);
