@@ -121,3 +121,16 @@ def test_threads_preserve_record_order_on_a_large_block():
     ids = [json.loads(x)["id"] for x in one.splitlines()]
     src = [json.loads(x)["id"] for x in data.splitlines()]
     assert ids == [i for i in src if i in set(ids)]
+
+
+@pytest.mark.skipif(not O.reference_available(), reason="oracle/_ref/oa_jsonl not built (needs /root/reference)")
+def test_cli_carries_partial_lines_across_its_32mb_blocks():
+    """The executable reads stdin in 32 MB blocks and carries the unfinished tail over: an input of
+    several blocks must come out byte-identical to the reference program's output."""
+    data = OA.synth_records(5, 11000, mean_words=120, filler=10)
+    assert len(data) > 36 << 20
+    want = O.convert_reference(data)
+    r = subprocess.run([CLI], input=data, capture_output=True, timeout=120)
+    assert r.returncode == 0 and r.stdout == want
+    r1 = subprocess.run([CLI, "1"], input=data[:-1], capture_output=True, timeout=120)  # no final newline, one thread
+    assert r1.returncode == 0 and r1.stdout == want
