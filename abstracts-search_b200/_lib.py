@@ -114,6 +114,8 @@ _SIGS = {
     "absb_merge_shards_dev": ([c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p], c_int),
     "absb_ivf_set_tunables": ([_H, c_int, c_int, c_int], c_int),
     "absb_ivf_set_scan_order": ([_H, c_int], c_int),
+    "absb_ivf_set_two_stage": ([_H, c_int], c_int),
+    "absb_ivf_two_stage_fallbacks": ([_H, _PI64], c_int),
     "absb_ivf_last_stats": ([_H, _PI64, _PI64, _PI64, _PI64], c_int),
     "absb_ivf_set_profile": ([_H, c_int], c_int),
     "absb_ivf_get_profile": ([_H, _PD, _PD, _PD, _PI64], c_int),
@@ -146,6 +148,7 @@ _SIGS = {
     "absb_peer_wait_dev": ([_H, POINTER(c_void_p), c_void_p], c_int),
     "absb_peer_status": ([_H, POINTER(c_int)], c_int),
     "absb_ivf_search_push_dev": ([_H, _H, c_int64, c_void_p, c_int, c_int, c_void_p], c_int),
+    "absb_peer_push_results_dev": ([_H, c_int64, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "absb_peer_merge_shards_dev": ([_H, c_int64, c_int, c_void_p, c_void_p, c_void_p], c_int),
     # OpenAlex JSON-lines front end (host only)
     "absb_oa_jsonl_convert": ([c_char_p, c_size_t, c_int, c_int, POINTER(c_char_p), POINTER(c_size_t),

@@ -723,6 +723,26 @@ int absb_ivf_search_push_dev(absb_ivf_t h, absb_peer_t p, int64_t n, const float
   ABSB_API_END
 }
 
+int absb_peer_push_results_dev(absb_peer_t p, int64_t n, int k, const float* D_dev, const int64_t* I_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(p);
+  ABSB_CHECK(n >= 1 && k >= 1 && k <= ABSB_MAX_K && D_dev && I_dev, ABSB_ERR_INVALID, "bad push arguments");
+  PeerExchange& px = p->px;
+  const size_t i_bytes = ((size_t)n * k * sizeof(long long) + 15) & ~(size_t)15;
+  const size_t d_bytes = ((size_t)n * k * sizeof(float) + 15) & ~(size_t)15;
+  ABSB_CHECK(i_bytes + d_bytes <= px.slot_bytes, ABSB_ERR_INVALID,
+             "record of %lld x %d results does not fit the exchange slot (%zu bytes)", (long long)n, k, px.slot_bytes);
+  DeviceGuard g(px.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  px.staging.reserve(px.slot_bytes);
+  ABSB_CUDA(cudaMemcpyAsync(px.staging.p, I_dev, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+  ABSB_CUDA(cudaMemcpyAsync(px.staging.p + i_bytes, D_dev, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  px.push(px.staging.p, i_bytes + d_bytes, st);
+  px.rec_n = n;
+  px.rec_k = k;
+  ABSB_API_END
+}
+
 int absb_peer_merge_shards_dev(absb_peer_t p, int64_t n, int k, float* D_dev, int64_t* I_dev, void* stream) {
   ABSB_API_BEGIN
   NEED(p);
@@ -735,6 +755,23 @@ int absb_peer_merge_shards_dev(absb_peer_t p, int64_t n, int k, float* D_dev, in
   merge_shards_wait(px.world, n, k, px.local_entry(px.epoch), (int64_t)px.slot_bytes, 0, (int64_t)i_bytes,
                     px.local_flags(), px.epoch, px.status.p, D_dev, reinterpret_cast<long long*>(I_dev),
                     (cudaStream_t)stream);
+  ABSB_API_END
+}
+
+int absb_ivf_set_two_stage(absb_ivf_t h, int shortlist) {
+  ABSB_API_BEGIN
+  NEED(h);
+  DeviceGuard g(h->ix.device);
+  h->ix.set_two_stage(shortlist);
+  ABSB_API_END
+}
+
+int absb_ivf_two_stage_fallbacks(absb_ivf_t h, int64_t* queries) {
+  ABSB_API_BEGIN
+  NEED(h);
+  NEED(queries);
+  DeviceGuard g(h->ix.device);
+  *queries = h->ix.two_stage_fallbacks(nullptr);
   ABSB_API_END
 }
 

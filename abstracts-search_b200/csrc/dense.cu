@@ -201,10 +201,12 @@ __global__ __launch_bounds__(kSelectWarps * 32) void select_rows_kernel(
 template <int SLOTS>
 __global__ __launch_bounds__(128) void merge_partials_kernel(
     int nq, int k, const int* __restrict__ q_begin, const float* __restrict__ part_s,
-    const long long* __restrict__ part_id, float* __restrict__ D, long long* __restrict__ I) {
+    const long long* __restrict__ part_id, float* __restrict__ D, long long* __restrict__ I,
+    const unsigned char* __restrict__ active) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq) return;
+  if (active != nullptr && active[q] == 0) return;
   WarpTopK<SLOTS> tk;
   tk.init(k, lane);
   const int64_t b = (int64_t)q_begin[q] * k, e = (int64_t)q_begin[q + 1] * k;
@@ -356,10 +358,10 @@ void select_rows(const float* S, int64_t ld, int64_t nrows, int ncols, long long
 }
 
 void merge_partials(int nq, int k, const int* q_begin, const float* part_s, const long long* part_id,
-                    float* D, long long* I, cudaStream_t st) {
+                    float* D, long long* I, cudaStream_t st, const unsigned char* active) {
   if (nq == 0) return;
   ABSB_DISPATCH_SLOTS(k, (merge_partials_kernel<SLOTS><<<(nq + 3) / 4, 128, 0, st>>>(
-                             nq, k, q_begin, part_s, part_id, D, I)));
+                             nq, k, q_begin, part_s, part_id, D, I, active)));
   ABSB_CUDA(cudaGetLastError());
 }
 

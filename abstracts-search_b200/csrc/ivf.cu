@@ -6,6 +6,8 @@
 // (/root/reference/README.md:16,28).  See SURVEY.md §8(a) a4–a8 for the semantics followed here.
 #include "ivf.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cub/cub.cuh>
 
 #include "gemm_tc.cuh"
@@ -71,10 +73,12 @@ __global__ void scatter_rows_kernel(int64_t n_kept, int d4, int P, int slab_shif
                                     float* const* __restrict__ code_slabs,
                                     long long* const* __restrict__ id_slabs,
                                     const float* __restrict__ x, const long long* __restrict__ ids,
-                                    long long id0) {
+                                    long long id0, unsigned short* const* __restrict__ half_slabs,
+                                    float* __restrict__ maxima) {
   const int lane = threadIdx.x & 31;
   const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float worst_r2 = 0.f, worst_x2 = 0.f;  // lane 0: largest |x - fp16(x)|^2 and |x|^2 of this warp's rows
   for (int64_t p = wid; p < n_kept; p += nw) {
     const unsigned l = keys_sorted[p];
     const int row = perm[p];
@@ -85,8 +89,40 @@ __global__ void scatter_rows_kernel(int64_t n_kept, int d4, int P, int slab_shif
     const long long in_slab = page & ((1ll << slab_shift) - 1);
     float4* dst = reinterpret_cast<float4*>(code_slabs[slab]) + ((size_t)in_slab * P + slot) * d4;
     const float4* src = reinterpret_cast<const float4*>(x) + (size_t)row * d4;
-    for (int j = lane; j < d4; j += 32) dst[j] = __ldcs(src + j);
+    if (half_slabs == nullptr) {
+      for (int j = lane; j < d4; j += 32) dst[j] = __ldcs(src + j);
+    } else {
+      // fp16 shadow copy for the two-stage scan + the two norms its error bound needs
+      uint2* hdst = reinterpret_cast<uint2*>(half_slabs[slab]) + ((size_t)in_slab * P + slot) * d4;
+      float r2 = 0.f, x2 = 0.f;
+      for (int j = lane; j < d4; j += 32) {
+        const float4 v = __ldcs(src + j);
+        dst[j] = v;
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const unsigned*>(&h0);
+        pk.y = *reinterpret_cast<const unsigned*>(&h1);
+        hdst[j] = pk;
+        const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+        const float e0 = v.x - b0.x, e1 = v.y - b0.y, e2 = v.z - b1.x, e3 = v.w - b1.y;
+        r2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+        x2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+      }
+      // NaN/inf rows (fp16 overflow) make the bound infinite: such an index always takes the fallback
+      worst_r2 = (r2 > worst_r2 || !(r2 == r2)) ? (r2 == r2 ? r2 : INFINITY) : worst_r2;
+      worst_x2 = (x2 > worst_x2 || !(x2 == x2)) ? (x2 == x2 ? x2 : INFINITY) : worst_x2;
+    }
     if (lane == 0) id_slabs[slab][(size_t)in_slab * P + slot] = ids ? ids[row] : id0 + row;
+  }
+  if (half_slabs != nullptr && lane == 0) {
+    // non-negative floats order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned*>(maxima), __float_as_uint(sqrtf(worst_r2)));
+    atomicMax(reinterpret_cast<unsigned*>(maxima) + 1, __float_as_uint(sqrtf(worst_x2)));
   }
 }
 
@@ -140,7 +176,8 @@ __global__ void copy_list_kernel(ListTable lt, long long l, float* __restrict__ 
 __global__ void move_pages_kernel(int64_t n_moves, const PageMove* __restrict__ moves, int P, int d4,
                                   int slab_shift, float* const* __restrict__ code_slabs,
                                   long long* const* __restrict__ id_slabs, float* __restrict__ scratch_codes,
-                                  long long* __restrict__ scratch_ids) {
+                                  long long* __restrict__ scratch_ids, unsigned short* const* __restrict__ half_slabs,
+                                  unsigned short* __restrict__ scratch_half) {
   const long long mask = (1ll << slab_shift) - 1;
   const size_t page_f4 = (size_t)P * d4;
   for (int64_t m = blockIdx.x; m < n_moves; m += gridDim.x) {
@@ -165,6 +202,16 @@ __global__ void move_pages_kernel(int64_t n_moves, const PageMove* __restrict__ 
     }
     for (size_t j = threadIdx.x; j < page_f4; j += blockDim.x) __stcs(dst_c + j, __ldcs(src_c + j));
     for (int j = threadIdx.x; j < P; j += blockDim.x) dst_i[j] = src_i[j];
+    if (half_slabs != nullptr) {
+      const size_t page_h4 = page_f4 / 2;  // 16-byte words of one page of fp16 codes
+      const float4* src_h = reinterpret_cast<const float4*>(
+          mv.from >= 0 ? half_slabs[mv.from >> slab_shift] + (size_t)(mv.from & mask) * page_h4 * 8
+                       : scratch_half + (size_t)(-1 - mv.from) * page_h4 * 8);
+      float4* dst_h = reinterpret_cast<float4*>(
+          mv.to >= 0 ? half_slabs[mv.to >> slab_shift] + (size_t)(mv.to & mask) * page_h4 * 8
+                     : scratch_half + (size_t)(-1 - mv.to) * page_h4 * 8);
+      for (size_t j = threadIdx.x; j < page_h4; j += blockDim.x) __stcs(dst_h + j, __ldcs(src_h + j));
+    }
   }
 }
 
@@ -199,8 +246,18 @@ void PagePool::ensure_pages(int64_t total_pages, cudaStream_t st) {
       cudaFree(c);
       ABSB_CUDA(e);
     }
+    unsigned short* hs = nullptr;
+    if (shadow) {
+      e = cudaMalloc(&hs, (size_t)per_slab * page_vecs * d * sizeof(unsigned short));
+      if (e != cudaSuccess) {
+        cudaFree(c);
+        cudaFree(i);
+        ABSB_CUDA(e);
+      }
+    }
     code_slabs.push_back(c);
     id_slabs.push_back(i);
+    half_slabs.push_back(hs);
   }
   if (code_slabs.size() > table_cap) {
     // the old tables may still be referenced by in-flight kernels on st: sync before freeing
@@ -208,10 +265,13 @@ void PagePool::ensure_pages(int64_t total_pages, cudaStream_t st) {
     table_cap = std::max<size_t>(64, code_slabs.size() * 2);
     d_code_slabs.alloc_exact(table_cap);
     d_id_slabs.alloc_exact(table_cap);
+    d_half_slabs.alloc_exact(table_cap);
   }
   ABSB_CUDA(cudaMemcpyAsync(d_code_slabs.p, code_slabs.data(), code_slabs.size() * sizeof(float*),
                             cudaMemcpyHostToDevice, st));
   ABSB_CUDA(cudaMemcpyAsync(d_id_slabs.p, id_slabs.data(), id_slabs.size() * sizeof(long long*),
+                            cudaMemcpyHostToDevice, st));
+  ABSB_CUDA(cudaMemcpyAsync(d_half_slabs.p, half_slabs.data(), half_slabs.size() * sizeof(unsigned short*),
                             cudaMemcpyHostToDevice, st));
   ABSB_CUDA(cudaStreamSynchronize(st));  // host vectors may reallocate later
 }
@@ -219,8 +279,11 @@ void PagePool::ensure_pages(int64_t total_pages, cudaStream_t st) {
 void PagePool::release() {
   for (auto p : code_slabs) cudaFree(p);
   for (auto p : id_slabs) cudaFree(p);
+  for (auto p : half_slabs)
+    if (p) cudaFree(p);
   code_slabs.clear();
   id_slabs.clear();
+  half_slabs.clear();
   pages_used = 0;
 }
 
@@ -262,6 +325,12 @@ IvfIndex::IvfIndex(int d_, int nlist_, int device_) : d(d_), nlist(nlist_), devi
   pt_off.alloc_exact(nlist + 1);
   ws_counters.alloc_exact(2);
   ws_stats.alloc_exact(2);
+  ws_counters2.alloc_exact(2);
+  ws_stats2.alloc_exact(2);
+  ws_maxima.alloc_exact(2);
+  ws_nflag.alloc_exact(1);
+  ABSB_CUDA(cudaMemsetAsync(ws_maxima.p, 0, 2 * sizeof(float), own_stream));
+  ABSB_CUDA(cudaMemsetAsync(ws_nflag.p, 0, sizeof(int), own_stream));
   ABSB_CUDA(cudaMemsetAsync(list_size.p, 0, sizeof(long long) * nlist, own_stream));
   ABSB_CUDA(cudaMemsetAsync(pt_off.p, 0, sizeof(long long) * (nlist + 1), own_stream));
   ABSB_CUDA(cudaStreamSynchronize(own_stream));
@@ -321,6 +390,7 @@ ListTable IvfIndex::table() const {
   lt.pt_pages = pt_pages.p;
   lt.code_slabs = pool.d_code_slabs.p;
   lt.id_slabs = pool.d_id_slabs.p;
+  lt.half_slabs = pool.shadow ? pool.d_half_slabs.p : nullptr;
   return lt;
 }
 
@@ -332,6 +402,7 @@ void IvfIndex::reset() {
   pt_total_pages = 0;
   ABSB_CUDA(cudaMemset(list_size.p, 0, sizeof(long long) * nlist));
   ABSB_CUDA(cudaMemset(pt_off.p, 0, sizeof(long long) * (nlist + 1)));
+  ABSB_CUDA(cudaMemset(ws_maxima.p, 0, 2 * sizeof(float)));
   h_list_size.assign(nlist, 0);
   h_pages_prefix_desc.clear();
   ntotal = 0;
@@ -487,7 +558,8 @@ void IvfIndex::add_core_dev(int64_t n, const float* x, const long long* ids,
   if (n_kept > 0) {
     scatter_rows_kernel<<<grid_for(n_kept * 32, 256, sms), 256, 0, st>>>(
         n_kept, d / 4, P, pool.slab_shift, keys_sorted.p, perm.p, call_off.p, list_size.p, new_off.p,
-        new_pages.p, pool.d_code_slabs.p, pool.d_id_slabs.p, x, ids, rows_seen);
+        new_pages.p, pool.d_code_slabs.p, pool.d_id_slabs.p, x, ids, rows_seen,
+        pool.shadow ? pool.d_half_slabs.p : nullptr, ws_maxima.p);
     ABSB_CUDA(cudaGetLastError());
   }
   ABSB_CUDA(cudaMemcpyAsync(list_size.p, new_size.p, sizeof(long long) * nlist, cudaMemcpyDeviceToDevice, st));
@@ -528,6 +600,27 @@ void IvfIndex::get_list(int64_t l, float* codes, long long* ids) {
   if (codes) ABSB_CUDA(cudaMemcpyAsync(codes, dc.p, sizeof(float) * (size_t)size * d, cudaMemcpyDeviceToHost, st));
   if (ids) ABSB_CUDA(cudaMemcpyAsync(ids, di.p, sizeof(long long) * (size_t)size, cudaMemcpyDeviceToHost, st));
   ABSB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---------------------------------------------------------------- two-stage scan -----------
+void IvfIndex::set_two_stage(int shortlist) {
+  ABSB_CHECK(shortlist == 0 || shortlist == 32 || shortlist == 64 || shortlist == 128, ABSB_ERR_INVALID,
+             "shortlist length %d (0 = off, 32, 64 or 128)", shortlist);
+  if (shortlist > 0 && !pool.shadow) {
+    ABSB_CHECK(d == 1024, ABSB_ERR_UNSUPPORTED, "the two-stage scan is built for d = 1024 (d=%d)", d);
+    ABSB_CHECK(ntotal == 0 && pool.pages_used == 0, ABSB_ERR_STATE,
+               "enable the two-stage scan before the first add(): the fp16 shadow codes are written by add()");
+    pool.shadow = true;
+  }
+  two_stage_k = shortlist;  // 0 keeps the shadow codes (if any) and returns to the single-pass scan
+}
+
+int64_t IvfIndex::two_stage_fallbacks(cudaStream_t st) {
+  int h = 0;
+  ABSB_CUDA(cudaMemcpyAsync(&h, ws_nflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ABSB_CUDA(cudaMemsetAsync(ws_nflag.p, 0, sizeof(int), st));
+  ABSB_CUDA(cudaStreamSynchronize(st));
+  return h;
 }
 
 // ---------------------------------------------------------------- compact ------------------
@@ -593,7 +686,7 @@ void IvfIndex::compact(int64_t scratch_pages, cudaStream_t st) {
   ABSB_CUDA(cudaMemcpyAsync(src.data(), pt_pages.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
   ABSB_CUDA(cudaStreamSynchronize(st));
   const int P = pool.page_vecs;
-  const size_t page_bytes = (size_t)P * d * sizeof(float) + (size_t)P * sizeof(long long);
+  const size_t page_bytes = (size_t)P * d * (pool.shadow ? 6 : 4) + (size_t)P * sizeof(long long);
   if (scratch_pages <= 0) {
     size_t free_b = 0, total_b = 0;
     ABSB_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -607,8 +700,10 @@ void IvfIndex::compact(int64_t scratch_pages, cudaStream_t st) {
     DBuf<float> sc_codes;
     DBuf<long long> sc_ids;
     DBuf<PageMove> d_moves;
+    DBuf<unsigned short> sc_half;
     sc_codes.alloc_exact((size_t)scratch_pages * P * d);
     sc_ids.alloc_exact((size_t)scratch_pages * P);
+    if (pool.shadow) sc_half.alloc_exact((size_t)scratch_pages * P * d);
     d_moves.alloc_exact(moves.size());
     ABSB_CUDA(cudaMemcpyAsync(d_moves.p, moves.data(), sizeof(PageMove) * moves.size(), cudaMemcpyHostToDevice, st));
     int64_t begin = 0;
@@ -617,7 +712,8 @@ void IvfIndex::compact(int64_t scratch_pages, cudaStream_t st) {
       if (cnt > 0) {
         const int grid = (int)std::min<int64_t>(cnt, (int64_t)props.sm_count * 8);
         move_pages_kernel<<<grid, 256, 0, st>>>(cnt, d_moves.p + begin, P, d / 4, pool.slab_shift, pool.d_code_slabs.p,
-                                                pool.d_id_slabs.p, sc_codes.p, sc_ids.p);
+                                                pool.d_id_slabs.p, sc_codes.p, sc_ids.p,
+                                                pool.shadow ? pool.d_half_slabs.p : nullptr, sc_half.p);
         ABSB_CUDA(cudaGetLastError());
       }
       begin = end;
@@ -857,14 +953,15 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
   if (nq == 0) return;
   const int64_t per_q = std::max<int64_t>(1, items_bound_per_query(nprobe));
   // bound the partial-result buffers to ~1 GiB per launch
-  int64_t nb_max = std::min<int64_t>(kMaxPlanQueries, std::max<int64_t>(1, ((int64_t)1 << 30) / (per_q * k * 12)));
+  const int k_part = std::max(k, two_stage_k);  // entries per work item in the partial-result buffers
+  int64_t nb_max = std::min<int64_t>(kMaxPlanQueries, std::max<int64_t>(1, ((int64_t)1 << 30) / (per_q * k_part * 12)));
   for (int64_t q0 = 0; q0 < nq; q0 += nb_max) {
     const int nb = (int)std::min(nb_max, nq - q0);
     const int64_t max_items = per_q * nb;
     ABSB_CHECK(max_items < ((int64_t)1 << 31), ABSB_ERR_UNSUPPORTED, "too many scan items");
     ws_items.reserve((size_t)max_items);
-    ws_part_s.reserve((size_t)max_items * k);
-    ws_part_id.reserve((size_t)max_items * k);
+    ws_part_s.reserve((size_t)max_items * k_part);
+    ws_part_id.reserve((size_t)max_items * k_part);
     ws_q_begin.reserve(kMaxPlanQueries + 1);
     if (stats_pending) fold_stats();  // only one plan's numbers fit in ws_stats
     {
@@ -897,6 +994,80 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
     a.part_id = ws_part_id.p;
     a.sm_count = props.sm_count;
     a.ctas_per_sm = scan_ctas_per_sm;
+    const bool two_stage = two_stage_k >= k && pool.shadow && d == 1024 && push == nullptr;
+    if (two_stage) {
+      // ---- stage 1: fp16 shadow codes -> shortlist of K approximate candidates per query (ivf_scan16.cu)
+      const int K = two_stage_k;
+      ws_short_s.reserve((size_t)kMaxPlanQueries * K);
+      ws_short_g.reserve((size_t)kMaxPlanQueries * K);
+      ws_items2.reserve((size_t)kMaxPlanQueries * K);
+      ws_part2_s.reserve((size_t)kMaxPlanQueries * K * k);
+      ws_part2_id.reserve((size_t)kMaxPlanQueries * K * k);
+      ws_q_begin2.reserve(kMaxPlanQueries + 1);
+      ws_flags.reserve(kMaxPlanQueries);
+      Scan16Launch s16;
+      s16.Q = a.Q;
+      s16.K = K;
+      s16.items = ws_items.p;
+      s16.n_items = ws_counters.p;
+      s16.queue_counter = ws_counters.p + 1;
+      s16.order = a.order;
+      s16.part_s = ws_part_s.p;
+      s16.part_g = ws_part_id.p;
+      s16.half_slabs = pool.d_half_slabs.p;
+      s16.slab_shift = pool.slab_shift;
+      s16.page_vecs = pool.page_vecs;
+      s16.sm_count = props.sm_count;
+      s16.ctas_per_sm = scan_ctas_per_sm;
+      {
+        Span sp(this, st, 0);
+        launch_scan16(s16, st);
+      }
+      {
+        Span sp(this, st, 2);
+        merge_partials(nb, K, ws_q_begin.p, ws_part_s.p, ws_part_id.p, ws_short_s.p, ws_short_g.p, st);
+        launch_rescore_items(table(), nb, K, ws_short_g.p, ws_items2.p, ws_q_begin2.p, ws_counters2.p,
+                             ws_counters2.p + 1, st);
+      }
+      // ---- stage 2: exact fp32 scores of the shortlist with the single-pass kernel
+      ScanLaunch a2 = a;
+      a2.items = ws_items2.p;
+      a2.n_items = ws_counters2.p;
+      a2.queue_counter = ws_counters2.p + 1;
+      a2.order = nullptr;
+      a2.part_s = ws_part2_s.p;
+      a2.part_id = ws_part2_id.p;
+      {
+        Span sp(this, st, 0);
+        launch_scan(a2, st);
+      }
+      {
+        Span sp(this, st, 2);
+        merge_partials(nb, k, ws_q_begin2.p, ws_part2_s.p, ws_part2_id.p, D + q0 * k, I + q0 * k, st);
+        launch_two_stage_check(nb, d, k, K, a.Q, D + q0 * k, I + q0 * k, ws_short_s.p, ws_short_g.p, ws_maxima.p,
+                               ws_flags.p, ws_nflag.p, st);
+        // ---- fallback: the queries the bound could not prove go through the single-pass scan (the plan
+        // emits no work for the others, so this costs a few empty launches when everything was proven)
+        launch_plan(table(), coarse + q0 * nprobe, nb, nprobe, scan_chunk, (int)max_items, ws_items.p, ws_q_begin.p,
+                    ws_counters.p, ws_counters.p + 1, ws_stats2.p, ws_pair_counts.p, ws_pair_offs.p, ws_plan_tmp.p,
+                    ws_plan_tmp.cap, nullptr, st, ws_flags.p);
+      }
+      ScanLaunch a3 = a;
+      a3.order = nullptr;
+      {
+        Span sp(this, st, 0);
+        launch_scan(a3, st);
+      }
+      {
+        Span sp(this, st, 2);
+        merge_partials(nb, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, D + q0 * k, I + q0 * k, st, ws_flags.p);
+      }
+      have_last_scan = false;
+      stats_pending = true;
+      stats.launches += (scan_order == 1 ? 11 : 5) + 12;
+      if (q0 + nb_max < nq) fold_stats();
+      continue;
+    }
     {
       Span sp(this, st, 0);
       launch_scan(a, st);

@@ -20,8 +20,11 @@ struct PagePool {
   int64_t pages_used = 0;
   std::vector<float*> code_slabs;
   std::vector<long long*> id_slabs;
+  std::vector<unsigned short*> half_slabs;  // fp16 shadow codes (two-stage scan), same page numbering
   DBuf<float*> d_code_slabs;
   DBuf<long long*> d_id_slabs;
+  DBuf<unsigned short*> d_half_slabs;
+  bool shadow = false;  // keep fp16 shadow codes for pages allocated from now on
   size_t table_cap = 0;
 
   void configure(int d_, int page_vecs_);
@@ -78,6 +81,7 @@ struct IvfIndex {
   int scan_chunk = 128;
   int coarse_impl = 1;  // 1 = tcgen05 split-bf16 (falls back to the FFMA GEMM for shapes it cannot take)
   int scan_ctas_per_sm = 0;
+  int two_stage_k = 0;  // shortlist length of the two-stage scan (0 = single-pass fp32 scan)
   int scan_order = 1;  // 1 = list-major work queue (probes of one list scanned together: L2 reuse), 0 = query-major
 
   // workspaces (single stream at a time)
@@ -92,6 +96,15 @@ struct IvfIndex {
   DBuf<unsigned char> ws_plan_tmp;
   DBuf<unsigned> ws_okeys, ws_okeys_sorted;  // list-major queue order (scan_order = 1)
   DBuf<int> ws_ovals, ws_ovals_sorted, ws_ocounts, ws_oqoffs, ws_order;
+  // two-stage scan (ivf_scan16.cu)
+  DBuf<float> ws_maxima;  // [0] max |x - fp16(x)|, [1] max |x| over everything added
+  DBuf<float> ws_short_s, ws_part2_s;
+  DBuf<long long> ws_short_g, ws_part2_id;
+  DBuf<ScanItem> ws_items2;
+  DBuf<int> ws_q_begin2, ws_counters2;
+  DBuf<unsigned char> ws_flags;
+  DBuf<int> ws_nflag;  // queries sent to the single-pass fallback since the last reset of the counter
+  DBuf<unsigned long long> ws_stats2;
   DBuf<int> ws_counters;  // [0] n_items, [1] queue counter
   DBuf<unsigned long long> ws_stats;
   DBuf<unsigned char> ws_cub;
@@ -160,6 +173,8 @@ struct IvfIndex {
   // Physically reorders the pages so that every list's pages are consecutive (in place, through a
   // bounded scratch of `scratch_pages` pages; <= 0 picks a size from the free memory).
   void compact(int64_t scratch_pages, cudaStream_t st);
+  void set_two_stage(int shortlist);
+  int64_t two_stage_fallbacks(cudaStream_t st);
   int64_t items_bound_per_query(int nprobe) const;
   void refresh_host_sizes(cudaStream_t st);
 };

@@ -52,6 +52,7 @@ __device__ __forceinline__ int walk_list(const ListTable& lt, long long l, int c
       it.ids = lt.id_slabs[slab] + (size_t)in_slab * P;
       it.len = (int)run_len;
       it.q = q;
+      it.pad = run_first * P;
       out[n] = it;
     }
     ++n;
@@ -79,12 +80,14 @@ __global__ void plan_count_kernel(ListTable lt, const long long* __restrict__ co
                                   int* __restrict__ counts /* [npairs + 1] */,
                                   unsigned* __restrict__ keys /* [npairs] list number, or nullptr */,
                                   int* __restrict__ vals /* [npairs] pair index */,
-                                  unsigned long long* __restrict__ stats) {
+                                  unsigned long long* __restrict__ stats, int nprobe,
+                                  const unsigned char* __restrict__ active) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   long long vec = 0;
   if (i < npairs) {
     const long long l = coarse[i];
-    counts[i] = walk_list(lt, l, chunk, 0, nullptr, &vec);
+    const bool on = active == nullptr || active[i / nprobe] != 0;
+    counts[i] = on ? walk_list(lt, l, chunk, 0, nullptr, &vec) : 0;
     if (keys) {
       keys[i] = (l >= 0 && l < lt.nlist) ? (unsigned)l : (unsigned)lt.nlist;
       vals[i] = i;
@@ -280,14 +283,14 @@ __global__ void plan_order_kernel(int npairs, int max_items, const int* __restri
 void launch_plan(const ListTable& lt, const long long* coarse, int nq, int nprobe, int chunk,
                  int max_items, ScanItem* items, int* q_begin, int* n_items, int* queue_counter,
                  unsigned long long* stats, int* pair_counts, int* pair_offs, void* scan_tmp,
-                 size_t scan_tmp_bytes, const PlanOrderWs* ow, cudaStream_t st) {
+                 size_t scan_tmp_bytes, const PlanOrderWs* ow, cudaStream_t st, const unsigned char* active) {
   ABSB_CHECK(nq >= 1 && nq <= kMaxPlanQueries, ABSB_ERR_INVALID, "plan: nq=%d", nq);
   const int npairs = nq * nprobe;
   ABSB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), st));
   const int threads = 256;
   const int pair_blocks = (npairs + 1 + threads - 1) / threads;
   plan_count_kernel<<<pair_blocks, threads, 0, st>>>(lt, coarse, npairs, chunk, pair_counts, ow ? ow->keys : nullptr,
-                                                     ow ? ow->vals : nullptr, stats);
+                                                     ow ? ow->vals : nullptr, stats, nprobe, active);
   ABSB_CUDA(cudaGetLastError());
   ABSB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_tmp_bytes, pair_counts, pair_offs, npairs + 1, st));
   if (ow) {

@@ -16,7 +16,7 @@ struct __align__(16) ScanItem {
   const long long* ids;  // [len]
   int len;
   int q;
-  long long pad;
+  long long pad;  // global slot number (page * page_vecs) of the first vector: locates the fp16 shadow codes
 };
 static_assert(sizeof(ScanItem) == 32, "ScanItem must be 32 bytes");
 
@@ -34,6 +34,7 @@ struct ListTable {
   const int* pt_pages;         // [pt_off[nlist]]
   float* const* code_slabs;    // device array of slab base pointers
   long long* const* id_slabs;
+  unsigned short* const* half_slabs;  // fp16 shadow codes of the two-stage scan (nullptr = none)
 };
 
 struct ScanLaunch {
@@ -55,20 +56,46 @@ struct PlanOrderWs {
   unsigned *keys, *keys_sorted;
   int *vals, *vals_sorted, *counts_sorted, *qoffs, *order;
 };
+// active (optional, [nq] bytes): queries with active[q] == 0 get no work items.
 void launch_plan(const ListTable& lt, const long long* coarse, int nq, int nprobe, int chunk,
                  int max_items, ScanItem* items, int* q_begin, int* n_items, int* queue_counter,
                  unsigned long long* stats, int* pair_counts, int* pair_offs, void* scan_tmp,
-                 size_t scan_tmp_bytes, const PlanOrderWs* order_ws, cudaStream_t st);
+                 size_t scan_tmp_bytes, const PlanOrderWs* order_ws, cudaStream_t st,
+                 const unsigned char* active = nullptr);
 size_t plan_scan_tmp_bytes(int max_pairs);
 void launch_scan(const ScanLaunch& a, cudaStream_t st);
+
+// ---- two-stage scan (ivf_scan16.cu): fp16 shortlist pass + exact fp32 re-score, d = 1024 ----
+struct Scan16Launch {
+  const float* Q;  // [nq, 1024]
+  int K;           // shortlist length per item and per query (32, 64 or 128)
+  const ScanItem* items;
+  const int* n_items;
+  int* queue_counter;
+  const int* order;
+  float* part_s;      // [max_items, K] approximate scores
+  long long* part_g;  // [max_items, K] global slot numbers
+  const unsigned short* const* half_slabs;
+  int slab_shift, page_vecs;
+  int sm_count, ctas_per_sm;
+};
+void launch_scan16(const Scan16Launch& a, cudaStream_t st);
+// shortlist G [nq, K] (global slot numbers, -1 = none) -> one single-vector fp32 work item each
+void launch_rescore_items(const ListTable& lt, int nq, int K, const long long* G, ScanItem* items, int* q_begin,
+                          int* n_items, int* queue_counter, cudaStream_t st);
+// flags[q] = 1 where the error bound cannot prove that the shortlist holds the exact top-k
+void launch_two_stage_check(int nq, int d, int k, int K, const float* Q, const float* D, const long long* I,
+                            const float* Dp, const long long* G, const float* maxima, unsigned char* flags,
+                            int* n_flagged, cudaStream_t st);
 
 // dense.cu
 void gemm_nt_f32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                  int ldc, cudaStream_t st);
 void select_rows(const float* S, int64_t ld, int64_t nrows, int ncols, long long id_offset, int k,
                  float* out_s, long long* out_id, int64_t out_ld, bool finalize, cudaStream_t st);
+// active (optional, [nq] bytes): rows of queries with active[q] == 0 are left untouched.
 void merge_partials(int nq, int k, const int* q_begin, const float* part_s, const long long* part_id,
-                    float* D, long long* I, cudaStream_t st);
+                    float* D, long long* I, cudaStream_t st, const unsigned char* active = nullptr);
 void merge_shards(int world, int64_t nq, int k, const float* D_all, const long long* I_all,
                   int64_t d_stride_bytes, int64_t i_stride_bytes, float* D, long long* I, cudaStream_t st);
 

@@ -42,6 +42,7 @@ struct PeerExchange {
   DBuf<unsigned long long*> d_flag_ptrs;  // [world]
   DBuf<unsigned> done_counter;
   DBuf<int> status;                    // 0 ok, 1 = a wait timed out
+  DBuf<char> staging;                  // packed {I, D} record of absb_peer_push_results_dev
   unsigned long long epoch = 0;        // last epoch pushed
   int64_t rec_n = 0;                   // shape of the last pushed search record
   int rec_k = 0;

@@ -242,6 +242,18 @@ class IndexIVFFlat:
     def set_tunables(self, scan_chunk: int = -1, coarse_impl: int = -1, scan_ctas_per_sm: int = -1):
         check(lib().absb_ivf_set_tunables(self._h, scan_chunk, coarse_impl, scan_ctas_per_sm))
 
+    def set_two_stage(self, shortlist: int = 64):
+        """Two-stage fine scan: fp16 shadow codes (+50% memory, written by add()) give a shortlist, the
+        fp32 codes its exact scores; queries the error bound cannot prove fall back to the single-pass
+        scan, so results are identical.  Enable before the first add(); 0 switches it off."""
+        check(lib().absb_ivf_set_two_stage(self._h, int(shortlist)))
+        self.two_stage = int(shortlist)
+
+    def two_stage_fallbacks(self) -> int:
+        n = c_int64()
+        check(lib().absb_ivf_two_stage_fallbacks(self._h, byref(n)))
+        return n.value
+
     def set_scan_order(self, list_major: bool = True):
         """Work-queue order of the fine scan: list-major (default, L2 reuse across queries) or query-major."""
         check(lib().absb_ivf_set_scan_order(self._h, 1 if list_major else 0))

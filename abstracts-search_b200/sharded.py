@@ -267,7 +267,12 @@ class ShardedIndexIVFFlat:
             raise ValueError(f"{n} x {k} results exceed the exchange slot ({px.slot_bytes} bytes); call use_peer_exchange(max_results=...)")
         with torch.cuda.device(x.device):
             st = current_stream_ptr()
-            check(lib().absb_ivf_search_push_dev(self.local._h, px._h, n, ptr(x), k, self.nprobe, st))
+            if getattr(self.local, "two_stage", 0) >= k:
+                # the two-stage scan ends in a local (D, I) (its fallback may rewrite rows): push that
+                Dl, Il = self.local.search(x, k)
+                check(lib().absb_peer_push_results_dev(px._h, n, k, ptr(Dl), ptr(Il), st))
+            else:
+                check(lib().absb_ivf_search_push_dev(self.local._h, px._h, n, ptr(x), k, self.nprobe, st))
             Dm = torch.empty((n, k), dtype=torch.float32, device=x.device)
             Im = torch.empty((n, k), dtype=torch.int64, device=x.device)
             check(lib().absb_peer_merge_shards_dev(px._h, n, k, ptr(Dm), ptr(Im), st))

@@ -191,6 +191,15 @@ int absb_merge_shards_dev(int device, int world, int64_t n, int k, const float* 
                           const int64_t* I_all_dev, int64_t rank_stride_bytes, float* D_dev,
                           int64_t* I_dev, void* stream);
 
+/* Two-stage fine scan (d = 1024): keep an fp16 shadow copy of the list codes (+50% memory) and
+ * answer Index.search from half the HBM traffic — a shortlist of `shortlist` (32, 64 or 128, >= k)
+ * candidates per query from the fp16 codes, exact fp32 re-score of the shortlist, and a per-query
+ * error-bound check that sends every query it cannot prove through the single-pass fp32 scan.
+ * Results (ids and scores) are identical to the single-pass scan.  Must be enabled before the first
+ * add(); shortlist = 0 returns to the single-pass scan.  absb_ivf_two_stage_fallbacks returns (and
+ * clears) the number of queries that took the fallback; it synchronises. */
+int absb_ivf_set_two_stage(absb_ivf_t h, int shortlist);
+int absb_ivf_two_stage_fallbacks(absb_ivf_t h, int64_t* queries);
 /* Tunables (chunk = vectors per scan work item; coarse_impl 0 = fp32 SIMT, 1 = tcgen05
  * split-bf16). Values < 0 leave a setting unchanged. */
 int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int scan_ctas_per_sm);
@@ -317,6 +326,10 @@ int absb_peer_status(absb_peer_t p, int* status);
  * separate copy or collective).  Record = I [n,k] i64 then D [n,k] f32 (16-byte aligned). */
 int absb_ivf_search_push_dev(absb_ivf_t h, absb_peer_t p, int64_t n, const float* q_dev, int k,
                              int nprobe, void* stream);
+/* Same exchange for a result that already sits in local (D, I) [n,k] (e.g. from the two-stage scan):
+ * packs the record and pushes it to every rank; absb_peer_merge_shards_dev consumes it. */
+int absb_peer_push_results_dev(absb_peer_t p, int64_t n, int k, const float* D_dev, const int64_t* I_dev,
+                               void* stream);
 /* The consuming half: waits (inside the kernel) for every rank's record of the last
  * absb_ivf_search_push_dev and merges world x k candidates per query with the single-index order
  * (score desc, id asc) -> D_dev [n,k], I_dev [n,k] on this rank. */

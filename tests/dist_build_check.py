@@ -79,8 +79,22 @@ def main():
         got = px.allgather(emb + it)
         want = torch.stack([torch.full_like(emb, float(r + 1 + it)) for r in range(world)])
         assert torch.equal(got, want), f"rank {rank}: peer all-gather"
+    # two-stage shards (fp16 shortlist + exact re-score) behind both exchanges: same result
+    loc2 = P.IndexIVFFlat(d, nlist, device=torch.cuda.current_device())
+    loc2.set_two_stage(32)
+    loc2.set_shard(rank, world)
+    loc2.set_centroids(ref_cent)
+    loc2.add(x[order])
+    sh2 = P.ShardedIndexIVFFlat(loc2)
+    sh2.nprobe = nprobe
+    D2, I2 = sh2.search(qd, k)
+    assert np.array_equal(I2.cpu().numpy(), Ir) and np.array_equal(D2.cpu().numpy(), Dr), f"rank {rank}: two-stage + nccl"
+    sh2.use_peer_exchange(max_results=nq * k)
+    for _ in range(3):
+        D2, I2 = sh2.search(qd, k)
+        assert np.array_equal(I2.cpu().numpy(), Ir) and np.array_equal(D2.cpu().numpy(), Dr), f"rank {rank}: two-stage + peer"
     torch.cuda.synchronize()
-    assert sh._px.status() == 0 and px.status() == 0
+    assert sh._px.status() == 0 and px.status() == 0 and sh2._px.status() == 0
     dist.barrier()
     if rank == 0:
         print(f"dist_build_check ok: world={world}, k-means matches, lists and search bit-exact, NVLink peer exchange bit-exact")

@@ -359,6 +359,96 @@ def test_scan_occupancy_cap_changes_no_result(gpu_pkg, lattice, ctas):
     assert np.array_equal(I, g["I"]) and np.array_equal(D, g["D"])
 
 
+# ------------------------------------------------------------------ two-stage scan -------------
+@pytest.mark.parametrize("shortlist", [32, 64, 128])
+def test_two_stage_scan_matches_golden_lattice(gpu_pkg, lattice, shortlist):
+    """fp16 shortlist + exact fp32 re-score + bound check/fallback (ivf_scan16.cu): ids and scores are
+    bit-identical to the single-pass scan's golden result, before and after compaction, and for a k
+    larger than the shortlist (which silently takes the single-pass scan)."""
+    g, x, q, c = lattice
+    d, nlist, nprobe, k = int(g["d"]), int(g["nlist"]), int(g["nprobe"]), int(g["k"])
+    ix = gpu_pkg.IndexIVFFlat(d, nlist)
+    ix.set_two_stage(shortlist)
+    ix.set_centroids(c)
+    ix.add(x[:3000])
+    ix.add(x[3000:])
+    ix.nprobe = nprobe
+    D, I = ix.search(q, k)
+    assert np.array_equal(I, g["I"]) and np.array_equal(D, g["D"])
+    assert 0 <= ix.two_stage_fallbacks() <= q.shape[0]
+    ix.compact()
+    D, I = ix.search(q, k)
+    assert np.array_equal(I, g["I"]) and np.array_equal(D, g["D"])
+    ref = gpu_pkg.IndexIVFFlat(d, nlist)
+    ref.set_centroids(c)
+    ref.add(x)
+    ref.nprobe = nprobe
+    for kk in (1, shortlist, shortlist + 8):
+        Dr, Ir = ref.search(q, kk)
+        D2, I2 = ix.search(q, kk)
+        assert np.array_equal(I2, Ir) and np.array_equal(D2, Dr), kk
+    ix.set_two_stage(0)
+    D, I = ix.search(q, k)
+    assert np.array_equal(I, g["I"]) and np.array_equal(D, g["D"])
+    with pytest.raises(gpu_pkg.AbsbError):
+        ref.set_two_stage(64)  # the shadow codes are written by add(): too late now
+    with pytest.raises(gpu_pkg.AbsbError):
+        ix.set_two_stage(48)
+
+
+def test_two_stage_scan_on_gaussian_rows_equals_single_pass_bit_for_bit(gpu_pkg):
+    """Unit-norm gaussian rows are NOT exactly representable in fp16: the shortlist is approximate, the
+    re-score uses the single-pass kernel on the fp32 codes, the bound decides per query.  Every query
+    must come out identical (ids and score bits) to an index without the shadow codes."""
+    rng = np.random.default_rng(5)
+    d, nlist, n, nq, k, nprobe = 1024, 32, 30000, 200, 10, 6
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    c = x[rng.choice(n, nlist, replace=False)].copy()
+    q = x[rng.choice(n, nq, replace=False)] + 0.05 * rng.standard_normal((nq, d)).astype(np.float32)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    res = {}
+    for mode in (0, 32, 128):
+        ix = gpu_pkg.IndexIVFFlat(d, nlist)
+        if mode:
+            ix.set_two_stage(mode)
+        ix.set_centroids(c)
+        for a in range(0, n, 7000):
+            ix.add(x[a:a + 7000])
+        ix.nprobe = nprobe
+        res[mode] = ix.search(q, k)
+        if mode:
+            fb = ix.two_stage_fallbacks()
+            assert fb < nq, f"shortlist {mode}: every query fell back ({fb})"
+    for mode in (32, 128):
+        assert np.array_equal(res[mode][1], res[0][1]) and np.array_equal(res[mode][0], res[0][0]), mode
+
+
+def test_two_stage_scan_falls_back_when_ties_defeat_the_bound(gpu_pkg):
+    """40 distinct rows, each stored 100 times: rank 10 and rank 32 have the SAME score, so the bound
+    can never separate the shortlist from the rest; those queries must take the single-pass fallback
+    and still return the smallest ids among the ties."""
+    rng = np.random.default_rng(9)
+    d, nlist, k = 1024, 8, 10
+    base = rng.standard_normal((40, d)).astype(np.float32)
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    x = np.repeat(base, 100, axis=0)[rng.permutation(4000)]
+    c = base[:nlist].copy()
+    q = base[:16].copy()
+    ref = gpu_pkg.IndexIVFFlat(d, nlist)
+    two = gpu_pkg.IndexIVFFlat(d, nlist)
+    two.set_two_stage(32)
+    for ix in (ref, two):
+        ix.set_centroids(c)
+        ix.add(x)
+        ix.nprobe = nlist
+    Dr, Ir = ref.search(q, k)
+    D2, I2 = two.search(q, k)
+    assert two.two_stage_fallbacks() == 16
+    assert np.array_equal(I2, Ir) and np.array_equal(D2, Dr)
+    assert (np.diff(Ir, axis=1) > 0).all(), "ties must come out in ascending id order"
+
+
 def test_peer_exchange_allgather_emulated_ranks(gpu_pkg):
     """csrc/peer.cuh protocol with 4 ranks emulated on one GPU (buffers wired by raw pointer): every
     rank pushes into every buffer, then every rank waits and reads its own ring entry.  Five epochs
@@ -413,6 +503,41 @@ def test_sharded_search_through_peer_exchange_equals_single_index(gpu_pkg, latti
     # a record that does not fit the slot is refused, not truncated
     small = P.PeerExchange.emulate(0, 1, 64)[0]
     assert L.absb_ivf_search_push_dev(parts[0]._h, small._h, nq, ctypes.c_void_p(qd.data_ptr()), k, nprobe, None) != 0
+
+
+def test_two_stage_results_through_peer_exchange_equal_single_index(gpu_pkg, lattice):
+    """Two-stage shards end in a local (D, I); absb_peer_push_results_dev packs and pushes that record,
+    the in-kernel wait + merge consumes it.  Two ranks emulated on one GPU; bit-exact to the golden."""
+    P = gpu_pkg
+    t = _torch()
+    g, x, q, c = lattice
+    d, nlist, nprobe, k = int(g["d"]), int(g["nlist"]), int(g["nprobe"]), int(g["k"])
+    nq, world = q.shape[0], 2
+    parts = []
+    for r in range(world):
+        ix = P.IndexIVFFlat(d, nlist)
+        ix.set_two_stage(32)
+        ix.set_shard(r, world)
+        ix.set_centroids(c)
+        ix.add(x)
+        ix.nprobe = nprobe
+        parts.append(ix)
+    pxs = P.PeerExchange.emulate(0, world, nq * k * 12 + 32)
+    L = P.lib()
+    qd = t.from_numpy(q).cuda()
+    for _ in range(3):
+        for r in range(world):
+            Dl, Il = parts[r].search(qd, k)
+            assert L.absb_peer_push_results_dev(pxs[r]._h, nq, k, ctypes.c_void_p(Dl.data_ptr()),
+                                                ctypes.c_void_p(Il.data_ptr()), None) == 0
+        for r in range(world):
+            Dm = t.empty((nq, k), dtype=t.float32, device="cuda")
+            Im = t.empty((nq, k), dtype=t.int64, device="cuda")
+            assert L.absb_peer_merge_shards_dev(pxs[r]._h, nq, k, ctypes.c_void_p(Dm.data_ptr()),
+                                                ctypes.c_void_p(Im.data_ptr()), None) == 0
+            t.cuda.synchronize()
+            assert np.array_equal(Im.cpu().numpy(), g["I"]) and np.array_equal(Dm.cpu().numpy(), g["D"])
+    assert all(p.status() == 0 for p in pxs)
 
 
 # ------------------------------------------------------------------ larger, property-based -----
