@@ -43,14 +43,19 @@ def read_launches(path):
 
 def launches(src, dst, steps=2):
     rows = read_launches(src)
-    # a bench step runs from the encoder's embed_kernel to the search's merge_partials kernel
-    ends = [i for i, (n, _) in enumerate(rows) if "merge_partials" in n]
-    begins = [i for i, (n, _) in enumerate(rows) if "embed_kernel" in n]
-    assert len(ends) >= steps, f"need {steps} search steps in the log, found {len(ends)}"
+    # a bench step runs from the encoder's embed_kernel to the LAST merge_partials kernel before the next
+    # embed_kernel (the two-stage scan merges three times per step); spans without a scan kernel (the
+    # extra encode the bench does after its warm-up) are not steps
+    begins = [i for i, (n, _) in enumerate(rows) if "embed_kernel" in n] + [len(rows)]
+    spans = []
+    for b, nb in zip(begins[:-1], begins[1:]):
+        merges = [i for i in range(b, nb) if "merge_partials" in rows[i][0]]
+        if merges and any("ivf_scan" in rows[i][0] for i in range(b, nb)):
+            spans.append((b, merges[-1] + 1))
+    assert len(spans) >= steps, f"need {steps} search steps in the log, found {len(spans)}"
     sel = []
-    for e in ends[-steps:]:
-        b = max(i for i in begins if i < e)
-        sel += rows[b: e + 1]
+    for b, e in spans[-steps:]:
+        sel += rows[b:e]
     agg = collections.OrderedDict()
     for n, v in sel:
         a = agg.setdefault(short(n), [0, 0.0])
