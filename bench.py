@@ -323,7 +323,31 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if args.gemm_variant:
         importlib.import_module("abstracts-search_b200.encoder").gemm_set_variant(args.gemm_variant)
     enc = P.Encoder(config=P.STELLA_1_5B, device=device, random_init_seed=0)
-    ix, build_s = build_shard(P, torch, args, rank, world, dev)
+    # The fp16 shadow codes of the two-stage scan take +50% index memory (159 GB of 180 GB for the
+    # 25.9M-row shard).  If any rank cannot allocate them, every rank rebuilds its shard without them
+    # and the step uses the single-pass scan: same results, config.two_stage_shortlist says which ran.
+    ix, build_s, err = None, 0.0, None
+    try:
+        ix, build_s = build_shard(P, torch, args, rank, world, dev)
+    except (MemoryError, RuntimeError) as e:
+        if not args.two_stage:
+            raise
+        err = repr(e)
+    if args.two_stage:
+        failed = [err]
+        if world > 1:
+            failed = [None] * world
+            dist.all_gather_object(failed, err)
+        if any(f is not None for f in failed):
+            if rank == 0:
+                print(f"two-stage index build failed ({[f for f in failed if f][0]}); rebuilding single-pass", file=sys.stderr)
+            ix = None
+            import gc
+
+            gc.collect()
+            torch.cuda.empty_cache()
+            args.two_stage = 0
+            ix, build_s = build_shard(P, torch, args, rank, world, dev)
     ix.nprobe = args.nprobe
     sh = P.ShardedIndexIVFFlat(ix) if world > 1 else None
     exchange = "none (single GPU)"
