@@ -59,7 +59,7 @@ __global__ __launch_bounds__(kThreads) void attention_tc_kernel(const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);  // qk_full, v_full, s_done, o_done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int blk = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int group = p.nh / p.nkv;
   const int S = p.S;
