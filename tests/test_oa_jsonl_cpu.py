@@ -134,3 +134,52 @@ def test_cli_carries_partial_lines_across_its_32mb_blocks():
     assert r.returncode == 0 and r.stdout == want
     r1 = subprocess.run([CLI, "1"], input=data[:-1], capture_output=True, timeout=120)  # no final newline, one thread
     assert r1.returncode == 0 and r1.stdout == want
+
+
+# ---------------------------------------------------------------------------------------------
+# property-based: arbitrary well-formed records (json.dumps of random nested values) through the
+# reference program, the restatement and the product
+# ---------------------------------------------------------------------------------------------
+try:
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as hst
+
+    _leaf = hst.one_of(hst.none(), hst.booleans(), hst.integers(-10**9, 10**9),
+                       hst.floats(allow_nan=False, allow_infinity=False, width=64),
+                       hst.text(max_size=12))
+    _json = hst.recursive(_leaf, lambda ch: hst.one_of(hst.lists(ch, max_size=4),
+                                                       hst.dictionaries(hst.text(max_size=6), ch, max_size=4)), max_leaves=12)
+    _words = hst.dictionaries(hst.text(max_size=8), hst.lists(hst.integers(0, 150), max_size=4), max_size=12)
+
+    @hst.composite
+    def _record(draw):
+        members = []
+        for i in range(draw(hst.integers(0, 4))):
+            members.append((draw(hst.text(min_size=1, max_size=6)) + str(i), draw(_json)))
+        if draw(hst.booleans()):
+            members.append(("id", draw(hst.text(max_size=20))))
+        if draw(hst.booleans()):
+            members.append(("title", draw(hst.one_of(hst.none(), hst.text(max_size=30)))))
+        if draw(hst.booleans()):
+            members.append(("language", draw(hst.one_of(hst.none(), hst.sampled_from(["en", "en", "fr", "EN", ""])))))
+        if draw(hst.booleans()):
+            members.append(("abstract_inverted_index", draw(hst.one_of(hst.none(), _words))))
+        members = draw(hst.permutations(members))
+        rec = {}
+        for key, val in members:
+            if key not in rec:
+                rec[key] = val
+        seps = draw(hst.sampled_from([(",", ":"), (", ", ": "), (" ,\t", " :\t")]))
+        return json.dumps(rec, separators=seps, ensure_ascii=draw(hst.booleans()))
+
+    @pytest.mark.skipif(not O.reference_available(), reason="oracle/_ref/oa_jsonl not built (needs /root/reference)")
+    @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(hst.lists(_record(), min_size=1, max_size=12), hst.booleans())
+    def test_random_wellformed_records_match_the_reference_program(records, final_newline):
+        data = ("\\n".join(records) + ("\\n" if final_newline else "")).encode("utf-8")
+        want = O.convert_reference(data)
+        assert OA.convert(data, threads=1) == want
+        assert OA.convert(data, threads=3) == want
+        assert O.convert(data) == want
+except ImportError:  # hypothesis is optional
+    pass
