@@ -86,6 +86,8 @@ _SIGS = {
     "absb_ivf_ntotal": ([_H, _PI64], c_int),
     "absb_ivf_is_trained": ([_H, POINTER(c_int)], c_int),
     "absb_ivf_set_clustering": ([_H, c_int, c_int, c_int, c_int64], c_int),
+    "absb_ivf_set_clustering_spherical": ([_H, c_int], c_int),
+    "absb_renorm_rows_dev": ([c_int, c_int64, c_int, c_void_p, c_void_p], c_int),
     "absb_ivf_train": ([_H, c_int64, c_void_p], c_int),
     "absb_ivf_train_dev": ([_H, c_int64, c_void_p, c_void_p], c_int),
     "absb_ivf_set_centroids": ([_H, c_void_p], c_int),

@@ -287,6 +287,22 @@ int absb_ivf_set_clustering(absb_ivf_t h, int niter, int max_points_per_centroid
   ABSB_API_END
 }
 
+int absb_ivf_set_clustering_spherical(absb_ivf_t h, int spherical) {
+  ABSB_API_BEGIN
+  NEED(h);
+  h->ix.cp.spherical = spherical != 0;
+  ABSB_API_END
+}
+
+int absb_renorm_rows_dev(int device, int64_t n, int d, float* x_dev, void* stream) {
+  ABSB_API_BEGIN
+  ABSB_CHECK(n >= 0 && d > 0 && (n == 0 || x_dev), ABSB_ERR_INVALID, "bad renorm arguments");
+  require_sm100(device);
+  DeviceGuard g(device);
+  renorm_rows(n, d, x_dev, (cudaStream_t)stream);
+  ABSB_API_END
+}
+
 int absb_ivf_train(absb_ivf_t h, int64_t n, const float* x) {
   ABSB_API_BEGIN
   NEED(h);
@@ -602,6 +618,10 @@ int absb_merge_shards_dev(int device, int world, int64_t n, int k, const float* 
   ABSB_API_BEGIN
   ABSB_CHECK(world >= 1 && n >= 0 && k >= 1 && k <= ABSB_MAX_K, ABSB_ERR_INVALID, "bad merge arguments");
   ABSB_CHECK(n == 0 || (D_all_dev && I_all_dev && D_dev && I_dev), ABSB_ERR_INVALID, "null argument");
+  ABSB_CHECK(rank_stride_bytes % 8 == 0 && (reinterpret_cast<uintptr_t>(I_all_dev) & 7) == 0 &&
+                 (reinterpret_cast<uintptr_t>(D_all_dev) & 3) == 0,
+             ABSB_ERR_INVALID, "merge_shards: the int64 ids of every rank must be 8-byte aligned (stride %lld)",
+             (long long)rank_stride_bytes);
   DeviceGuard g(device);
   const int64_t ds = rank_stride_bytes ? rank_stride_bytes : n * k * (int64_t)sizeof(float);
   const int64_t is = rank_stride_bytes ? rank_stride_bytes : n * k * (int64_t)sizeof(long long);
@@ -698,7 +718,7 @@ int absb_peer_status(absb_peer_t p, int* status) {
   NEED(p);
   NEED(status);
   DeviceGuard g(p->px.device);
-  *status = p->px.read_status(nullptr);
+  *status = p->px.read_status();
   ABSB_API_END
 }
 
@@ -753,7 +773,7 @@ int absb_peer_merge_shards_dev(absb_peer_t p, int64_t n, int k, float* D_dev, in
   DeviceGuard g(px.device);
   const size_t i_bytes = ((size_t)n * k * sizeof(long long) + 15) & ~(size_t)15;
   merge_shards_wait(px.world, n, k, px.local_entry(px.epoch), (int64_t)px.slot_bytes, 0, (int64_t)i_bytes,
-                    px.local_flags(), px.epoch, px.status.p, D_dev, reinterpret_cast<long long*>(I_dev),
+                    px.local_flags(), px.epoch, px.status_dev, D_dev, reinterpret_cast<long long*>(I_dev),
                     (cudaStream_t)stream);
   ABSB_API_END
 }

@@ -233,22 +233,28 @@ __global__ __launch_bounds__(128) void merge_partials_kernel(
 // merge_partials fused with the shard exchange (peer.cuh): the merged k-best of every query is
 // stored straight into slot [rank] of EVERY rank's ring entry over NVLink instead of a local
 // (D, I); the last CTA of the launch that completes the record raises this rank's flag everywhere.
+// With `active` (the two-stage scan's fallback flags) only flagged queries are merged from the
+// partials; the others push the row the earlier stages left in (Dbase, Ibase).
 template <int SLOTS>
 __global__ __launch_bounds__(128) void merge_partials_push_kernel(
     int nq, int k, const int* __restrict__ q_begin, const float* __restrict__ part_s,
-    const long long* __restrict__ part_id, PeerPush pp) {
+    const long long* __restrict__ part_id, PeerPush pp, const unsigned char* __restrict__ active,
+    const float* __restrict__ Dbase, const long long* __restrict__ Ibase) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q < nq) {
     WarpTopK<SLOTS> tk;
     tk.init(k, lane);
-    const int64_t b = (int64_t)q_begin[q] * k, e = (int64_t)q_begin[q + 1] * k;
-    for (int64_t c0 = b; c0 < e; c0 += 32) {
-      const int64_t c = c0 + lane;
-      const bool valid = c < e;
-      const float v = valid ? part_s[c] : 0.f;
-      const long long id = valid ? part_id[c] : 0;
-      tk.offer_lanes(v, id, valid && id != kIdSentinel);
+    const bool merge = active == nullptr || active[q] != 0;
+    if (merge) {
+      const int64_t b = (int64_t)q_begin[q] * k, e = (int64_t)q_begin[q + 1] * k;
+      for (int64_t c0 = b; c0 < e; c0 += 32) {
+        const int64_t c = c0 + lane;
+        const bool valid = c < e;
+        const float v = valid ? part_s[c] : 0.f;
+        const long long id = valid ? part_id[c] : 0;
+        tk.offer_lanes(v, id, valid && id != kIdSentinel);
+      }
     }
 #pragma unroll
     for (int i = 0; i < SLOTS; ++i) {
@@ -256,7 +262,12 @@ __global__ __launch_bounds__(128) void merge_partials_push_kernel(
       if (r < k) {
         float s = tk.s[i];
         long long id = tk.id[i];
-        if (id == kIdSentinel) { s = -3.4028234663852886e38f; id = -1; }
+        if (merge) {
+          if (id == kIdSentinel) { s = -3.4028234663852886e38f; id = -1; }
+        } else {
+          s = Dbase[(int64_t)q * k + r];
+          id = Ibase[(int64_t)q * k + r];
+        }
         const int64_t o = (pp.q_off + q) * k + r;
         for (int w = 0; w < pp.world; ++w) {
           char* rec = pp.slot_ptrs[w];
@@ -291,8 +302,11 @@ __global__ __launch_bounds__(128) void merge_shards_kernel(int world, int64_t nq
                                                            long long* __restrict__ I,
                                                            const unsigned long long* __restrict__ flags,
                                                            unsigned long long epoch, int* __restrict__ status) {
+  __shared__ int timed_out;
   if (flags != nullptr) {
     // fused with the peer exchange: acquire the arrival flag of every rank before reading its record
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
     if ((int)threadIdx.x < world) {
       unsigned long long t0, t1, v;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -301,13 +315,27 @@ __global__ __launch_bounds__(128) void merge_shards_kernel(int world, int64_t nq
         if (v >= epoch) break;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > 20000000000ull) {  // a dead peer must not hang the GPU
-          *status = 1;
+          *reinterpret_cast<volatile int*>(status) = 1;  // mapped host memory: the host sees it without a sync
+          __threadfence_system();
+          timed_out = 1;
           break;
         }
         __nanosleep(64);
       }
     }
     __syncthreads();
+    if (timed_out) {
+      // never hand back a merge of stale records: every slot reads "missing" (faiss: -FLT_MAX, -1)
+      const int64_t q0 = (int64_t)blockIdx.x * (blockDim.x >> 5);
+      for (int64_t i = threadIdx.x; i < (int64_t)(blockDim.x >> 5) * k; i += blockDim.x) {
+        const int64_t o = q0 * k + i;
+        if (o < nq * k) {
+          D[o] = -3.4028234663852886e38f;
+          I[o] = -1;
+        }
+      }
+      return;
+    }
   }
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -374,10 +402,12 @@ void merge_shards(int world, int64_t nq, int k, const float* D_all, const long l
 }
 
 void merge_partials_push(int nq, int k, const int* q_begin, const float* part_s, const long long* part_id,
-                         const PeerPush& pp, cudaStream_t st) {
+                         const PeerPush& pp, cudaStream_t st, const unsigned char* active, const float* Dbase,
+                         const long long* Ibase) {
   if (nq == 0) return;
+  ABSB_CHECK(active == nullptr || (Dbase && Ibase), ABSB_ERR_INVALID, "masked push needs the base rows");
   ABSB_DISPATCH_SLOTS(k, (merge_partials_push_kernel<SLOTS><<<(nq + 3) / 4, 128, 0, st>>>(nq, k, q_begin, part_s,
-                                                                                         part_id, pp)));
+                                                                                         part_id, pp, active, Dbase, Ibase)));
   ABSB_CUDA(cudaGetLastError());
 }
 

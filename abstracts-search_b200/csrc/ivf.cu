@@ -404,7 +404,8 @@ void IvfIndex::reset() {
   ABSB_CUDA(cudaMemset(pt_off.p, 0, sizeof(long long) * (nlist + 1)));
   ABSB_CUDA(cudaMemset(ws_maxima.p, 0, 2 * sizeof(float)));
   h_list_size.assign(nlist, 0);
-  h_pages_prefix_desc.clear();
+  h_items_prefix_desc.clear();
+  items_bound_chunk = -1;
   ntotal = 0;
   rows_seen = 0;
   have_last_scan = false;
@@ -477,17 +478,26 @@ void IvfIndex::refresh_host_sizes(cudaStream_t st) {
   ABSB_CUDA(cudaMemcpyAsync(h_list_size.data(), list_size.p, sizeof(long long) * nlist,
                             cudaMemcpyDeviceToHost, st));
   ABSB_CUDA(cudaStreamSynchronize(st));
-  std::vector<int64_t> pages(nlist);
-  const int P = pool.page_vecs;
-  for (int l = 0; l < nlist; ++l) pages[l] = (h_list_size[l] + P - 1) / P;
-  std::sort(pages.begin(), pages.end(), std::greater<int64_t>());
-  h_pages_prefix_desc.assign(nlist + 1, 0);
-  for (int l = 0; l < nlist; ++l) h_pages_prefix_desc[l + 1] = h_pages_prefix_desc[l] + pages[l];
+  items_bound_chunk = -1;
 }
 
-int64_t IvfIndex::items_bound_per_query(int nprobe) const {
-  if (h_pages_prefix_desc.empty()) return 0;
-  return h_pages_prefix_desc[std::min(nprobe, nlist)];
+// Upper bound of the work items one query can produce: the sum of the `nprobe` largest per-list item
+// counts, counted by the plan's own list walk (contiguous page runs cut at scan_chunk vectors), so a
+// compacted 3,000-vector list costs ~25 entries instead of one per 16-vector page.
+int64_t IvfIndex::items_bound_per_query(int nprobe, cudaStream_t st) {
+  if (ntotal == 0) return 0;
+  if (items_bound_chunk != scan_chunk) {
+    ws_list_items.reserve((size_t)nlist);
+    launch_count_list_items(table(), scan_chunk, ws_list_items.p, st);
+    std::vector<int> cnt((size_t)nlist);
+    ABSB_CUDA(cudaMemcpyAsync(cnt.data(), ws_list_items.p, sizeof(int) * nlist, cudaMemcpyDeviceToHost, st));
+    ABSB_CUDA(cudaStreamSynchronize(st));
+    std::sort(cnt.begin(), cnt.end(), std::greater<int>());
+    h_items_prefix_desc.assign((size_t)nlist + 1, 0);
+    for (int l = 0; l < nlist; ++l) h_items_prefix_desc[l + 1] = h_items_prefix_desc[l] + cnt[l];
+    items_bound_chunk = scan_chunk;
+  }
+  return h_items_prefix_desc[std::min(nprobe, nlist)];
 }
 
 void IvfIndex::add_core_dev(int64_t n, const float* x, const long long* ids,
@@ -724,6 +734,7 @@ void IvfIndex::compact(int64_t scratch_pages, cudaStream_t st) {
     ABSB_CUDA(cudaStreamSynchronize(st));  // scratch and host vectors die with this frame
   }
   have_last_scan = false;
+  items_bound_chunk = -1;
 }
 
 // ---------------------------------------------------------------- train --------------------
@@ -770,6 +781,30 @@ int64_t split_clusters_host(int d, int64_t k, int64_t n, std::vector<float>& has
   return nsplit;
 }
 }  // namespace
+
+namespace {
+// faiss fvec_renorm_L2: x_i *= 1 / sqrt(|x_i|^2) for every row with a non-zero norm; one warp per row.
+__global__ void renorm_rows_kernel(int64_t n, int d, float* __restrict__ x) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  float* xr = x + (size_t)r * d;
+  float ss = 0.f;
+  for (int j = lane; j < d; j += 32) ss = fmaf(xr[j], xr[j], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (ss > 0.f) {
+    const float inv = 1.0f / sqrtf(ss);
+    for (int j = lane; j < d; j += 32) xr[j] *= inv;
+  }
+}
+}  // namespace
+
+void renorm_rows(int64_t n, int d, float* x, cudaStream_t st) {
+  if (n == 0) return;
+  renorm_rows_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(n, d, x);
+  ABSB_CUDA(cudaGetLastError());
+}
 
 void rand_perm_export(int64_t n, int64_t seed, int* out) {
   std::vector<int> p = rand_perm_host(n, seed);
@@ -850,6 +885,7 @@ void IvfIndex::train_dev(int64_t n, const float* x, cudaStream_t st) {
     ABSB_CUDA(cudaMemcpyAsync(rows.p, perm.data(), sizeof(int) * k, cudaMemcpyHostToDevice, st));
     gather_rows_kernel<<<grid_for(k * 32, 256, sms), 256, 0, st>>>(k, d4, rows.p, xs, centroids.p);
     ABSB_CUDA(cudaGetLastError());
+    if (cp.spherical) renorm_rows(k, d, centroids.p, st);  // post_process_centroids before the first assignment
     ABSB_CUDA(cudaStreamSynchronize(st));
   }
   trained = true;  // coarse_dev needs it; centroids are valid from here on
@@ -893,6 +929,7 @@ void IvfIndex::train_dev(int64_t n, const float* x, cudaStream_t st) {
       ABSB_CUDA(cudaMemcpy(centroids.p, hcent.data(), sizeof(float) * (size_t)k * d, cudaMemcpyHostToDevice));
       c3_dirty = true;
     }
+    if (cp.spherical) renorm_rows(k, d, centroids.p, st);  // post_process_centroids: after mean + split
   }
 }
 
@@ -951,7 +988,7 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
   ABSB_CHECK(k >= 1 && k <= ABSB_MAX_K, ABSB_ERR_INVALID, "k=%d outside [1,%d]", k, ABSB_MAX_K);
   ABSB_CHECK(nprobe >= 1, ABSB_ERR_INVALID, "nprobe=%d", nprobe);
   if (nq == 0) return;
-  const int64_t per_q = std::max<int64_t>(1, items_bound_per_query(nprobe));
+  const int64_t per_q = std::max<int64_t>(1, items_bound_per_query(nprobe, st));
   // bound the partial-result buffers to ~1 GiB per launch
   const int k_part = std::max(k, two_stage_k);  // entries per work item in the partial-result buffers
   int64_t nb_max = std::min<int64_t>(kMaxPlanQueries, std::max<int64_t>(1, ((int64_t)1 << 30) / (per_q * k_part * 12)));
@@ -994,8 +1031,18 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
     a.part_id = ws_part_id.p;
     a.sm_count = props.sm_count;
     a.ctas_per_sm = scan_ctas_per_sm;
-    const bool two_stage = two_stage_k >= k && pool.shadow && d == 1024 && push == nullptr;
+    const bool two_stage = two_stage_k >= k && pool.shadow && d == 1024;
     if (two_stage) {
+      // with a push target the stages work on a local (D, I) and the LAST merge stores every row into
+      // the peers' buffers (fallback rows merged, proven rows copied): no separate pack + push kernel
+      float* Dl = D ? D + q0 * k : nullptr;
+      long long* Il = I ? I + q0 * k : nullptr;
+      if (push) {
+        ws_push_D.reserve((size_t)kMaxPlanQueries * k);
+        ws_push_I.reserve((size_t)kMaxPlanQueries * k);
+        Dl = ws_push_D.p;
+        Il = ws_push_I.p;
+      }
       // ---- stage 1: fp16 shadow codes -> shortlist of K approximate candidates per query (ivf_scan16.cu)
       const int K = two_stage_k;
       ws_short_s.reserve((size_t)kMaxPlanQueries * K);
@@ -1043,8 +1090,8 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
       }
       {
         Span sp(this, st, 2);
-        merge_partials(nb, k, ws_q_begin2.p, ws_part2_s.p, ws_part2_id.p, D + q0 * k, I + q0 * k, st);
-        launch_two_stage_check(nb, d, k, K, a.Q, D + q0 * k, I + q0 * k, ws_short_s.p, ws_short_g.p, ws_maxima.p,
+        merge_partials(nb, k, ws_q_begin2.p, ws_part2_s.p, ws_part2_id.p, Dl, Il, st);
+        launch_two_stage_check(nb, d, k, K, a.Q, Dl, Il, ws_short_s.p, ws_short_g.p, ws_maxima.p,
                                ws_flags.p, ws_nflag.p, st);
         // ---- fallback: the queries the bound could not prove go through the single-pass scan (the plan
         // emits no work for the others, so this costs a few empty launches when everything was proven)
@@ -1060,7 +1107,14 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
       }
       {
         Span sp(this, st, 2);
-        merge_partials(nb, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, D + q0 * k, I + q0 * k, st, ws_flags.p);
+        if (push) {
+          PeerPush pp = push->pp;
+          pp.q_off = push->q_base + q0;
+          if (push->q_base + q0 + nb != push->nq_total) pp.epoch = 0;  // record not complete yet
+          merge_partials_push(nb, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, pp, st, ws_flags.p, Dl, Il);
+        } else {
+          merge_partials(nb, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, Dl, Il, st, ws_flags.p);
+        }
       }
       have_last_scan = false;
       stats_pending = true;

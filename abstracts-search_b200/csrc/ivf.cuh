@@ -38,6 +38,7 @@ struct ClusteringParams {
   int max_points_per_centroid = 256;
   int min_points_per_centroid = 39;
   int64_t seed = 1234;
+  bool spherical = false;  // faiss ClusteringParameters::spherical (index_factory sets it for inner product)
 };
 
 // Where a search sends its merged top-k when it feeds the peer exchange instead of a local (D, I).
@@ -73,7 +74,12 @@ struct IvfIndex {
   DBuf<int> pt_pages;
   int64_t pt_total_pages = 0;
   std::vector<int64_t> h_list_size;
-  std::vector<int64_t> h_pages_prefix_desc;  // prefix sums of per-list page counts, sorted descending
+  // prefix sums of the per-list work-item counts (what the plan emits under scan_chunk), sorted
+  // descending: entry [p] bounds the items of any p probes.  Rebuilt lazily (one small D2H copy) on
+  // the first search after add / compact / reset or a change of scan_chunk.
+  std::vector<int64_t> h_items_prefix_desc;
+  int items_bound_chunk = -1;  // scan_chunk the table was built for; -1 = stale
+  DBuf<int> ws_list_items;
   int64_t ntotal = 0;
   int64_t rows_seen = 0;  // rows offered to add() so far, kept or not: the next default id
 
@@ -113,6 +119,8 @@ struct IvfIndex {
   DBuf<long long> ws_list_ids;
   DBuf<float> ws_D;
   DBuf<long long> ws_I;
+  DBuf<float> ws_push_D;  // local (D, I) of a two-stage search whose final merge pushes to the peers
+  DBuf<long long> ws_push_I;
 
   // replay info for absb_ivf_time_scan
   ScanLaunch last_scan{};
@@ -175,7 +183,7 @@ struct IvfIndex {
   void compact(int64_t scratch_pages, cudaStream_t st);
   void set_two_stage(int shortlist);
   int64_t two_stage_fallbacks(cudaStream_t st);
-  int64_t items_bound_per_query(int nprobe) const;
+  int64_t items_bound_per_query(int nprobe, cudaStream_t st);
   void refresh_host_sizes(cudaStream_t st);
 };
 
@@ -189,6 +197,7 @@ void plan_page_compaction(std::vector<int> src, int64_t scratch_pages, std::vect
                           std::vector<int64_t>& phase_end);
 
 void rand_perm_export(int64_t n, int64_t seed, int* out);
+void renorm_rows(int64_t n, int d, float* x, cudaStream_t st);  // fvec_renorm_L2
 int64_t split_clusters_export(int d, int64_t k, int64_t n, float* hassign, float* centroids);
 
 struct FlatIndex {

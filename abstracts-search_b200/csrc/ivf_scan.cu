@@ -120,6 +120,13 @@ __global__ void plan_emit_kernel(ListTable lt, const long long* __restrict__ coa
   if (offs[i + 1] > off) walk_list(lt, coarse[i], chunk, i / nprobe, items + off, nullptr);
 }
 
+// Work items per list under the current chunk length (the exact count the plan would emit for it):
+// the host sums the nprobe largest to size the partial-result buffers of a search.
+__global__ void count_list_items_kernel(ListTable lt, int chunk, int* __restrict__ out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < lt.nlist) out[l] = walk_list(lt, l, chunk, 0, nullptr, nullptr);
+}
+
 // ------------------------------------------------------------------ scan --------------------
 __device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
   acc = fmaf(a.x, b.x, acc);
@@ -309,6 +316,11 @@ void launch_plan(const ListTable& lt, const long long* coarse, int nq, int nprob
   plan_emit_kernel<<<(work + threads - 1) / threads, threads, 0, st>>>(lt, coarse, nq, nprobe, chunk, max_items,
                                                                       pair_offs, items, q_begin, n_items,
                                                                       queue_counter, stats);
+  ABSB_CUDA(cudaGetLastError());
+}
+
+void launch_count_list_items(const ListTable& lt, int chunk, int* out, cudaStream_t st) {
+  count_list_items_kernel<<<(lt.nlist + 255) / 256, 256, 0, st>>>(lt, chunk, out);
   ABSB_CUDA(cudaGetLastError());
 }
 

@@ -63,6 +63,8 @@ void launch_plan(const ListTable& lt, const long long* coarse, int nq, int nprob
                  size_t scan_tmp_bytes, const PlanOrderWs* order_ws, cudaStream_t st,
                  const unsigned char* active = nullptr);
 size_t plan_scan_tmp_bytes(int max_pairs);
+// out[l] = number of work items the plan emits for list l with this chunk length
+void launch_count_list_items(const ListTable& lt, int chunk, int* out, cudaStream_t st);
 void launch_scan(const ScanLaunch& a, cudaStream_t st);
 
 // ---- two-stage scan (ivf_scan16.cu): fp16 shortlist pass + exact fp32 re-score, d = 1024 ----

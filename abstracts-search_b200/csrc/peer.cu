@@ -64,9 +64,10 @@ PeerExchange::PeerExchange(int device_, int rank_, int world_, size_t slot_bytes
   ABSB_CUDA(cudaMalloc(&local, data_bytes + sizeof(unsigned long long) * world));
   ABSB_CUDA(cudaMemset(local, 0, data_bytes + sizeof(unsigned long long) * world));
   done_counter.alloc_exact(1);
-  status.alloc_exact(1);
+  ABSB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&status_host), sizeof(int), cudaHostAllocMapped));
+  *status_host = 0;
+  ABSB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&status_dev), status_host, 0));
   ABSB_CUDA(cudaMemset(done_counter.p, 0, sizeof(unsigned)));
-  ABSB_CUDA(cudaMemset(status.p, 0, sizeof(int)));
   ABSB_CUDA(cudaDeviceSynchronize());  // zeroed before anybody can learn the handle
   base.assign(world, nullptr);
   opened.assign(world, false);
@@ -79,6 +80,7 @@ PeerExchange::~PeerExchange() {
   for (int w = 0; w < world; ++w)
     if (opened[w] && base[w]) cudaIpcCloseMemHandle(base[w]);
   if (local) cudaFree(local);
+  if (status_host) cudaFreeHost(status_host);
 }
 
 void PeerExchange::ipc_handle(void* blob64) const {
@@ -139,7 +141,7 @@ PeerPush PeerExchange::begin_push(long long i_off, long long d_off) {
 }
 
 void PeerExchange::wait(cudaStream_t st) {
-  peer_wait_kernel<<<1, 64, 0, st>>>(world, local_flags(), epoch, status.p);
+  peer_wait_kernel<<<1, 64, 0, st>>>(world, local_flags(), epoch, status_dev);
   ABSB_CUDA(cudaGetLastError());
 }
 
@@ -160,13 +162,6 @@ char* PeerExchange::allgather(const void* src, size_t bytes, cudaStream_t st) {
   push(src, bytes, st);
   wait(st);
   return local_entry(epoch);
-}
-
-int PeerExchange::read_status(cudaStream_t st) {
-  int h = 0;
-  ABSB_CUDA(cudaMemcpyAsync(&h, status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  ABSB_CUDA(cudaStreamSynchronize(st));
-  return h;
 }
 
 }  // namespace absb

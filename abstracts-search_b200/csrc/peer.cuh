@@ -41,7 +41,10 @@ struct PeerExchange {
   DBuf<char*> d_slot_ptrs;             // [2][world]
   DBuf<unsigned long long*> d_flag_ptrs;  // [world]
   DBuf<unsigned> done_counter;
-  DBuf<int> status;                    // 0 ok, 1 = a wait timed out
+  // 0 ok, 1 = a wait timed out.  Lives in mapped pinned host memory: the waiting kernel writes it
+  // through the device alias, the host polls it after every search WITHOUT a synchronisation.
+  int* status_host = nullptr;
+  int* status_dev = nullptr;
   DBuf<char> staging;                  // packed {I, D} record of absb_peer_push_results_dev
   unsigned long long epoch = 0;        // last epoch pushed
   int64_t rec_n = 0;                   // shape of the last pushed search record
@@ -63,12 +66,15 @@ struct PeerExchange {
   void push(const void* src, size_t bytes, cudaStream_t st);
   char* allgather(const void* src, size_t bytes, cudaStream_t st);
   void wait(cudaStream_t st);
-  int read_status(cudaStream_t st);
+  int read_status() const { return *const_cast<volatile int*>(status_host); }
 };
 
 // dense.cu
+// active (optional, [nq] bytes): only queries with active[q] != 0 are merged from the partials; the
+// others push row q of (Dbase, Ibase) as it is.
 void merge_partials_push(int nq, int k, const int* q_begin, const float* part_s, const long long* part_id,
-                         const PeerPush& pp, cudaStream_t st);
+                         const PeerPush& pp, cudaStream_t st, const unsigned char* active = nullptr,
+                         const float* Dbase = nullptr, const long long* Ibase = nullptr);
 void merge_shards_wait(int world, int64_t nq, int k, const char* entry, int64_t slot_bytes, int64_t i_off,
                        int64_t d_off, const unsigned long long* flags, unsigned long long epoch, int* status,
                        float* D, long long* I, cudaStream_t st);

@@ -76,6 +76,69 @@ __global__ void synth_fill_kernel(int kind, uint64_t seed, int64_t row0,
   }
 }
 
+// Unit-norm variant (kind | 4): the same integer row v, written as v / sqrt(sum v^2) — a real-valued fp32
+// corpus (what `index fill` stores: L2-normalised embeddings, /root/reference/Makefile:24-25) that is
+// NOT exactly representable in fp16.  sum v^2 <= 1024 * 127^2 < 2^24 is an exact integer in fp32, and
+// sqrt / divide are the correctly rounded IEEE operations, so numpy reproduces every bit
+// (oracle/synth.py: v.astype(f32) / np.sqrt(f32(ss))).  One warp per row.
+__global__ void synth_fill_unit_kernel(int kind, uint64_t seed, int64_t row0, const long long* __restrict__ row_ids,
+                                       int64_t n, int d, int nlist, int64_t corpus_rows, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int groups = d / 8;
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < n;
+       i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const uint64_t r = row_ids ? (uint64_t)row_ids[i] : (uint64_t)(row0 + i);
+    uint64_t src = r;
+    if (kind == 2) src = (row_key(seed ^ SALT_QSRC, r) >> 1) % (uint64_t)corpus_rows;
+    const int c = kind == 1 ? 0 : cluster_of(seed, src, nlist);
+    const uint64_t key_mu = row_key(seed ^ SALT_MU, kind == 1 ? r : (uint64_t)c);
+    const uint64_t key_eps = row_key(seed ^ SALT_EPS, src);
+    const uint64_t key_d = row_key(seed ^ SALT_QDELTA, r);
+    int ss = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      float inv_den = 0.f;
+      if (pass == 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        inv_den = __fsqrt_rn((float)ss);
+      }
+      for (int g = lane; g < groups; g += 32) {
+        int v[8];
+        const uint64_t wm = word(key_mu, g);
+        if (kind == 1) {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) v[b] = (int)((wm >> (8 * b)) & 0xFF) % 193 - 96;
+        } else {
+          const uint64_t we = word(key_eps, g);
+#pragma unroll
+          for (int b = 0; b < 8; ++b)
+            v[b] = (int)((wm >> (8 * b)) & 0xFF) % 193 - 96 + (int)((we >> (8 * b)) & 0xFF) % 63 - 31;
+          if (kind == 2) {
+            const uint64_t wd = word(key_d, g);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+              int x = v[b] + (int)((wd >> (8 * b)) & 0xFF) % 31 - 15;
+              v[b] = x < -127 ? -127 : (x > 127 ? 127 : x);
+            }
+          }
+        }
+        if (pass == 0) {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) ss += v[b] * v[b];
+        } else {
+          float4* o = reinterpret_cast<float4*>(out + i * d + g * 8);
+          // ss == 0 cannot happen for d >= 8 in practice; keep the row zero instead of NaN if it does
+          const bool ok = ss > 0;
+          o[0] = make_float4(ok ? __fdiv_rn((float)v[0], inv_den) : 0.f, ok ? __fdiv_rn((float)v[1], inv_den) : 0.f,
+                             ok ? __fdiv_rn((float)v[2], inv_den) : 0.f, ok ? __fdiv_rn((float)v[3], inv_den) : 0.f);
+          o[1] = make_float4(ok ? __fdiv_rn((float)v[4], inv_den) : 0.f, ok ? __fdiv_rn((float)v[5], inv_den) : 0.f,
+                             ok ? __fdiv_rn((float)v[6], inv_den) : 0.f, ok ? __fdiv_rn((float)v[7], inv_den) : 0.f);
+        }
+      }
+    }
+  }
+}
+
 __global__ void synth_cluster_kernel(uint64_t seed, int64_t row0, int64_t n, int nlist,
                                      long long* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
@@ -87,11 +150,18 @@ __global__ void synth_cluster_kernel(uint64_t seed, int64_t row0, int64_t n, int
 
 void synth_fill(int kind, uint64_t seed, int64_t row0, const long long* row_ids, int64_t n, int d,
                 int nlist, int64_t corpus_rows, float* out, cudaStream_t st) {
-  ABSB_CHECK(kind >= 0 && kind <= 2, ABSB_ERR_INVALID, "synth kind %d", kind);
+  ABSB_CHECK(kind >= 0 && kind <= 6 && (kind & 3) <= 2, ABSB_ERR_INVALID, "synth kind %d", kind);
   ABSB_CHECK(d > 0 && d % 8 == 0, ABSB_ERR_INVALID, "synth needs d %% 8 == 0 (d=%d)", d);
   ABSB_CHECK(nlist > 0 && n >= 0, ABSB_ERR_INVALID, "synth nlist/n");
-  ABSB_CHECK(kind != 2 || corpus_rows > 0, ABSB_ERR_INVALID, "queries need corpus_rows");
+  ABSB_CHECK((kind & 3) != 2 || corpus_rows > 0, ABSB_ERR_INVALID, "queries need corpus_rows");
   if (n == 0) return;
+  if (kind & 4) {
+    ABSB_CHECK(d <= 1024, ABSB_ERR_UNSUPPORTED, "unit-norm synth rows need d <= 1024 (exact integer norm in fp32)");
+    const int blocks = (int)std::min<int64_t>(ceil_div(n * 32, 256), 148 * 16);
+    synth_fill_unit_kernel<<<blocks, 256, 0, st>>>(kind & 3, seed, row0, row_ids, n, d, nlist, corpus_rows, out);
+    ABSB_CUDA(cudaGetLastError());
+    return;
+  }
   const int64_t total = n * (d / 8);
   const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
   synth_fill_kernel<<<blocks, 256, 0, st>>>(kind, seed, row0, row_ids, n, d, nlist, corpus_rows, out);

@@ -204,19 +204,29 @@ class Encoder:
         if not files:
             raise RuntimeError(f"no .safetensors files under {path}")
         known = set(self.config.param_shapes())
+        loaded = set()
         for fpath in files:
             for name, (arr, dt) in read_safetensors(fpath).items():
                 short = name[6:] if name.startswith("model.") else name
                 short = {"linear.weight": "dense.weight", "linear.bias": "dense.bias"}.get(short, short)
                 if short in known:
                     self.load_weight(short, arr, bf16_raw=(dt == "BF16"))
+                    loaded.add(short)
+        missing = sorted(known - loaded)
+        if missing:
+            # e.g. a snapshot without its 2_Dense_1024 folder: embeddings from uninitialised weights
+            # would be meaningless and nothing downstream could tell
+            raise RuntimeError(f"{path}: {len(missing)} parameters of the model are in none of the safetensors files "
+                               f"(first: {missing[:4]})")
         if self.tokenizer is None:
+            # real weights with the hash stand-in would produce garbage embeddings silently: a model
+            # directory must bring its tokenizer (or the caller passes tokenizer=...)
             try:
                 from transformers import AutoTokenizer
 
                 self.tokenizer = AutoTokenizer.from_pretrained(path, trust_remote_code=self.trust_remote_code)
-            except Exception:
-                self.tokenizer = None
+            except Exception as e:
+                raise RuntimeError(f"{path}: the tokenizer could not be loaded ({e!r}); pass tokenizer=... explicitly") from e
 
     # ---- SentenceTransformer surface -------------------------------------------------------
     def get_sentence_embedding_dimension(self) -> int:

@@ -21,8 +21,9 @@ tests/test_faiss_io_cpu.py, see DESIGN.md "parity unpinned"):
       "sprs" (count u64 + (list, size) u64 pairs), then per non-empty list: codes
       [n * code_size] bytes, ids [n] i64
   OnDiskInvertedLists                           fourcc "ilod"
-      nlist u64, code_size u64, lists: count u64 + {size, capacity, offset} u64 triples,
-      slots: count u64 + {offset, capacity} u64 pairs, filename: count u64 + bytes, totsize u64;
+      nlist u64, code_size u64, lists: count u64 (= nlist STRUCTS of 24 bytes, faiss WRITEVECTOR counts
+      elements, not u64 words) + {size, capacity, offset} u64 triples, slots: count u64 (16-byte structs)
+      + {offset, capacity} u64 pairs, filename: count u64 + bytes, totsize u64;
       in the .ivfdata file list l holds codes [capacity * code_size] at `offset`, then ids
       [capacity] i64.
 
@@ -154,8 +155,10 @@ def write_ivfflat(path: str, ix: IVFFlatData, ondisk_path: str | None = None, si
                     off += n * (code_size + 8)
         f.write(b"ilod")
         f.write(struct.pack("<QQ", ix.nlist, code_size))
-        _w_vector(f, table.reshape(-1))
-        f.write(struct.pack("<Q", 0))  # no free slots
+        # WRITEVECTOR(od->lists): the count is the number of 24-byte OnDiskOneList structs
+        f.write(struct.pack("<Q", ix.nlist))
+        f.write(table.tobytes())
+        f.write(struct.pack("<Q", 0))  # no free slots (count of 16-byte Slot structs)
         name = os.path.basename(ondisk_path).encode()
         f.write(struct.pack("<Q", len(name)))
         f.write(name)
@@ -245,7 +248,11 @@ def read_ivfflat(path: str, ondisk_dir: str | None = None) -> IVFFlatData:
             out.codes.append(c)
             out.ids.append(i)
     elif il == b"ilod":
-        table = r.vector(np.uint64).reshape(nlist, 3)
+        n_structs = r.take("<Q")
+        if n_structs != nlist:
+            raise RuntimeError(f"OnDiskInvertedLists: {n_structs} list records for nlist = {nlist}")
+        table = np.frombuffer(buf, dtype=np.uint64, count=3 * nlist, offset=r.o).reshape(nlist, 3)
+        r.o += 24 * nlist
         nslots = r.take("<Q")
         r.o += nslots * 16
         name = bytes(r.vector(np.uint8)).decode()

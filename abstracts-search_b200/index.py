@@ -74,6 +74,9 @@ class ClusteringParameters:
         self.min_points_per_centroid = 39
         self.seed = 1234
         self.verbose = False
+        # normalise the centroids after every iteration.  faiss's struct default is False; its
+        # index_factory turns it on for inner-product IVF indexes (mirrored in index_factory below).
+        self.spherical = False
 
 
 class SearchParametersIVF:
@@ -271,6 +274,7 @@ class IndexIVFFlat:
                           f"{self.nlist * cp.min_points_per_centroid} training points")
         check(lib().absb_ivf_set_clustering(self._h, cp.niter, cp.max_points_per_centroid,
                                             cp.min_points_per_centroid, cp.seed))
+        check(lib().absb_ivf_set_clustering_spherical(self._h, 1 if getattr(cp, "spherical", False) else 0))
         if _is_cuda_tensor(x):
             check(lib().absb_ivf_train_dev(self._h, n, ptr(x), _lib.current_stream_ptr()))
         else:
@@ -435,7 +439,12 @@ def index_factory(d: int, description: str, metric: int = METRIC_L2, device: int
         return IndexFlatIP(d, device=device)
     m = re.fullmatch(r"IVF(\d+),Flat", desc)
     if m:
-        return IndexIVFFlat(d, int(m.group(1)), metric, device=device)
+        ix = IndexIVFFlat(d, int(m.group(1)), metric, device=device)
+        # faiss index_factory: `if (metric == METRIC_INNER_PRODUCT) index_ivf->cp.spherical = true` — what
+        # `sidecar-search index train` gets (/root/reference/Makefile:38-39).  faiss is external and
+        # unpinned here, so this is a switch: set `index.cp.spherical = False` for the plain Lloyd update.
+        ix.cp.spherical = True
+        return ix
     raise RuntimeError(f"could not parse index description {description!r} (supported: Flat, IVF<n>,Flat)")
 
 

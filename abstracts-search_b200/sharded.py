@@ -71,6 +71,13 @@ class DeviceOps:
         check(lib().absb_rand_perm(n, seed, ptr(out)))
         return out.astype(np.int64)
 
+    def renorm(self, cent):
+        """fvec_renorm_L2 of the centroid rows, in place (ClusteringParameters.spherical)."""
+        from ._lib import check, current_stream_ptr, lib, ptr
+
+        check(lib().absb_renorm_rows_dev(cent.device.index or 0, cent.shape[0], cent.shape[1], ptr(cent), current_stream_ptr()))
+        return cent
+
     def split_clusters(self, d: int, k: int, n: int, hassign: np.ndarray, centroids: np.ndarray) -> int:
         from ctypes import byref, c_int64
 
@@ -207,6 +214,7 @@ class ShardedIndexIVFFlat:
         niter = cp.niter if cp else 10
         max_ppc = cp.max_points_per_centroid if cp else 256
         seed = cp.seed if cp else 1234
+        spherical = bool(getattr(cp, "spherical", False))
         k, d = self.nlist, self.d
         x = ops.to_device(x_local)
         dev = x.device
@@ -235,9 +243,12 @@ class ShardedIndexIVFFlat:
         if len(have):
             cent[torch.from_numpy(have).to(dev)] = xs[torch.from_numpy(src[have]).to(dev)]
         dist.all_reduce(cent, group=self.group)
-        self.local.set_centroids(cent if cent.is_cuda else cent.numpy())
         if ns == k:
+            self.local.set_centroids(cent if cent.is_cuda else cent.numpy())
             return
+        if spherical:
+            cent = ops.renorm(cent)  # post_process_centroids before the first assignment
+        self.local.set_centroids(cent if cent.is_cuda else cent.numpy())
         for _ in range(niter):
             assign = ops.assign(xs)
             sums, counts = ops.centroid_sums(xs, assign if hasattr(assign, "device") and not isinstance(assign, np.ndarray)
@@ -251,6 +262,8 @@ class ShardedIndexIVFFlat:
                 c_h = np.ascontiguousarray(cent.cpu().numpy())
                 ops.split_clusters(d, k, ns, hassign, c_h)
                 cent = torch.from_numpy(c_h).to(dev)
+            if spherical:
+                cent = ops.renorm(cent.contiguous())
             self.local.set_centroids(cent if cent.is_cuda else cent.numpy())
 
     def _search_peer(self, x, k: int):
@@ -265,14 +278,16 @@ class ShardedIndexIVFFlat:
         assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == self.d
         if ((n * k * 8 + 15) & ~15) + n * k * 4 > px.slot_bytes:
             raise ValueError(f"{n} x {k} results exceed the exchange slot ({px.slot_bytes} bytes); call use_peer_exchange(max_results=...)")
+        # a wait of an EARLIER search that gave up on a dead peer (20 s) left its mark in mapped host
+        # memory: reading it costs no synchronisation, so every search checks it
+        if px.status() != 0:
+            raise RuntimeError("peer exchange timed out waiting for another rank; the merged results of that search "
+                               "were returned as missing (-1)")
         with torch.cuda.device(x.device):
             st = current_stream_ptr()
-            if getattr(self.local, "two_stage", 0) >= k:
-                # the two-stage scan ends in a local (D, I) (its fallback may rewrite rows): push that
-                Dl, Il = self.local.search(x, k)
-                check(lib().absb_peer_push_results_dev(px._h, n, k, ptr(Dl), ptr(Il), st))
-            else:
-                check(lib().absb_ivf_search_push_dev(self.local._h, px._h, n, ptr(x), k, self.nprobe, st))
+            # single-pass and two-stage scans alike end in a merge kernel that stores this shard's top-k
+            # into every rank's buffer (merge_partials_push): no pack / push kernel of its own
+            check(lib().absb_ivf_search_push_dev(self.local._h, px._h, n, ptr(x), k, self.nprobe, st))
             Dm = torch.empty((n, k), dtype=torch.float32, device=x.device)
             Im = torch.empty((n, k), dtype=torch.int64, device=x.device)
             check(lib().absb_peer_merge_shards_dev(px._h, n, k, ptr(Dm), ptr(Im), st))
@@ -282,7 +297,7 @@ class ShardedIndexIVFFlat:
         """x: the full query batch on every rank.  Returns the merged (D, I) on every rank.
 
         The per-rank record {I [n,k] i64, D [n,k] f32} is packed into one byte buffer so that the
-        exchange is ONE all-gather (n*k*12 bytes per rank: 61,440 B for 512 x 10)."""
+        exchange is ONE all-gather (n*k*12 bytes per rank, segments padded to 16: 61,440 B for 512 x 10)."""
         import torch
         import torch.distributed as dist
 
@@ -298,18 +313,21 @@ class ShardedIndexIVFFlat:
             if dist.get_backend(self.group) == "nccl":
                 D, I = D.cuda(), I.cuda()
         n = D.shape[0]
-        rec = n * k * 12
+        # record = {I [n,k] i64 | D [n,k] f32}, both segments padded to 16 bytes so that every rank's
+        # block of the gathered buffer stays 8-byte aligned for the merge kernel's int64 loads (odd n*k)
+        i_bytes = (n * k * 8 + 15) & ~15
+        rec = i_bytes + ((n * k * 4 + 15) & ~15)
         if self._gD is None or self._gD.numel() != self.world * rec or self._gD.device != D.device:
             self._gD = torch.empty(self.world * rec, dtype=torch.uint8, device=D.device)
-            self._gI = torch.empty(rec, dtype=torch.uint8, device=D.device)
+            self._gI = torch.zeros(rec, dtype=torch.uint8, device=D.device)
         mine = self._gI
         mine[: n * k * 8].view(torch.int64).copy_(I.reshape(-1))
-        mine[n * k * 8:].view(torch.float32).copy_(D.reshape(-1))
+        mine[i_bytes: i_bytes + n * k * 4].view(torch.float32).copy_(D.reshape(-1))
         dist.all_gather_into_tensor(self._gD, mine, group=self.group)
         if self._merge_fn is not None:
             g = self._gD.cpu().view(self.world, rec)
             I_all = g[:, : n * k * 8].contiguous().view(torch.int64).view(self.world, n, k).numpy()
-            D_all = g[:, n * k * 8:].contiguous().view(torch.float32).view(self.world, n, k).numpy()
+            D_all = g[:, i_bytes: i_bytes + n * k * 4].contiguous().view(torch.float32).view(self.world, n, k).numpy()
             return self._merge_fn(D_all, I_all, k)
         from ctypes import c_void_p
 
@@ -318,7 +336,7 @@ class ShardedIndexIVFFlat:
         Dm = torch.empty((n, k), dtype=torch.float32, device=D.device)
         Im = torch.empty((n, k), dtype=torch.int64, device=D.device)
         base = self._gD.data_ptr()
-        check(lib().absb_merge_shards_dev(D.device.index or 0, self.world, n, k, c_void_p(base + n * k * 8),
+        check(lib().absb_merge_shards_dev(D.device.index or 0, self.world, n, k, c_void_p(base + i_bytes),
                                           c_void_p(base), rec, ptr(Dm), ptr(Im), current_stream_ptr()))
         if as_numpy:
             return Dm.cpu().numpy(), Im.cpu().numpy()

@@ -73,38 +73,112 @@ def count_rows(dir_path: str) -> int:
     return sum(pq.ParquetFile(p).metadata.num_rows for p in sorted(glob.glob(os.path.join(dir_path, "*.parquet"))))
 
 
+def list_row_groups(dir_path: str) -> list[tuple[str, int, int]]:
+    """(file, row group, rows) of every row group of the store, from the parquet FOOTERS only — no
+    column data is read."""
+    import pyarrow.parquet as pq
+
+    files = sorted(glob.glob(os.path.join(dir_path, "*.parquet")))
+    if not files:
+        raise RuntimeError(f"no parquet shards under {dir_path}")
+    out = []
+    for path in files:
+        md = pq.ParquetFile(path).metadata
+        out.extend((path, g, md.row_group(g).num_rows) for g in range(md.num_row_groups))
+    return out
+
+
+def _read_group(path: str, g: int, d: int | None, columns):
+    import pyarrow.parquet as pq
+
+    t = pq.ParquetFile(path).read_row_group(g, columns=list(columns))
+    ids = t.column("id") if "id" in t.column_names else None
+    return ids, _embedding_matrix(t.column("embedding"), d)
+
+
+def _prefetched(groups, d, columns, depth: int = 2):
+    """Row groups decoded by a background thread `depth` ahead of the consumer: parquet decode + fp16 ->
+    fp32 conversion of group i+1 (pyarrow and numpy release the GIL) overlap the H2D copy and the GPU
+    add() of group i (ctypes releases the GIL for the C call)."""
+    import queue
+    import threading
+
+    q: queue.Queue = queue.Queue(maxsize=depth)
+
+    def work():
+        try:
+            for path, g, _ in groups:
+                q.put(_read_group(path, g, d, columns))
+            q.put(None)
+        except BaseException as e:  # noqa: BLE001 - re-raised in the consumer
+            q.put(e)
+
+    th = threading.Thread(target=work, daemon=True)
+    th.start()
+    while True:
+        item = q.get()
+        if item is None:
+            break
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+    th.join()
+
+
 def fill_index(index, dir_path: str, ids_parquet: str | None = None) -> int:
     """`sidecar-search index fill DATA_DIR` (/root/reference/Makefile:24-25): stream every shard into
     index.add(); faiss ids are the running row numbers, and `ids.parquet` (row -> document id) is
-    written next to the index when a path is given."""
-    from .faiss_io import write_ids_parquet
+    written next to the index when a path is given.  Memory stays bounded: two decoded row groups in
+    flight, and the id column goes to the ids.parquet writer one row group at a time (the 207M-row
+    corpus would otherwise leave 207M Python strings in a list)."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
 
-    all_ids, n = [], 0
-    for ids, x in iter_row_groups(dir_path, index.d):
-        index.add(x)
-        n += x.shape[0]
-        if ids_parquet is not None:
-            all_ids.extend(ids)
+    groups = list_row_groups(dir_path)
+    writer, n = None, 0
+    try:
+        for ids, x in _prefetched(groups, index.d, ("id", "embedding")):
+            index.add(x)
+            n += x.shape[0]
+            if ids_parquet is not None:
+                t = pa.table({"id": ids})
+                if writer is None:
+                    writer = pq.ParquetWriter(ids_parquet, t.schema)
+                writer.write_table(t)
+    finally:
+        if writer is not None:
+            writer.close()
+    if ids_parquet is not None and writer is None:
+        from .faiss_io import write_ids_parquet
+
+        write_ids_parquet(ids_parquet, [])
     if hasattr(index, "compact"):
         index.compact()  # row-group-sized add() calls leave every list scattered over the page pool
-    if ids_parquet is not None:
-        write_ids_parquet(ids_parquet, all_ids)
     return n
 
 
 def train_index(index, dir_path: str, max_rows: int | None = None, seed: int = 1234) -> int:
     """`sidecar-search index train DATA_DIR` (/root/reference/Makefile:38-39): train on a sample of
     the store.  faiss itself subsamples to 256 x nlist rows; reading more than that from disk is
-    wasted I/O, so whole row groups are drawn (seeded) until that many rows are gathered."""
+    wasted I/O, so whole row groups are drawn (seeded permutation of the (file, row group) pairs listed
+    from the parquet footers) and ONLY the drawn groups are read, until that many rows are gathered —
+    68 GB of fp32 for IVF65536 however large the store is (the reference trains on a 16 GB box with
+    faiss's own on-disk sampling, Makefile:34-39)."""
     cap = max_rows or index.nlist * index.cp.max_points_per_centroid
-    groups = list(iter_row_groups(dir_path, index.d, columns=("embedding",)))
+    groups = list_row_groups(dir_path)
     order = np.random.RandomState(seed).permutation(len(groups))
-    take, rows = [], 0
+    chosen, rows = [], 0
     for g in order:
-        take.append(groups[g][1])
-        rows += take[-1].shape[0]
+        chosen.append(groups[g])
+        rows += groups[g][2]
         if rows >= cap:
             break
-    x = np.concatenate(take, axis=0)
+    d = index.d
+    x = np.empty((rows, d), dtype=np.float32)
+    r0 = 0
+    for _, xg in _prefetched(chosen, d, ("embedding",)):
+        x[r0:r0 + xg.shape[0]] = xg
+        r0 += xg.shape[0]
+    assert r0 == rows
     index.train(x)
-    return x.shape[0]
+    return rows

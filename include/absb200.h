@@ -65,6 +65,9 @@ int absb_device_info(int device, char* name, int name_len, int* sm_count, int* c
  * kind 0: corpus rows   x[r] = (mu[c(r)] + eps(r)) / 128
  * kind 1: centroids     c[j] =  mu[j] / 128           (row index = list number)
  * kind 2: queries       q[i] = clamp(mu[c(s)] + eps(s) + delta(i)) / 128, s = source row of query i
+ * kind | 4: the same integer row divided by its L2 norm instead of by 128 — real-valued unit-length
+ *           fp32 rows (what `index fill` stores, /root/reference/Makefile:24-25), not representable in
+ *           fp16, still bit-identical to oracle/synth.py (exact integer norm, IEEE sqrt and divide).
  * out is a DEVICE pointer to [n, d] float32. */
 int absb_synth_fill_dev(int kind, uint64_t seed, int64_t row0, int64_t n, int d, int nlist,
                         int64_t corpus_rows, float* out_dev, void* stream);
@@ -105,6 +108,15 @@ int absb_ivf_is_trained(absb_ivf_t h, int* trained);
  * min_points_per_centroid=39, seed=1234 by default. */
 int absb_ivf_set_clustering(absb_ivf_t h, int niter, int max_points_per_centroid,
                             int min_points_per_centroid, int64_t seed);
+/* faiss ClusteringParameters.spherical: L2-normalise the centroids after the initial draw and after
+ * every Lloyd iteration (Clustering::post_process_centroids -> fvec_renorm_L2).  The struct default is
+ * false; faiss's index_factory switches it on for METRIC_INNER_PRODUCT IVF indexes — the
+ * `index train` call of /root/reference/Makefile:38-39 goes through index_factory (external, faiss
+ * unpinned: the Python index_factory mirrors that default, IndexIVFFlat(...) keeps false). */
+int absb_ivf_set_clustering_spherical(absb_ivf_t h, int spherical);
+/* In-place fvec_renorm_L2 of [n, d] device rows (zero rows stay zero): the step above, exported for
+ * the distributed trainer. */
+int absb_renorm_rows_dev(int device, int64_t n, int d, float* x_dev, void* stream);
 /* Index.train(x)  (SURVEY §8a a5): subsample, random-row init, niter Lloyd iterations with
  * arg-max-IP assignment, mean update, empty-cluster split. x is a HOST pointer [n,d]. */
 int absb_ivf_train(absb_ivf_t h, int64_t n, const float* x);

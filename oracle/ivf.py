@@ -125,11 +125,24 @@ class FlatIP:
 
 
 # ------------------------------------------------------------------ Clustering ----------------
+def renorm_l2(c: np.ndarray) -> np.ndarray:
+    """faiss fvec_renorm_L2 (Clustering::post_process_centroids when cp.spherical): every row with a
+    non-zero norm is scaled by 1 / sqrtf(|row|^2), in fp32; zero rows stay zero."""
+    c = np.ascontiguousarray(c, dtype=np.float32)
+    nr = np.einsum("ij,ij->i", c, c, dtype=np.float32)
+    inv = np.zeros_like(nr)
+    np.divide(np.float32(1.0), np.sqrt(nr, dtype=np.float32), out=inv, where=nr > 0)
+    return c * inv[:, None]
+
+
 def kmeans_train(x: np.ndarray, k: int, niter: int = 10, max_points_per_centroid: int = 256,
-                 seed: int = 1234, assign_fn=None, return_history: bool = False):
-    """faiss Clustering::train with an IndexFlatIP assignment index (spherical=False):
+                 seed: int = 1234, assign_fn=None, return_history: bool = False, spherical: bool = False):
+    """faiss Clustering::train with an IndexFlatIP assignment index:
     subsample to k*max_ppc rows with rand_perm(seed); centroids = rows rand_perm(seed+1)[:k];
-    niter x {assign = argmax IP, centroid = mean, split empty clusters}.  """
+    niter x {assign = argmax IP, centroid = mean, split empty clusters}.  
+    spherical (faiss ClusteringParameters.spherical; index_factory turns it on for inner-product IVF
+    indexes — external, unpinned, hence a switch): post_process_centroids = fvec_renorm_L2 after the
+    initial draw and after every iteration's mean + split."""
     x = np.ascontiguousarray(x, dtype=np.float32)
     n, d = x.shape
     assert n >= k, "faiss: number of training points should be at least as large as number of clusters"
@@ -142,6 +155,8 @@ def kmeans_train(x: np.ndarray, k: int, niter: int = 10, max_points_per_centroid
         return (cent, []) if return_history else cent
     perm = rand_perm(n, seed + 1)
     cent = np.ascontiguousarray(x[perm[:k]])
+    if spherical:
+        cent = renorm_l2(cent)
     lib = clib()
     history = []
     for _ in range(niter):
@@ -157,7 +172,7 @@ def kmeans_train(x: np.ndarray, k: int, niter: int = 10, max_points_per_centroid
         # faiss leaves an empty cluster's centroid at zero before the split copies over it
         nsplit = lib.orc_split_clusters(ctypes.c_int(d), ctypes.c_int64(k), ctypes.c_int64(n),
                                         _p(hassign, ctypes.c_float), _p(new, ctypes.c_float))
-        cent = new
+        cent = renorm_l2(new) if spherical else new
         history.append((assign, int(nsplit)))
     return (cent, history) if return_history else cent
 
@@ -192,6 +207,7 @@ class IVFFlat:
         self.d, self.nlist = d, nlist
         self.nprobe = 1
         self.niter, self.max_points_per_centroid, self.seed = 10, 256, 1234
+        self.spherical = False  # ClusteringParameters.spherical (faiss index_factory: True for inner product)
         self.centroids = None
         self.ntotal = 0
         self.codes = [np.zeros((0, d), dtype=np.float32) for _ in range(nlist)]
@@ -203,7 +219,8 @@ class IVFFlat:
         return self.centroids is not None
 
     def train(self, x):
-        self.centroids = kmeans_train(x, self.nlist, self.niter, self.max_points_per_centroid, self.seed)
+        self.centroids = kmeans_train(x, self.nlist, self.niter, self.max_points_per_centroid, self.seed,
+                                      spherical=self.spherical)
 
     def set_centroids(self, c):
         c = np.ascontiguousarray(c, dtype=np.float32)

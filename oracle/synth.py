@@ -34,6 +34,7 @@ SALT_QSRC = np.uint64(0x71737263)
 SALT_QDELTA = np.uint64(0x7164)
 
 KIND_CORPUS, KIND_CENTROIDS, KIND_QUERIES = 0, 1, 2
+KIND_UNIT = 4  # flag: the same integer row divided by its L2 norm (real-valued fp32, unit length)
 
 
 def _mix64(z: np.ndarray) -> np.ndarray:
@@ -94,6 +95,35 @@ def centroids(seed: int, nlist: int, d: int, list0: int = 0, n: int | None = Non
     n = nlist - list0 if n is None else n
     lists = np.arange(list0, list0 + n, dtype=np.int64)
     return mu_int(seed, lists, d).astype(np.float32) / np.float32(128.0)
+
+
+def unit_rows(v: np.ndarray) -> np.ndarray:
+    """int32 lattice rows -> float32 unit-norm rows, bit-identical to synth.cu's unit variant: the squared
+    norm (< 2^24 for d <= 1024) is an exact fp32 integer, sqrt and divide are correctly rounded IEEE
+    operations on both sides.  Real-valued embeddings that fp16 cannot hold exactly — what
+    `index fill` stores (/root/reference/Makefile:24-25) — yet regenerable by the oracle bit for bit."""
+    v = np.asarray(v, dtype=np.int32)
+    assert v.shape[1] <= 1024
+    ss = (v.astype(np.int64) * v).sum(axis=1)
+    den = np.sqrt(ss.astype(np.float32), dtype=np.float32)
+    out = np.zeros(v.shape, dtype=np.float32)
+    np.divide(v.astype(np.float32), den[:, None], out=out, where=(ss > 0)[:, None])
+    return out
+
+
+def corpus_rows_unit(seed: int, rows: np.ndarray, d: int, nlist: int) -> np.ndarray:
+    return unit_rows(corpus_int(seed, rows, d, nlist))
+
+
+def corpus_unit(seed: int, row0: int, n: int, d: int, nlist: int) -> np.ndarray:
+    return corpus_rows_unit(seed, np.arange(row0, row0 + n, dtype=np.int64), d, nlist)
+
+
+def queries_unit(seed: int, q0: int, n: int, d: int, nlist: int, corpus_rows_total: int) -> np.ndarray:
+    idx = np.arange(q0, q0 + n, dtype=np.int64)
+    src = query_src(seed, idx, corpus_rows_total)
+    delta = _bytes(np.uint64(seed) ^ SALT_QDELTA, idx, d) % 31 - 15
+    return unit_rows(np.clip(corpus_int(seed, src, d, nlist) + delta, -127, 127))
 
 
 def query_src(seed: int, idx: np.ndarray, corpus_rows_total: int) -> np.ndarray:

@@ -109,3 +109,88 @@ def test_flat_and_ids_parquet(tmp_path):
     q = str(tmp_path / "ids.parquet")
     fio.write_ids_parquet(q, ids)
     assert fio.read_ids_parquet(q) == ids
+
+
+def _hand_built_faiss_ondisk(tmp_path, free_slots=((4096, 64),)):
+    """index.faiss + ondisk.ivfdata assembled field by field the way faiss's own writers emit them
+    (write_index -> write_ivf_header -> write_InvertedLists -> OnDiskInvertedListsIOHook::write; every
+    WRITEVECTOR is `size_t count of ELEMENTS` + raw elements) — nothing here calls faiss_io's writer.
+    Lists have capacity > size and sit at non-monotonic offsets, as after faiss's in-place growth."""
+    d, nlist, nprobe = 4, 3, 2
+    rng = np.random.default_rng(5)
+    cent = rng.standard_normal((nlist, d)).astype(np.float32)
+    sizes, caps = [2, 0, 3], [4, 0, 3]
+    codes = [rng.standard_normal((n, d)).astype(np.float32) for n in sizes]
+    ids = [np.arange(10 * l, 10 * l + n, dtype=np.int64) for l, n in enumerate(sizes)]
+    code_size = d * 4
+    # data file: list 2 first, then a hole, then list 0 (codes [capacity * code_size], ids [capacity] i64)
+    offs = [256, 0xFFFFFFFFFFFFFFFF, 0]
+    tot = 256 + caps[0] * (code_size + 8)
+    data = bytearray(tot)
+    for l in (0, 2):
+        o = offs[l]
+        data[o:o + sizes[l] * code_size] = codes[l].tobytes()
+        io = o + caps[l] * code_size
+        data[io:io + sizes[l] * 8] = ids[l].tobytes()
+    (tmp_path / "ondisk.ivfdata").write_bytes(bytes(data))
+    hdr = lambda nt: struct.pack("<iqqqBi", d, nt, 1 << 20, 1 << 20, 1, 0)  # noqa: E731  d, ntotal, dummies, trained, metric
+    b = b"IwFl" + hdr(sum(sizes)) + struct.pack("<QQ", nlist, nprobe)
+    b += b"IxFI" + hdr(nlist) + struct.pack("<Q", nlist * d) + cent.tobytes()  # quantizer: xb as floats
+    b += struct.pack("<B", 0) + struct.pack("<Q", 0)  # DirectMap NoMap + empty array
+    b += b"ilod" + struct.pack("<QQ", nlist, code_size)
+    b += struct.pack("<Q", nlist)  # WRITEVECTOR(od->lists): nlist structs of {size, capacity, offset}
+    for l in range(nlist):
+        b += struct.pack("<QQQ", sizes[l], caps[l], offs[l])
+    b += struct.pack("<Q", len(free_slots))  # WRITEVECTOR(slots): structs of {offset, capacity}
+    for o, c in free_slots:
+        b += struct.pack("<QQ", o, c)
+    name = b"/some/build/dir/ondisk.ivfdata"  # faiss stores the path it was written with
+    b += struct.pack("<Q", len(name)) + name + struct.pack("<Q", tot)
+    (tmp_path / "index.faiss").write_bytes(b)
+    return str(tmp_path / "index.faiss"), cent, codes, ids, b
+
+
+def test_reads_hand_built_faiss_ondisk_file(tmp_path):
+    """the 'ilod' list table is nlist 24-byte structs (count = nlist, not 3 * nlist)."""
+    fio = _fio()
+    p, cent, codes, ids, _ = _hand_built_faiss_ondisk(tmp_path)
+    back = fio.read_ivfflat(p)
+    assert (back.d, back.nlist, back.nprobe, back.ntotal) == (4, 3, 2, 5)
+    assert np.array_equal(back.centroids, cent)
+    for l in range(3):
+        assert np.array_equal(back.codes[l], codes[l]) and np.array_equal(back.ids[l], ids[l])
+    assert back.ondisk["filename"].endswith("ondisk.ivfdata") and back.ondisk["lists"].shape == (3, 3)
+
+
+def test_writer_emits_the_hand_built_ondisk_layout(tmp_path):
+    """Our writer's index.faiss for the same lists parses with an independent field-by-field walk that
+    uses faiss's element counts (and is byte-identical to the hand-built file where layouts coincide)."""
+    fio = _fio()
+    d, nlist = 4, 3
+    rng = np.random.default_rng(6)
+    cent = rng.standard_normal((nlist, d)).astype(np.float32)
+    sizes = [2, 0, 3]
+    codes = [rng.standard_normal((n, d)).astype(np.float32) for n in sizes]
+    ids = [np.arange(10 * l, 10 * l + n, dtype=np.int64) for l, n in enumerate(sizes)]
+    p, dp = str(tmp_path / "index.faiss"), str(tmp_path / "ondisk.ivfdata")
+    fio.write_ivfflat(p, fio.IVFFlatData(d, nlist, 7, 0, True, cent, codes, ids), ondisk_path=dp)
+    b = open(p, "rb").read()
+    o = b.index(b"ilod") + 4
+    assert struct.unpack_from("<QQ", b, o) == (nlist, d * 4)
+    o += 16
+    assert struct.unpack_from("<Q", b, o)[0] == nlist, "lists vector must count structs, not u64 words"
+    o += 8
+    table = np.frombuffer(b, np.uint64, 3 * nlist, o).reshape(nlist, 3)
+    o += 24 * nlist
+    assert table[:, 0].tolist() == sizes and table[1, 2] == 0xFFFFFFFFFFFFFFFF
+    assert struct.unpack_from("<Q", b, o)[0] == 0  # no free slots
+    o += 8
+    n_name = struct.unpack_from("<Q", b, o)[0]
+    assert b[o + 8:o + 8 + n_name] == b"ondisk.ivfdata"
+    o += 8 + n_name
+    assert struct.unpack_from("<Q", b, o)[0] == sum(sizes) * (d * 4 + 8) and o + 8 == len(b)
+    raw = open(dp, "rb").read()
+    for l in (0, 2):
+        off = int(table[l, 2])
+        assert raw[off:off + sizes[l] * 16] == codes[l].tobytes()
+        assert raw[off + int(table[l, 1]) * 16: off + int(table[l, 1]) * 16 + sizes[l] * 8] == ids[l].tobytes()

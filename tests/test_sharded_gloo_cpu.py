@@ -6,6 +6,7 @@ import socket
 import sys
 
 import numpy as np
+import pytest
 import torch.multiprocessing as mp
 
 from conftest import ROOT
@@ -89,6 +90,13 @@ class OracleOps:
 
         return oivf.rand_perm(n, seed)
 
+    def renorm(self, cent):
+        import torch
+
+        from oracle import ivf as oivf
+
+        return torch.from_numpy(oivf.renorm_l2(cent.numpy()))
+
     def split_clusters(self, d, k, n, hassign, centroids):
         import ctypes
 
@@ -111,7 +119,7 @@ def _worker(rank, world, port, out_dir):
     P = importlib.import_module("abstracts-search_b200")
     from oracle import synth as osynth
 
-    d, nlist, n, nq, k, nprobe = 64, 16, 3000, 12, 7, 5
+    d, nlist, n, nq, k, nprobe = 64, 16, 3000, 11, 7, 5  # nq * k odd: the packed record needs its padding
     local = OracleShard(d, nlist, rank, world)
     local.set_centroids(osynth.centroids(7, nlist, d))
     sh = P.ShardedIndexIVFFlat(local, merge_fn=P.merge_partials_host)
@@ -126,7 +134,7 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def _build_worker(rank, world, port, out_dir):
+def _build_worker(rank, world, port, out_dir, spherical=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import importlib
@@ -147,6 +155,7 @@ def _build_worker(rank, world, port, out_dir):
     local = OracleShard(d, nlist, rank, world)
     local.cp = P.ClusteringParameters()
     local.cp.max_points_per_centroid = 200  # 16 * 200 = 3200 < 5000: the subsampling branch
+    local.cp.spherical = spherical
     local.device = "cpu"
     sh = P.ShardedIndexIVFFlat(local, merge_fn=P.merge_partials_host)
     ops = OracleOps(local)
@@ -165,17 +174,21 @@ def _build_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_distributed_train_and_add_world2_gloo(tmp_path):
+@pytest.mark.parametrize("spherical", [False, True])
+def test_distributed_train_and_add_world2_gloo(tmp_path, spherical):
     """train_distributed == single-process k-means (exact on the lattice corpus, where fp32 sums do not
-    depend on order); add_distributed routes every row to its list owner with global ids."""
+    depend on order), with and without ClusteringParameters.spherical; add_distributed routes every row
+    to its list owner with global ids."""
     world = 2
-    mp.spawn(_build_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_build_worker, args=(world, _free_port(), str(tmp_path), spherical), nprocs=world, join=True)
     from oracle import ivf as oivf
     from oracle import synth as osynth
 
     d, nlist, n, nq, k, nprobe = 64, 16, 5000, 9, 6, 4
     x = osynth.corpus(11, 0, n, d, nlist)
-    cent = oivf.kmeans_train(x, nlist, max_points_per_centroid=200)
+    cent = oivf.kmeans_train(x, nlist, max_points_per_centroid=200, spherical=spherical)
+    if spherical:
+        assert np.allclose(np.linalg.norm(cent, axis=1), 1.0, atol=1e-6)
     res = [np.load(tmp_path / f"b{r}.npz") for r in range(world)]
     for r in res:
         assert np.array_equal(r["cent"], cent), "distributed k-means differs from the single-process oracle"
@@ -203,7 +216,7 @@ def test_sharded_search_world2_gloo(tmp_path):
     from oracle import ivf as oivf
     from oracle import synth as osynth
 
-    d, nlist, n, nq, k, nprobe = 64, 16, 3000, 12, 7, 5
+    d, nlist, n, nq, k, nprobe = 64, 16, 3000, 11, 7, 5
     ref = oivf.IVFFlat(d, nlist)
     ref.set_centroids(osynth.centroids(7, nlist, d))
     ref.add(osynth.corpus(7, 0, n, d, nlist))

@@ -74,3 +74,26 @@ def test_tune_sweep_recall_pareto_and_params(tmp_path):
     assert choice["recall"] >= 0.99 and ix.nprobe == choice["nprobe"]
     assert json.load(open(tmp_path / "params.json"))["nprobe"] == choice["nprobe"]
     assert len(json.load(open(tmp_path / "untuned.json"))["sweep"]) == 4
+
+
+def test_train_index_reads_only_the_drawn_row_groups(tmp_path, monkeypatch):
+    """train_index must not decode the whole store — (file, row group) pairs come from the
+    parquet footers, and only the seeded draw is read (3 of 8 groups for 300 rows of 128-row groups)."""
+    P = _pkg()
+    d, nlist, n = 64, 8, 1000
+    x = osynth.corpus(3, 0, n, d, nlist)
+    P.store.write_shards(str(tmp_path / "data"), [str(i) for i in range(n)], x, shard_size=400, row_group_size=128)
+    groups = P.store.list_row_groups(str(tmp_path / "data"))
+    assert len(groups) == 10 and sum(g[2] for g in groups) == n  # 3 shards: 4 + 4 + 2 row groups
+    reads = []
+    real = P.store._read_group
+    monkeypatch.setattr(P.store, "_read_group", lambda path, g, dd, cols: (reads.append((path, g, tuple(cols))), real(path, g, dd, cols))[1])
+    ix = _OracleIndex(d, nlist)
+    seen = {}
+    ix.train = lambda xs: seen.setdefault("x", xs.copy())
+    rows = P.store.train_index(ix, str(tmp_path / "data"), max_rows=300, seed=7)
+    assert rows == seen["x"].shape[0] >= 300 and len(reads) == 3 and all(c == ("embedding",) for _, _, c in reads)
+    # the sample is the concatenation of exactly those groups, in draw order
+    want = np.concatenate([real(p, g, d, ("embedding",))[1] for p, g, _ in reads])
+    assert np.array_equal(seen["x"], want)
+    assert P.store.train_index(ix, str(tmp_path / "data"), max_rows=300, seed=7) == rows  # seeded: same draw
