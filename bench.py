@@ -87,6 +87,18 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--corpus", default="unit", choices=["unit", "lattice"],
+                    help="synthetic index contents: unit = real-valued L2-normalised fp32 rows (what `index fill` stores; not "
+                         "exactly representable in fp16, so the two-stage scan's error bound is genuinely exercised), "
+                         "lattice = integer/128 components (every fp32 score exact in any summation order: scores as well as "
+                         "ids are compared bit for bit with the oracle)")
+    ap.add_argument("--parity-queries", type=int, default=-1,
+                    help="queries of the untimed oracle parity leg (half taken from the step's GPU-encoded embeddings, half "
+                         "synthetic perturbed corpus rows); -1 = auto (<= 32, bounded by the rows the oracle must regenerate), 0 = off")
+    ap.add_argument("--skip-secondary", action="store_true",
+                    help="skip the secondary metrics (bulk encode, Index.add / k-means rates, 10M-row search) measured before "
+                         "the main index is built")
+    ap.add_argument("--secondary-rows", type=int, default=10_000_000, help="rows per GPU of the BASELINE configs[2] search index")
     return ap.parse_args()
 
 
@@ -105,7 +117,8 @@ def peaks():
 class CpuPath:
     """torch-CPU fp32 stella encoder + C/OpenMP IVF over the probed lists of a bounded query sample."""
 
-    def __init__(self, total_rows: int, nlist: int, nprobe: int, k: int, nq: int, tokens: int, d: int = 1024):
+    def __init__(self, total_rows: int, nlist: int, nprobe: int, k: int, nq: int, tokens: int, d: int = 1024,
+                 corpus: str = "unit"):
         import torch
 
         from oracle import encoder as oenc
@@ -139,19 +152,7 @@ class CpuPath:
         self.o = oivf.IVFFlat(d, nlist)
         self.o.set_centroids(cent)
         _, Ic = self.o.coarse(emb, nprobe, impl="c")
-        want = np.unique(Ic)
-        rows_l, lists_l = [], []
-        for r0 in range(0, total_rows, 1 << 22):
-            rows = np.arange(r0, min(r0 + (1 << 22), total_rows), dtype=np.int64)
-            c = osynth.cluster_of(SEED, rows, nlist)
-            m = np.isin(c, want)
-            rows_l.append(rows[m])
-            lists_l.append(c[m].astype(np.int64))
-        rows, lists = np.concatenate(rows_l), np.concatenate(lists_l)
-        for r0 in range(0, len(rows), 32768):
-            r, l = rows[r0:r0 + 32768], lists[r0:r0 + 32768]
-            self.o.add(osynth.corpus_rows(SEED, r, d, nlist), ids=r, list_ids=l)
-        self.o._as_csr()
+        oracle_fill_lists(self.o, np.unique(Ic), total_rows, nlist, d, corpus)
         self.vectors_per_query = float(self.o.list_sizes()[Ic].sum()) / nq
         self.setup_s = time.time() - t0
 
@@ -164,6 +165,30 @@ class CpuPath:
         return (f"{self.nq} queries x {self.ids.shape[1]} tokens per step: torch-CPU fp32 Qwen2-1.5B forward + C/OpenMP "
                 f"coarse over {self.o.nlist} centroids + scan of the probed lists "
                 f"({self.vectors_per_query:.0f} vectors/query)")
+
+
+def oracle_fill_lists(o, want_lists, total_rows: int, nlist: int, d: int, corpus: str) -> int:
+    """Rebuild exactly the inverted lists `want_lists` of the synthetic index inside the oracle index `o`
+    from oracle/synth.py alone (rows in ascending order = the insertion order of the bench's fill): the
+    oracle never sees product memory.  Returns the number of rows regenerated."""
+    from oracle import synth as osynth
+
+    want = np.unique(np.asarray(want_lists, dtype=np.int64))
+    want = want[want >= 0]
+    rows_l, lists_l = [], []
+    for r0 in range(0, total_rows, 1 << 22):
+        rows = np.arange(r0, min(r0 + (1 << 22), total_rows), dtype=np.int64)
+        c = osynth.cluster_of(SEED, rows, nlist)
+        m = np.isin(c, want)
+        rows_l.append(rows[m])
+        lists_l.append(c[m].astype(np.int64))
+    rows, lists = np.concatenate(rows_l), np.concatenate(lists_l)
+    gen = osynth.corpus_rows_unit if corpus == "unit" else osynth.corpus_rows
+    for r0 in range(0, len(rows), 32768):
+        r, l = rows[r0:r0 + 32768], lists[r0:r0 + 32768]
+        o.add(gen(SEED, r, d, nlist), ids=r, list_ids=l)
+    o._as_csr()
+    return int(len(rows))
 
 
 def auto_cpu_sample(total_rows: int, nlist: int, nprobe: int) -> int:
@@ -187,7 +212,7 @@ def run_reference(args, rank: int, world: int):
         return
     total_rows = args.rows_per_gpu * world
     nq = args.cpu_sample or auto_cpu_sample(total_rows, args.nlist, args.nprobe)
-    cp = CpuPath(total_rows, args.nlist, args.nprobe, args.k, nq, args.query_tokens)
+    cp = CpuPath(total_rows, args.nlist, args.nprobe, args.k, nq, args.query_tokens, corpus=args.corpus)
     qps, s_per_step = time_cpu(cp, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -209,6 +234,8 @@ def workload_config(args, world: int):
                      f"{total} x 1024 fp32 rows sharded by inverted list over {world} GPU(s) "
                      f"({args.rows_per_gpu} rows = {args.rows_per_gpu * 4104 / 1e9:.0f} GB per GPU; 8 GPUs = the 207M index)"),
         "rows_total": total, "rows_per_gpu": args.rows_per_gpu, "nlist": args.nlist, "nprobe": args.nprobe, "k": args.k,
+        "corpus": ("unit: real-valued L2-normalised fp32 rows from the counter-based generator (oracle/synth.py regenerates "
+                   "them bit for bit)" if args.corpus == "unit" else "lattice: integer/128 components, fp32 scores exact"),
         "queries_per_step": args.batch, "query_tokens": args.query_tokens,
         "parallelism": f"encode dp{world}; index sharded by list x{world}; 1 all-gather of partial top-k",
         "l2": "inputs larger than L2: >= 20 GB of list codes and 3.1 GB of weights stream per step (L2 = 126 MB)",
@@ -270,9 +297,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def build_shard(P, torch, args, rank: int, world: int, dev: int):
+def build_shard(P, torch, args, rank: int, world: int, dev: int, rows_per_gpu: int | None = None):
     d, nlist = 1024, args.nlist
-    total = args.rows_per_gpu * world
+    total = (rows_per_gpu or args.rows_per_gpu) * world
     ix = P.index_factory(d, f"IVF{nlist},Flat", P.METRIC_INNER_PRODUCT, device=dev)
     ix.set_tunables(scan_chunk=args.scan_chunk, coarse_impl=args.coarse_impl, scan_ctas_per_sm=args.scan_ctas)
     ix.set_scan_order(bool(args.scan_order))
@@ -294,7 +321,7 @@ def build_shard(P, torch, args, rank: int, world: int, dev: int):
             lists = lists[sel].contiguous()
         else:
             rows = torch.arange(r0, r0 + n, dtype=torch.int64, device=f"cuda:{dev}")
-        x = P.synth.corpus_rows(SEED, rows, d, nlist, out=xbuf)
+        x = P.synth.corpus_rows(SEED, rows, d, nlist, out=xbuf, unit=args.corpus == "unit")
         ix.add_core(x, rows, lists)
     torch.cuda.synchronize()
     del xbuf
@@ -304,6 +331,242 @@ def build_shard(P, torch, args, rank: int, world: int, dev: int):
         # (in place) so that the scan's work items are scan_chunk vectors long instead of one page
         ix.compact()
     return ix, time.time() - t0
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle parity at the configuration the metric is quoted on (untimed; rank 0 checks, all ranks search)
+# ------------------------------------------------------------------------------------------------
+def auto_parity_queries(total_rows: int, nlist: int, nprobe: int) -> int:
+    # bounded by the rows the oracle has to regenerate (~2.2M rows = 9 GB of fp32 at the 207M index)
+    per_q = max(1.0, total_rows / nlist * nprobe)
+    return int(max(4, min(32, (2_200_000 // per_q) // 2 * 2)))
+
+
+def parity_sample(args, P, torch, dist, rank, world, ix, search_fn, emb_step, device):
+    """The north star's "top-k ids bit-exact at matched nprobe" (reference call sites
+    /root/reference/Makefile:31-32, README.md:16,28) checked INSIDE the bench run, on the index the
+    number is measured on: a sample of queries — half of them embeddings the GPU encoder produced in
+    the timed step, half synthetic perturbed corpus rows (they have true near neighbours) — goes through
+    the product's whole search (coarse + fine scan + exchange + merge, every rank taking part) once per
+    scan mode, and through the oracle (C restatement: coarse over all centroids, scan of the probed
+    lists regenerated from oracle/synth.py, k-best).  ids must be equal wherever the fp64 margin between
+    neighbouring ranks exceeds the fp32 rounding bound (2e-5; such queries are counted, not hidden);
+    scores within 2e-5, and bit-identical on the lattice corpus for the lattice queries."""
+    n_total = args.parity_queries if args.parity_queries > 0 else auto_parity_queries(args.rows_per_gpu * world, args.nlist, args.nprobe)
+    n_enc = min(n_total // 2, emb_step.shape[0])
+    n_syn = n_total - n_enc
+    d, k, nprobe, nlist = 1024, args.k, args.nprobe, args.nlist
+    total_rows = args.rows_per_gpu * world
+    unit = args.corpus == "unit"
+    q_syn = P.synth.queries(SEED, 1000, n_syn, d, nlist, total_rows, device=int(device.split(":")[1]), unit=unit)
+    q_dev = torch.cat([emb_step[:n_enc], q_syn], 0).contiguous()
+    modes = ([("two_stage_%d" % args.two_stage, args.two_stage)] if args.two_stage else []) + [("single_pass", 0)]
+    got = {}
+    for name, ts in modes:
+        ix.set_two_stage(ts)  # shadow codes stay; 0 = single-pass fp32 scan over the same lists
+        D, I = search_fn(q_dev)
+        got[name] = (D.cpu().numpy(), I.cpu().numpy())
+    ix.set_two_stage(args.two_stage)
+    _, Ic_gpu = ix.coarse(q_dev, nprobe)
+    Ic_gpu = Ic_gpu.cpu().numpy()
+    if rank != 0:
+        return None
+    from oracle import ivf as oivf
+    from oracle import synth as osynth
+
+    t0 = time.time()
+    q = q_dev.cpu().numpy()
+    cent = np.empty((nlist, d), dtype=np.float32)
+    for l0 in range(0, nlist, 8192):
+        cent[l0:l0 + 8192] = osynth.centroids(SEED, nlist, d, l0, min(8192, nlist - l0))
+    o = oivf.IVFFlat(d, nlist)
+    o.set_centroids(cent)
+    _, Ic = o.coarse(q, nprobe, impl="c")
+    # coarse ties / near-ties: a query whose nprobe-th and (nprobe+1)-th centroid scores are closer than
+    # the fp32 rounding bound may legitimately probe a different last list; it is compared on the
+    # oracle's own probe set only if the GPU chose the same one
+    same_probe = np.array([np.array_equal(np.sort(a), np.sort(b)) for a, b in zip(Ic, Ic_gpu)])
+    coarse_order_equal = bool(np.array_equal(Ic, Ic_gpu))
+    rows_regen = oracle_fill_lists(o, Ic, total_rows, nlist, d, args.corpus)
+    Do, Io = o.search_preassigned(q, k, Ic, impl="c")
+    # fp64 margins over each query's probed vectors
+    off, codes, ids = o._as_csr()
+    safe = np.ones(len(q), dtype=bool)
+    for i in range(len(q)):
+        sc = np.concatenate([codes[off[l]:off[l + 1]].astype(np.float64) @ q[i].astype(np.float64) for l in Ic[i]])
+        top = np.sort(sc)[::-1][:k + 1]
+        if len(top) > 1 and np.min(top[:-1] - top[1:]) <= 2e-5:
+            safe[i] = False
+    out = {"queries": int(len(q)), "from_gpu_encoder": int(n_enc), "synthetic_perturbed_rows": int(n_syn),
+           "rows_total": int(total_rows), "oracle_rows_regenerated": rows_regen, "nprobe": nprobe, "k": k,
+           "corpus": args.corpus, "coarse_ids_equal": coarse_order_equal,
+           "queries_with_other_probe_set": int((~same_probe).sum()), "ambiguous_queries_fp64_margin_below_2e-5": int((~safe).sum()),
+           "oracle": "oracle/ivf_oracle.c (orc_coarse + orc_ivf_scan) over lists regenerated by oracle/synth.py", "modes": {}}
+    check = same_probe & safe
+    ids_ok, scores_ok, bit_ok = True, True, True
+    for name, (Dg, Ig) in got.items():
+        ids_eq = bool(np.array_equal(Ig[check], Io[check]))
+        # ambiguous queries: same id SET within the top-k is still required unless the k/k+1 gap itself is the tie
+        diff = float(np.max(np.abs(Dg[same_probe] - Do[same_probe]))) if same_probe.any() else 0.0
+        bit = bool(np.array_equal(Dg[check], Do[check]))
+        out["modes"][name] = {"ids_equal": ids_eq, "scores_max_abs_diff": diff, "scores_bit_identical": bit,
+                              "queries_compared": int(check.sum())}
+        ids_ok &= ids_eq
+        scores_ok &= diff <= 2e-5
+        bit_ok &= bit
+    syn = np.arange(len(q)) >= n_enc
+    if args.corpus == "lattice" and (check & syn).any():
+        # lattice rows x lattice queries: every fp32 partial sum is exact -> scores must match bit for bit
+        m = check & syn
+        out["lattice_queries_scores_bit_identical"] = bool(all(np.array_equal(Dg[m], Do[m]) for Dg, _ in got.values()))
+        scores_ok &= out["lattice_queries_scores_bit_identical"]
+    if len(got) == 2:
+        (Da, Ia), (Db, Ib) = got.values()
+        out["two_stage_equals_single_pass_bitwise"] = bool(np.array_equal(Ia, Ib) and np.array_equal(Da, Db))
+        ids_ok &= out["two_stage_equals_single_pass_bitwise"]
+    out.update({"ids_equal": ids_ok, "scores_equal": scores_ok, "scores_bit_identical": bit_ok, "seconds": time.time() - t0})
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# secondary metrics, measured in the same run before the main index takes the memory
+# ------------------------------------------------------------------------------------------------
+def secondary_metrics(args, P, torch, dist, enc, rank, world, dev):
+    """The other rates the north star asks for at every N (embeddings/s, index build, the 10M-row
+    single-GPU search config), each a few hundred ms of GPU time:
+      encode_b32_s256   BASELINE configs[1]: bulk encode, b = 32 x 256-token abstracts per GPU per step (DP)
+      add / kmeans      BASELINE configs[4]: Index.add (assign GEMM + append; rows spread over ranks and routed to
+                        the list owners by ONE NCCL all-to-all at N > 1) and k-means (ONE all-reduce of the
+                        centroid sums per iteration at N > 1); the resulting list sizes are checked
+                        against the histogram oracle/synth.py predicts for the same rows
+      search_10M        BASELINE configs[2]: IVF65536,Flat search over 10M rows per GPU, nprobe 32, k 10."""
+    device = f"cuda:{dev}"
+    d, nlist = 1024, args.nlist
+    out = {}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(steps):
+            fn(warm + i)
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1)) / steps
+
+    # ---- bulk encode, b = 32 x 256 tokens (and 512, stella's max_seq_length) ----------------------
+    g = torch.Generator().manual_seed(99 + rank)
+    for S in (256, 512):
+        B = 32
+        ids = torch.randint(0, P.STELLA_1_5B.vocab_size, (4, B, S), generator=g, dtype=torch.int64).to(device)
+        mask = torch.ones((B, S), dtype=torch.int32, device=device)
+        ms = timed(lambda i: enc.encode_tokens(ids[i % 4], mask, normalize_embeddings=True), 5, 3)
+        fl = enc.last_stats()["flops"]
+        out[f"encode_b32_s{S}"] = {"embeddings_per_s": B * world / (ms * 1e-3), "ms_per_step": ms, "unit": "embeddings/s",
+                                   "tflops_per_gpu": fl / (ms * 1e-3) / 1e12,
+                                   "frac_of_sustained_bf16": fl / (ms * 1e-3) / 1e12 / peaks()["tf_sustained"],
+                                   "parallelism": f"dp{world}, no collective"}
+        del ids, mask
+    # ---- index build: k-means iterations and Index.add ------------------------------------------
+    n_add = 1 << 20
+    ix = P.index_factory(d, f"IVF{nlist},Flat", P.METRIC_INNER_PRODUCT, device=dev)
+    ix.set_tunables(coarse_impl=args.coarse_impl)
+    sh = None
+    if world > 1:
+        ix.set_shard(rank, world)
+        sh = P.ShardedIndexIVFFlat(ix)
+    unit = args.corpus == "unit"
+    xt = P.synth.corpus(SEED + 1, rank * n_add, n_add, d, nlist, device=dev, unit=unit)
+    ix.cp.niter = 2
+    ix.cp.max_points_per_centroid = 1 << 30
+    barrier()
+    t0 = time.perf_counter()
+    if sh is not None:
+        sh.train_distributed(xt)
+    else:
+        ix.train(xt)
+    barrier()
+    train_s = max_over_ranks(time.perf_counter() - t0)
+    cent = ix.get_centroids()
+    out["kmeans"] = {"rows_x_iters_per_s": n_add * world * 2 / train_s, "seconds": train_s, "rows_per_gpu": n_add, "niter": 2,
+                     "spherical": bool(ix.cp.spherical), "centroids_finite": bool(np.isfinite(cent).all()),
+                     "centroid_norm_min_max": [float(np.linalg.norm(cent, axis=1).min()), float(np.linalg.norm(cent, axis=1).max())],
+                     "collective": "1 all-reduce of [nlist, d] sums + counts per iteration (NCCL)" if world > 1 else "none"}
+    del xt, cent
+    ix.set_centroids(P.synth.centroids(SEED, nlist, d, device=dev))  # the generating centres: known assignment
+    steps_add, warm_add = 3, 1
+    xb = [P.synth.corpus(SEED, (s_ * world + rank) * n_add, n_add, d, nlist, device=dev, unit=unit) for s_ in range(steps_add + warm_add)]
+
+    def add_step(i):
+        if sh is not None:
+            sh.add_distributed(xb[i])
+        else:
+            ix.add(xb[i])
+
+    ms = timed(add_step, steps_add, warm_add)
+    sizes = torch.from_numpy(ix.list_sizes()).to(device)
+    if world > 1:
+        dist.all_reduce(sizes)
+    hist_ok = None
+    if rank == 0:
+        from oracle import synth as osynth
+
+        rows = np.arange(0, (steps_add + warm_add) * world * n_add, dtype=np.int64)
+        want = np.bincount(osynth.cluster_of(SEED, rows, nlist), minlength=nlist)
+        hist_ok = bool(np.array_equal(want, sizes.cpu().numpy()))
+    out["add"] = {"rows_per_s": n_add * world / (ms * 1e-3), "ms_per_step": ms, "rows_per_step_per_gpu": n_add,
+                  "assign_tflops_per_gpu": n_add * 6 * 2.0 * nlist * d / (ms * 1e-3) / 1e12,
+                  "list_sizes_equal_generator_histogram": hist_ok,
+                  "collective": "1 all-to-all of (vector, id, list) to the list owners (NCCL)" if world > 1 else "none"}
+    del xb, ix, sh, sizes
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    # ---- BASELINE configs[2]: IVF65536,Flat search over 10M rows per GPU --------------------------
+    ix, _ = build_shard(P, torch, args, rank, world, dev, rows_per_gpu=args.secondary_rows)
+    ix.nprobe = args.nprobe
+    sh = P.ShardedIndexIVFFlat(ix) if world > 1 else None
+    if sh is not None:
+        sh.nprobe = args.nprobe
+        if args.exchange == "peer":
+            sh.use_peer_exchange(max_results=args.batch * args.k, strict=False)
+    total = args.secondary_rows * world
+    q = P.synth.queries(SEED, 0, args.batch, d, nlist, total, device=dev, unit=unit)  # perturbed rows of THIS corpus
+    fn = (lambda i: sh.search(q, args.k)) if sh is not None else (lambda i: ix.search(q, args.k))
+    ms = timed(fn, 10, 3)
+    ix.set_profile(2)
+    timed(fn, 5, 0)
+    prof = ix.get_profile()
+    ix.set_profile(0)
+    st = ix.last_stats()
+    moved = st["vectors"] * 2048 + args.batch * args.two_stage * 4104 if args.two_stage else st["bytes"]
+    scan_ms = prof["scan_ms"] / 5
+    out["search_10M"] = {"qps": args.batch / (ms * 1e-3), "ms_per_step": ms, "rows_total": total, "unit": "queries/s",
+                         "vectors_scanned_per_query_per_gpu": st["vectors"] / args.batch,
+                         "scan_ms": scan_ms, "scan_gbs_bytes_moved": moved / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None,
+                         "scan_frac_of_hbm": moved / (scan_ms * 1e-3) / 1e9 / peaks()["hbm_gbs"] if scan_ms > 0 else None,
+                         "coarse_gemm_ms": prof["coarse_gemm_ms"] / 5, "other_ms": prof["other_ms"] / 5,
+                         "two_stage_shortlist": args.two_stage, "search only (queries resident, no encoder)": True}
+    del ix, sh, q
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args, rank: int, world: int, local_rank: int):
@@ -323,6 +586,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if args.gemm_variant:
         importlib.import_module("abstracts-search_b200.encoder").gemm_set_variant(args.gemm_variant)
     enc = P.Encoder(config=P.STELLA_1_5B, device=device, random_init_seed=0)
+    secondary = None
+    if not args.skip_secondary:
+        secondary = secondary_metrics(args, P, torch, dist, enc, rank, world, dev)
     # The fp16 shadow codes of the two-stage scan take +50% index memory (159 GB of 180 GB for the
     # 25.9M-row shard).  If any rank cannot allocate them, every rank rebuilds its shard without them
     # and the step uses the single-pass scan: same results, config.two_stage_shortlist says which ran.
@@ -369,13 +635,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     lo, hi = rank * per, (rank + 1) * per
     emb_all = torch.empty((nq, 1024), dtype=torch.float32, device=device)
 
+    last = {}
+
     def step_dev():
         e = enc.encode_tokens(ids_d[lo:hi], mask_d[lo:hi], normalize_embeddings=True)
         if world > 1:
             if px_emb is not None:
-                return sh.search(px_emb.allgather(e).view(nq, 1024), k)
+                last["emb"] = px_emb.allgather(e).view(nq, 1024)
+                return sh.search(last["emb"], k)
             dist.all_gather_into_tensor(emb_all, e)
+            last["emb"] = emb_all
             return sh.search(emb_all, k)
+        last["emb"] = e
         return ix.search(e, k)
 
     # ---- optional two-stream software pipeline over consecutive batches ---------------------------
@@ -561,19 +832,35 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         phases, dominant = {}, None
     load_traffic(rooflines)
 
+    # ---- oracle parity on a sample of this run's queries, both scan modes (untimed) -----------------
+    fallbacks = ix.two_stage_fallbacks() if args.two_stage else 0  # of the timed + warm-up steps, before the parity leg
+    if world > 1:
+        t = torch.tensor([fallbacks], dtype=torch.int64, device=device)
+        dist.all_reduce(t)
+        fallbacks = int(t.item())
+    parity = None
+    if args.parity_queries != 0:
+        step_dev()
+        emb_step = last["emb"].clone()
+        parity = parity_sample(args, P, torch, dist, rank, world, ix, (lambda qd: sh.search(qd, k)) if world > 1 else (lambda qd: ix.search(qd, k)),
+                               emb_step, device)
+        if world > 1:
+            dist.barrier()
+
     if rank != 0:
         return
     # ---- CPU baseline (oracle port) on a bounded sample ----------------------------------------
     cpu = None
     if world == 1 and not args.skip_cpu_baseline:
         n_cpu = args.cpu_sample or auto_cpu_sample(args.rows_per_gpu, args.nlist, args.nprobe)
-        cp = CpuPath(args.rows_per_gpu, args.nlist, args.nprobe, k, n_cpu, S)
+        cp = CpuPath(args.rows_per_gpu, args.nlist, args.nprobe, k, n_cpu, S, corpus=args.corpus)
         qps, _ = time_cpu(cp, 2, 1)
         cpu = {"value": qps, "unit": UNIT, "cores": cp.cores, "kind": "port", "sample": cp.describe()}
 
     cfg = workload_config(args, world)
     cfg.update({"two_stage_shortlist": args.two_stage,
-                "two_stage_fallback_queries_total": (ix.two_stage_fallbacks() if args.two_stage else None),
+                "two_stage_fallback_queries_total": (fallbacks if args.two_stage else None),
+                "two_stage_fallback_note": "summed over ranks, warm-up + timed + instrumented + e2e steps, %d queries each" % nq,
                 "pipeline": ("two streams: encode of batch i+1 overlaps search of batch i; K batches timed over K+1 iterations "
                              "including fill and drain" if args.pipeline else "none: encode then search, one stream"),
                 "exchange": exchange, "index_build_s": build_s, "distinct_probed_lists_per_step": distinct_lists,
@@ -586,6 +873,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "roofline": dict(rooflines[dominant], kernel=dominant) if dominant else None,
         "rooflines": rooflines, "phases_ms_per_step": phases, "cpu_baseline": cpu,
+        "parity_sample": parity, "secondary": secondary,
     }
     emit(line)
 
