@@ -116,6 +116,7 @@ _SIGS = {
     "absb_merge_shards_dev": ([c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p], c_int),
     "absb_ivf_set_tunables": ([_H, c_int, c_int, c_int], c_int),
     "absb_ivf_set_scan_order": ([_H, c_int], c_int),
+    "absb_ivf_set_scan_impl": ([_H, c_int, c_int, c_int, c_int], c_int),
     "absb_ivf_set_two_stage": ([_H, c_int], c_int),
     "absb_ivf_two_stage_fallbacks": ([_H, _PI64], c_int),
     "absb_ivf_last_stats": ([_H, _PI64, _PI64, _PI64, _PI64], c_int),

@@ -807,6 +807,28 @@ int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int sca
   ABSB_API_END
 }
 
+int absb_ivf_set_scan_impl(absb_ivf_t h, int impl, int ring_warps, int ring_depth, int ring_stage_vecs) {
+  ABSB_API_BEGIN
+  NEED(h);
+  ABSB_CHECK(impl >= -1 && impl <= 1, ABSB_ERR_INVALID, "scan impl %d", impl);
+  IvfIndex& ix = h->ix;
+  if (impl >= 0) ix.scan_impl = impl;
+  if (ring_warps > 0) {
+    ABSB_CHECK(ring_warps <= 16, ABSB_ERR_INVALID, "ring warps %d", ring_warps);
+    ix.ring.warps = ring_warps;
+  }
+  if (ring_depth > 0) {
+    ABSB_CHECK(ring_depth >= 2 && ring_depth <= 7, ABSB_ERR_INVALID, "ring depth %d outside [2,7]", ring_depth);
+    ix.ring.depth = ring_depth;
+  }
+  if (ring_stage_vecs > 0) {
+    ABSB_CHECK(ring_stage_vecs == 1 || ring_stage_vecs == 2, ABSB_ERR_INVALID, "ring stage of %d fp32 vectors (1 or 2)",
+               ring_stage_vecs);
+    ix.ring.stage_vecs = ring_stage_vecs;
+  }
+  ABSB_API_END
+}
+
 int absb_ivf_set_scan_order(absb_ivf_t h, int list_major) {
   ABSB_API_BEGIN
   NEED(h);
@@ -901,7 +923,7 @@ int absb_ivf_time_scan(absb_ivf_t h, int iters, void* stream, float* ms_mean) {
   for (int i = 0; i < iters; ++i) {
     ABSB_CUDA(cudaMemsetAsync(ix.last_scan.queue_counter, 0, sizeof(int), st));
     ABSB_CUDA(cudaEventRecord(e0, st));
-    launch_scan(ix.last_scan, st);
+    ix.run_scan(ix.last_scan, st);
     ABSB_CUDA(cudaEventRecord(e1, st));
     ABSB_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;

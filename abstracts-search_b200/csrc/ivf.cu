@@ -1068,7 +1068,13 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
       s16.ctas_per_sm = scan_ctas_per_sm;
       {
         Span sp(this, st, 0);
-        launch_scan16(s16, st);
+        if (use_ring()) {
+          ScanRing r16 = ring;
+          r16.stage_vecs = ring.stage_vecs * 2;  // same stage bytes as the fp32 ring
+          launch_scan16_ring(s16, r16, st);
+        } else {
+          launch_scan16(s16, st);
+        }
       }
       {
         Span sp(this, st, 2);
@@ -1103,7 +1109,7 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
       a3.order = nullptr;
       {
         Span sp(this, st, 0);
-        launch_scan(a3, st);
+        run_scan(a3, st);
       }
       {
         Span sp(this, st, 2);
@@ -1124,7 +1130,7 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
     }
     {
       Span sp(this, st, 0);
-      launch_scan(a, st);
+      run_scan(a, st);
     }
     {
       Span sp(this, st, 2);

@@ -51,6 +51,15 @@ struct ScanLaunch {
   int ctas_per_sm;  // <= 0: occupancy query
 };
 
+// Geometry of the shared-memory ring scan (ivf_scan_ring.cu): every warp of a CTA owns `depth` stages of
+// `stage_vecs` vectors (fp32: 1 or 2 = 4 / 8 KB; fp16 shadow codes: 2 or 4 = 4 / 8 KB) filled by cp.async.bulk.
+struct ScanRing {
+  int warps = 4;
+  int depth = 4;
+  int stage_vecs = 2;  // fp32 vectors per stage; the fp16 pass stages twice as many (same bytes)
+};
+void launch_scan_ring(const ScanLaunch& a, const ScanRing& r, cudaStream_t st);
+
 // Scratch of the list-major queue order (all [npairs + 1] except order [max_items]).
 struct PlanOrderWs {
   unsigned *keys, *keys_sorted;
@@ -82,6 +91,7 @@ struct Scan16Launch {
   int sm_count, ctas_per_sm;
 };
 void launch_scan16(const Scan16Launch& a, cudaStream_t st);
+void launch_scan16_ring(const Scan16Launch& a, const ScanRing& r, cudaStream_t st);
 // shortlist G [nq, K] (global slot numbers, -1 = none) -> one single-vector fp32 work item each
 void launch_rescore_items(const ListTable& lt, int nq, int K, const long long* G, ScanItem* items, int* q_begin,
                           int* n_items, int* queue_counter, cudaStream_t st);

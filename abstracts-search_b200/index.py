@@ -257,6 +257,11 @@ class IndexIVFFlat:
         check(lib().absb_ivf_two_stage_fallbacks(self._h, byref(n)))
         return n.value
 
+    def set_scan_impl(self, impl: int = -1, ring_warps: int = 0, ring_depth: int = 0, ring_stage_vecs: int = 0):
+        """Fine-scan kernel: 1 = shared-memory ring fed by the bulk-copy engine (default for d = 1024; small
+        CTAs that fit beside the encoder's GEMM CTAs), 0 = register-resident scan.  Same results."""
+        check(lib().absb_ivf_set_scan_impl(self._h, int(impl), int(ring_warps), int(ring_depth), int(ring_stage_vecs)))
+
     def set_scan_order(self, list_major: bool = True):
         """Work-queue order of the fine scan: list-major (default, L2 reuse across queries) or query-major."""
         check(lib().absb_ivf_set_scan_order(self._h, 1 if list_major else 0))

@@ -349,9 +349,10 @@ def parity_sample(args, P, torch, dist, rank, world, ix, search_fn, emb_step, de
     the timed step, half synthetic perturbed corpus rows (they have true near neighbours) — goes through
     the product's whole search (coarse + fine scan + exchange + merge, every rank taking part) once per
     scan mode, and through the oracle (C restatement: coarse over all centroids, scan of the probed
-    lists regenerated from oracle/synth.py, k-best).  ids must be equal wherever the fp64 margin between
-    neighbouring ranks exceeds the fp32 rounding bound (2e-5; such queries are counted, not hidden);
-    scores within 2e-5, and bit-identical on the lattice corpus for the lattice queries."""
+    lists regenerated from oracle/synth.py, k-best).  ids must be identical; a query whose ids differ is
+    accepted only as a near-tie (at every rank the two ids' fp64 scores agree within the fp32 rounding
+    bound, 2e-6 — counted, not hidden); scores within 2e-5, and bit-identical on the lattice corpus for the
+    lattice queries."""
     n_total = args.parity_queries if args.parity_queries > 0 else auto_parity_queries(args.rows_per_gpu * world, args.nlist, args.nprobe)
     n_enc = min(n_total // 2, emb_step.shape[0])
     n_syn = n_total - n_enc
@@ -389,36 +390,45 @@ def parity_sample(args, P, torch, dist, rank, world, ix, search_fn, emb_step, de
     coarse_order_equal = bool(np.array_equal(Ic, Ic_gpu))
     rows_regen = oracle_fill_lists(o, Ic, total_rows, nlist, d, args.corpus)
     Do, Io = o.search_preassigned(q, k, Ic, impl="c")
-    # fp64 margins over each query's probed vectors
+    # fp64 scores of each query's probed vectors: the referee for near-ties
     off, codes, ids = o._as_csr()
-    safe = np.ones(len(q), dtype=bool)
+    TOL = 2e-6  # fp32 rounding of a 1024-term inner product of unit vectors (observed: 2.4e-7)
+    s64 = []
     for i in range(len(q)):
         sc = np.concatenate([codes[off[l]:off[l + 1]].astype(np.float64) @ q[i].astype(np.float64) for l in Ic[i]])
-        top = np.sort(sc)[::-1][:k + 1]
-        if len(top) > 1 and np.min(top[:-1] - top[1:]) <= 2e-5:
-            safe[i] = False
+        idv = np.concatenate([ids[off[l]:off[l + 1]] for l in Ic[i]])
+        s64.append(dict(zip(idv.tolist(), sc.tolist())))
     out = {"queries": int(len(q)), "from_gpu_encoder": int(n_enc), "synthetic_perturbed_rows": int(n_syn),
            "rows_total": int(total_rows), "oracle_rows_regenerated": rows_regen, "nprobe": nprobe, "k": k,
-           "corpus": args.corpus, "coarse_ids_equal": coarse_order_equal,
-           "queries_with_other_probe_set": int((~same_probe).sum()), "ambiguous_queries_fp64_margin_below_2e-5": int((~safe).sum()),
+           "corpus": args.corpus, "coarse_ids_equal_in_order": coarse_order_equal,
+           "queries_with_other_probe_set": int((~same_probe).sum()), "near_tie_tolerance": TOL,
            "oracle": "oracle/ivf_oracle.c (orc_coarse + orc_ivf_scan) over lists regenerated by oracle/synth.py", "modes": {}}
-    check = same_probe & safe
     ids_ok, scores_ok, bit_ok = True, True, True
     for name, (Dg, Ig) in got.items():
-        ids_eq = bool(np.array_equal(Ig[check], Io[check]))
-        # ambiguous queries: same id SET within the top-k is still required unless the k/k+1 gap itself is the tie
+        exact = np.array([np.array_equal(a, b) for a, b in zip(Ig, Io)])
+        # a query whose ids differ is acceptable only as a near-tie: at every rank the fp64 score of the id
+        # the GPU returned equals the fp64 score of the oracle's id within the fp32 rounding bound
+        excused = np.zeros(len(q), dtype=bool)
+        for i in np.nonzero(~exact & same_probe)[0]:
+            try:
+                excused[i] = all(abs(s64[i][int(a)] - s64[i][int(b)]) <= TOL for a, b in zip(Ig[i], Io[i]))
+            except KeyError:  # an id outside the probed lists: never acceptable
+                excused[i] = False
+        ok = exact | excused | ~same_probe
         diff = float(np.max(np.abs(Dg[same_probe] - Do[same_probe]))) if same_probe.any() else 0.0
-        bit = bool(np.array_equal(Dg[check], Do[check]))
-        out["modes"][name] = {"ids_equal": ids_eq, "scores_max_abs_diff": diff, "scores_bit_identical": bit,
-                              "queries_compared": int(check.sum())}
-        ids_ok &= ids_eq
+        bit = bool(np.array_equal(Dg[same_probe], Do[same_probe]))
+        out["modes"][name] = {"ids_equal": bool(ok.all()), "queries_ids_identical": int((exact & same_probe).sum()),
+                              "queries_near_tie_reordered": int(excused.sum()), "queries_compared": int(same_probe.sum()),
+                              "scores_max_abs_diff": diff, "scores_bit_identical": bit}
+        ids_ok &= bool(ok.all())
         scores_ok &= diff <= 2e-5
         bit_ok &= bit
     syn = np.arange(len(q)) >= n_enc
-    if args.corpus == "lattice" and (check & syn).any():
+    if args.corpus == "lattice" and (same_probe & syn).any():
         # lattice rows x lattice queries: every fp32 partial sum is exact -> scores must match bit for bit
-        m = check & syn
-        out["lattice_queries_scores_bit_identical"] = bool(all(np.array_equal(Dg[m], Do[m]) for Dg, _ in got.values()))
+        m = same_probe & syn
+        out["lattice_queries_scores_bit_identical"] = bool(all(np.array_equal(Dg[m], Do[m]) and np.array_equal(Ig[m], Io[m])
+                                                               for Dg, Ig in got.values()))
         scores_ok &= out["lattice_queries_scores_bit_identical"]
     if len(got) == 2:
         (Da, Ia), (Db, Ib) = got.values()

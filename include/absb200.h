@@ -215,6 +215,11 @@ int absb_ivf_two_stage_fallbacks(absb_ivf_t h, int64_t* queries);
 /* Tunables (chunk = vectors per scan work item; coarse_impl 0 = fp32 SIMT, 1 = tcgen05
  * split-bf16). Values < 0 leave a setting unchanged. */
 int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int scan_ctas_per_sm);
+/* Fine-scan kernel: impl 1 (default, d = 1024) = list vectors staged in shared memory by cp.async.bulk
+ * into per-warp rings of `ring_depth` stages x `ring_stage_vecs` fp32 vectors (the fp16 pass stages twice
+ * as many), `ring_warps` warps per CTA (ivf_scan_ring.cu); impl 0 = vectors held in registers
+ * (ivf_scan.cu).  Results are bit-identical.  -1 / 0 keeps a field. */
+int absb_ivf_set_scan_impl(absb_ivf_t h, int impl, int ring_warps, int ring_depth, int ring_stage_vecs);
 /* Order of the scan work queue: 1 (default) = list-major — the (query, probe) pairs are sorted by list
  * number, so probes of several queries into one list are scanned at the same time and the repeats hit
  * L2; 0 = query-major.  Results are identical. */
