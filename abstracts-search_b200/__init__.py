@@ -13,4 +13,5 @@ from .index import (METRIC_INNER_PRODUCT, METRIC_L2, ClusteringParameters, Index
 from .sharded import DeviceOps, ShardedIndexIVFFlat, merge_partials_host, owner_of_list  # noqa: F401
 from .encoder import STELLA_1_5B, Encoder, EncoderConfig, SentenceTransformer  # noqa: F401
 from .peer import PeerExchange  # noqa: F401
-from . import faiss_io, oa_jsonl, peer, store, synth, tune  # noqa: F401
+from .pipeline import QueryPipeline  # noqa: F401
+from . import faiss_io, oa_jsonl, peer, pipeline, store, synth, tune  # noqa: F401

@@ -810,9 +810,18 @@ int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int sca
 int absb_ivf_set_scan_impl(absb_ivf_t h, int impl, int ring_warps, int ring_depth, int ring_stage_vecs) {
   ABSB_API_BEGIN
   NEED(h);
-  ABSB_CHECK(impl >= -1 && impl <= 1, ABSB_ERR_INVALID, "scan impl %d", impl);
+  ABSB_CHECK(impl >= -1 && impl <= 2, ABSB_ERR_INVALID, "scan impl %d", impl);
   IvfIndex& ix = h->ix;
-  if (impl >= 0) ix.scan_impl = impl;
+  if (impl >= 0) {
+    ix.scan_impl = impl;
+    ix.ring.small = impl == 2;
+    if (impl == 2) {  // the co-resident shape: ONE CTA of 8 warps x 2 stages x 4 KB per SM
+      ix.ring.warps = 8;
+      ix.ring.depth = 2;
+      ix.ring.stage_vecs = 1;
+      ix.scan_ctas_per_sm = 1;
+    }
+  }
   if (ring_warps > 0) {
     ABSB_CHECK(ring_warps <= 16, ABSB_ERR_INVALID, "ring warps %d", ring_warps);
     ix.ring.warps = ring_warps;

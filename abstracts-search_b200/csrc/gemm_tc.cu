@@ -56,20 +56,31 @@ struct SmemLayout {
   // residual-add epilogue: one 32 x 32 fp32 box (4 KB, SWIZZLE_128B) per epilogue warp, the source of
   // its cp.reduce.async.bulk.tensor
   static constexpr int kEpiBytes = (EPI == EPI_F32_ADD && kTmaReduce) ? 8 * 4096 : 0;
-  static constexpr int kStages = (216 * 1024 - kEpiBytes) / kStageBytes;
-  static constexpr int kEpiOff = kStages * kStageBytes;
-  static constexpr int kBarOff = kEpiOff + kEpiBytes;
-  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr
-  static constexpr int kTotal = kBarOff + (2 * kStages + 4) * 8 + 16;
-  static constexpr int kDyn = kTotal + 1024;  // slack for manual 1024-byte alignment
+  // The ring depth is a LAUNCH parameter (KernelParams::stages): kMaxStages fills the SM when the GEMM has it
+  // to itself; a smaller budget (absb_gemm_set_smem_budget) leaves room for a co-resident scan CTA.
+  static constexpr int kMaxStages = (216 * 1024 - kEpiBytes) / kStageBytes;
+  static constexpr int epi_off(int stages) { return stages * kStageBytes; }
+  static constexpr int bar_off(int stages) { return epi_off(stages) + kEpiBytes; }
+  // full[stages], empty[stages], tmem_full[2], tmem_empty[2], tmem ptr
+  static constexpr int total(int stages) { return bar_off(stages) + (2 * stages + 4) * 8 + 16; }
+  static constexpr int dyn(int stages) { return total(stages) + 1024; }  // slack for manual 1024-byte alignment
+  static int stages_for(int budget_bytes) {
+    int s = kMaxStages;
+    while (s > 2 && dyn(s) > budget_bytes) --s;
+    return s;
+  }
   static_assert(kBBytes % 1024 == 0, "SWIZZLE_128B tiles must stay 1024-byte aligned");
-  static_assert(kDyn <= 227 * 1024, "shared memory budget");
+  static_assert(dyn(kMaxStages) <= 227 * 1024, "shared memory budget");
 };
+
+int g_gemm_smem_budget = 227 * 1024;
+inline int gemm_smem_budget() { return g_gemm_smem_budget; }
 
 struct KernelParams {
   int M, N, K;
   int tiles_m, tiles_n;  // tiles_m counts (128 * NCTA)-row blocks
   int n_fast;            // raster: 1 = consecutive tiles walk N (A tile shared), 0 = walk M (B tile shared)
+  int stages;            // depth of the shared-memory operand ring (<= SmemLayout::kMaxStages)
   int num_kb;            // k-blocks per tile over all segments
   int seg_kb;            // k-blocks per segment
   int a_off[kMaxGemmSegs];
@@ -99,16 +110,19 @@ __device__ __forceinline__ void tile_coords(const KernelParams& p, int tile, int
   }
 }
 
+// Register cap: 104 per thread (384 x 112 allocated = 43,008 of the SM's 65,536), so that one small CTA of the
+// shared-memory ring scan (ivf_scan_ring.cu: 8 warps x 80 registers) fits on the same SM while a GEMM of the
+// encoder is resident — the HBM-bound list scan of batch i runs under the tensor-bound encode of batch i+1.
 template <int BN, int EPI, int NCTA>
-__global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ __maxnreg__(104) void gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmC,
                                                                    const KernelParams p) {
   using L = SmemLayout<BN, NCTA, EPI>;
-  constexpr int kStages = L::kStages;
+  const int kStages = p.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::bar_off(kStages));
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -359,7 +373,7 @@ __global__ __launch_bounds__(kThreads, 1) void gemm_bf16_tc_kernel(const __grid_
             // box -> cp.reduce.async.bulk.tensor (.add, fp32).  Rows past M are clipped by the tensor map;
             // every element is added exactly once, so the result does not depend on timing.
             if (col < p.N) {  // warp-uniform
-              uint8_t* stg = smem + L::kEpiOff + (warp - kEpiWarp0) * 4096;
+              uint8_t* stg = smem + L::epi_off(kStages) + (warp - kEpiWarp0) * 4096;
               if (lane == 0) tc::bulk_wait_read_all();  // the previous box has left this buffer
               __syncwarp();
 #pragma unroll
@@ -491,9 +505,10 @@ void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const vo
   auto kern = gemm_bf16_tc_kernel<BN, EPI, NCTA>;
   static bool configured = false;  // per instantiation
   if (!configured) {
-    ABSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn));
+    ABSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn(L::kMaxStages)));
     configured = true;
   }
+  p.stages = L::stages_for(gemm_smem_budget());
   p.tiles_m = (int)ceil_div(p.M, BM * NCTA);
   p.tiles_n = (int)ceil_div(p.N, BN);
   // Few N tiles: walk N first so the CTAs running concurrently share A tiles (A is the big operand of the
@@ -507,7 +522,7 @@ void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const vo
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(workers * NCTA));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = L::kDyn;
+  cfg.dynamicSmemBytes = L::dyn(p.stages);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -561,6 +576,7 @@ int g_gemm_variant = 0;  // 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3
 }  // namespace
 
 void gemm_set_variant(int v) { g_gemm_variant = v; }
+void gemm_set_smem_budget(int bytes) { g_gemm_smem_budget = bytes; }
 
 void gemm_bf16_tc_ex(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
                      int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st, const GemmRope* rope,
@@ -753,6 +769,14 @@ extern "C" int absb_gemm_set_variant(int variant) {
   ABSB_API_BEGIN
   ABSB_CHECK(variant >= 0 && variant <= 3, ABSB_ERR_INVALID, "GEMM variant %d outside [0,3]", variant);
   absb::gemm_set_variant(variant);
+  ABSB_API_END
+}
+
+extern "C" int absb_gemm_set_smem_budget(int bytes) {
+  ABSB_API_BEGIN
+  ABSB_CHECK(bytes == 0 || (bytes >= 96 * 1024 && bytes <= 227 * 1024), ABSB_ERR_INVALID,
+             "GEMM shared-memory budget %d outside [96 KB, 227 KB] (0 = all of it)", bytes);
+  absb::gemm_set_smem_budget(bytes == 0 ? 227 * 1024 : bytes);
   ABSB_API_END
 }
 

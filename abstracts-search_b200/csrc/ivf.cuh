@@ -88,7 +88,8 @@ struct IvfIndex {
   int coarse_impl = 1;  // 1 = tcgen05 split-bf16 (falls back to the FFMA GEMM for shapes it cannot take)
   int scan_ctas_per_sm = 0;
   int two_stage_k = 0;  // shortlist length of the two-stage scan (0 = single-pass fp32 scan)
-  int scan_impl = 1;  // 1 = shared-memory ring scan (cp.async.bulk staging, ivf_scan_ring.cu; d = 1024), 0 = register scan
+  int scan_impl = 1;  // 1 = shared-memory ring scan (cp.async.bulk staging, ivf_scan_ring.cu; d = 1024), 2 = its small
+                      // co-resident variant (one 8-warp CTA per SM beside the encoder's GEMM CTAs), 0 = register scan
   ScanRing ring;      // geometry of the ring scan
   int scan_order = 1;  // 1 = list-major work queue (probes of one list scanned together: L2 reuse), 0 = query-major
 
@@ -127,7 +128,7 @@ struct IvfIndex {
   // replay info for absb_ivf_time_scan
   ScanLaunch last_scan{};
   bool have_last_scan = false;
-  bool use_ring() const { return scan_impl == 1 && d == 1024; }
+  bool use_ring() const { return scan_impl >= 1 && d == 1024; }
   void run_scan(const ScanLaunch& a, cudaStream_t st) {
     if (use_ring()) launch_scan_ring(a, ring, st);
     else launch_scan(a, st);

@@ -67,10 +67,36 @@ __device__ __forceinline__ float dot8r(const uint4 x, const float4 qa, const flo
   return acc;
 }
 
-__device__ __forceinline__ float warp_sum_r(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
-  return v;
+// Transposed butterfly: reduces the per-lane partial sums of U = 1, 2 or 4 vectors at once.  Afterwards lane l
+// holds the complete inner product of vector l / (32 / U) (every lane of that group the same value).  For each
+// vector the additions form exactly the xor-butterfly tree of warp_sum (levels 16, 8, 4, 2, 1; fp32 addition is
+// commutative), so the value is bit-identical to the register kernels' `acc += shfl_xor(acc, o)` chain — with
+// 5 / 5 / 6 shuffles per stage instead of 5 per vector.
+template <int U>
+__device__ __forceinline__ float warp_sum_transposed(const float (&acc)[U], int lane) {
+  float r;
+  if (U == 1) {
+    r = acc[0] + __shfl_xor_sync(kFullMask, acc[0], 16);
+    r += __shfl_xor_sync(kFullMask, r, 8);
+  } else if (U == 2) {
+    const bool hi = lane & 16;
+    const float keep = hi ? acc[1] : acc[0], send = hi ? acc[0] : acc[1];
+    r = keep + __shfl_xor_sync(kFullMask, send, 16);
+    r += __shfl_xor_sync(kFullMask, r, 8);
+  } else {
+    const bool hi = lane & 16;
+    const float k0 = hi ? acc[2] : acc[0], s0 = hi ? acc[0] : acc[2];
+    const float k1 = hi ? acc[3] : acc[1], s1 = hi ? acc[1] : acc[3];
+    const float r0 = k0 + __shfl_xor_sync(kFullMask, s0, 16);
+    const float r1 = k1 + __shfl_xor_sync(kFullMask, s1, 16);
+    const bool hi8 = lane & 8;
+    const float keep = hi8 ? r1 : r0, send = hi8 ? r0 : r1;
+    r = keep + __shfl_xor_sync(kFullMask, send, 8);
+  }
+  r += __shfl_xor_sync(kFullMask, r, 4);
+  r += __shfl_xor_sync(kFullMask, r, 2);
+  r += __shfl_xor_sync(kFullMask, r, 1);
+  return r;
 }
 
 struct RingItem {
@@ -105,12 +131,12 @@ __device__ __forceinline__ RingItem load_ring_item(const ScanItem* p, const unsi
 // HALF = false: fp32 codes, k results per item with the vectors' int64 ids   (ivf_scan_kernel's contract)
 // HALF = true : fp16 shadow codes, K approximate candidates per item as global slot numbers (ivf_scan16_kernel's)
 template <int SLOTS, bool HALF, int SV>
-__global__ void ivf_scan_ring_kernel(const float* __restrict__ Q, const ScanItem* __restrict__ items,
-                                     const int* __restrict__ n_items_ptr, int* __restrict__ queue_counter,
-                                     const int* __restrict__ order, int k, float* __restrict__ part_s,
-                                     long long* __restrict__ part_id,
-                                     const unsigned short* const* __restrict__ half_slabs, int slab_shift, int P,
-                                     int depth) {
+__device__ __forceinline__ void ivf_scan_ring_body(const float* __restrict__ Q, const ScanItem* __restrict__ items,
+                                                   const int* __restrict__ n_items_ptr, int* __restrict__ queue_counter,
+                                                   const int* __restrict__ order, int k, float* __restrict__ part_s,
+                                                   long long* __restrict__ part_id,
+                                                   const unsigned short* const* __restrict__ half_slabs, int slab_shift,
+                                                   int P, int depth) {
   constexpr int VB = HALF ? kD * 2 : kD * 4;  // bytes per vector
   constexpr int SB = SV * VB;                 // bytes per stage
   extern __shared__ __align__(128) unsigned char ring_smem[];
@@ -236,25 +262,28 @@ __global__ void ivf_scan_ring_kernel(const float* __restrict__ Q, const ScanItem
       }
     }
     // the stage's bytes are in registers: hand it back to the bulk-copy engine before the (latency-bound)
-    // reduction and top-k update
+    // reduction and top-k update.  The refill is issued by lane 0 after the warp barrier, i.e. after every
+    // lane's shared-memory reads of this stage have been performed (same ordering the mbarrier-based
+    // consumer-release of a TMA pipeline relies on).
     __syncwarp();
-    if (lane == 0) tc::fence_proxy_async();  // generic-proxy reads of the stage precede the async-proxy refill
     --in_flight;
     produce(stage);
     __syncwarp();
-#pragma unroll
-    for (int u = 0; u < SV; ++u)
-      if (u < nv) acc[u] = warp_sum_r(acc[u]);
-#pragma unroll
-    for (int u = 0; u < SV; ++u) {
-      if (u < nv) {
-        if (HALF) {
-          const long long g = cit.g0 + c_v + u;
-          if (tk.may_enter(acc[u]) && tk.admits(acc[u], g)) tk.insert(acc[u], g);
-        } else if (tk.may_enter(acc[u])) {
-          const long long id = __ldg(cit.ids + c_v + u);
-          if (tk.admits(acc[u], id)) tk.insert(acc[u], id);
-        }
+    // lane l now gets the score of vector u(l) = l / (32 / SV); one ballot finds the (rare) candidates
+    const float sc = warp_sum_transposed<SV>(acc, lane);
+    const int my_u = SV == 1 ? 0 : (SV == 2 ? lane >> 4 : lane >> 3);
+    unsigned m = __ballot_sync(kFullMask, my_u < nv && tk.may_enter(sc));
+    while (m) {
+      const int src = __ffs(m) - 1;  // first lane of the lowest candidate vector: ascending u = list order
+      const int u = SV == 1 ? 0 : (SV == 2 ? src >> 4 : src >> 3);
+      m &= ~(SV == 1 ? 0xffffffffu : (SV == 2 ? 0xffffu << (u * 16) : 0xffu << (u * 8)));
+      const float cs = __shfl_sync(kFullMask, sc, src);
+      if (HALF) {
+        const long long g = cit.g0 + c_v + u;
+        if (tk.admits(cs, g)) tk.insert(cs, g);
+      } else if (tk.may_enter(cs)) {  // the threshold may have risen since the ballot
+        const long long id = __ldg(cit.ids + c_v + u);
+        if (tk.admits(cs, id)) tk.insert(cs, id);
       }
     }
     c_v += nv;
@@ -265,6 +294,27 @@ __global__ void ivf_scan_ring_kernel(const float* __restrict__ Q, const ScanItem
       parity ^= 1;
     }
   }
+}
+
+#define ABSB_RING_ARGS                                                                                            \
+  const float *__restrict__ Q, const ScanItem *__restrict__ items, const int *__restrict__ n_items_ptr,           \
+      int *__restrict__ queue_counter, const int *__restrict__ order, int k, float *__restrict__ part_s,          \
+      long long *__restrict__ part_id, const unsigned short *const *__restrict__ half_slabs, int slab_shift, int P, \
+      int depth
+
+// Full-size variant: whatever registers the compiler wants (120-165), several CTAs per SM when alone on the GPU.
+template <int SLOTS, bool HALF, int SV>
+__global__ void ivf_scan_ring_kernel(ABSB_RING_ARGS) {
+  ivf_scan_ring_body<SLOTS, HALF, SV>(Q, items, n_items_ptr, queue_counter, order, k, part_s, part_id, half_slabs,
+                                      slab_shift, P, depth);
+}
+
+// Co-resident variant: capped at 96 registers so that ONE CTA of 8 warps (24,576 registers, 64 KB of ring) fits
+// next to a tcgen05 GEMM CTA of the encoder (384 threads x 104 registers, <= 161 KB) on the same SM.
+template <int SLOTS, bool HALF, int SV>
+__global__ __maxnreg__(96) void ivf_scan_ring_small_kernel(ABSB_RING_ARGS) {
+  ivf_scan_ring_body<SLOTS, HALF, SV>(Q, items, n_items_ptr, queue_counter, order, k, part_s, part_id, half_slabs,
+                                      slab_shift, P, depth);
 }
 
 template <typename Kern>
@@ -292,7 +342,10 @@ void launch_ring(Kern kern, const ScanRing& r, int sm_count, int ctas_per_sm, in
 void launch_scan_ring(const ScanLaunch& a, const ScanRing& r, cudaStream_t st) {
   ABSB_CHECK(a.d == kD, ABSB_ERR_UNSUPPORTED, "the shared-memory ring scan is built for d = %d (d=%d)", kD, a.d);
   ABSB_DISPATCH_SLOTS(a.k, {
-    if (r.stage_vecs == 1)
+    if (r.small)
+      launch_ring(ivf_scan_ring_small_kernel<SLOTS, false, 1>, r, a.sm_count, a.ctas_per_sm, 1 * kD * 4, st, a.Q, a.items,
+                  a.n_items, a.queue_counter, a.order, a.k, a.part_s, a.part_id, nullptr, 0, 1);
+    else if (r.stage_vecs == 1)
       launch_ring(ivf_scan_ring_kernel<SLOTS, false, 1>, r, a.sm_count, a.ctas_per_sm, 1 * kD * 4, st, a.Q, a.items,
                   a.n_items, a.queue_counter, a.order, a.k, a.part_s, a.part_id, nullptr, 0, 1);
     else
@@ -304,7 +357,10 @@ void launch_scan_ring(const ScanLaunch& a, const ScanRing& r, cudaStream_t st) {
 void launch_scan16_ring(const Scan16Launch& a, const ScanRing& r, cudaStream_t st) {
   ABSB_CHECK(a.K == 32 || a.K == 64 || a.K == 128, ABSB_ERR_INVALID, "shortlist length %d (32, 64 or 128)", a.K);
   ABSB_DISPATCH_SLOTS(a.K, {
-    if (r.stage_vecs <= 2)
+    if (r.small)
+      launch_ring(ivf_scan_ring_small_kernel<SLOTS, true, 2>, r, a.sm_count, a.ctas_per_sm, 2 * kD * 2, st, a.Q, a.items,
+                  a.n_items, a.queue_counter, a.order, a.K, a.part_s, a.part_g, a.half_slabs, a.slab_shift, a.page_vecs);
+    else if (r.stage_vecs <= 2)
       launch_ring(ivf_scan_ring_kernel<SLOTS, true, 2>, r, a.sm_count, a.ctas_per_sm, 2 * kD * 2, st, a.Q, a.items,
                   a.n_items, a.queue_counter, a.order, a.K, a.part_s, a.part_g, a.half_slabs, a.slab_shift, a.page_vecs);
     else

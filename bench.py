@@ -69,15 +69,21 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=512, help="queries per step (whole job)")
     ap.add_argument("--query-tokens", type=int, default=32)
     ap.add_argument("--coarse-impl", type=int, default=1, help="0 fp32 FFMA GEMM, 1 tcgen05 split-bf16 GEMM")
-    ap.add_argument("--scan-chunk", type=int, default=-1)
+    ap.add_argument("--scan-chunk", type=int, default=512, help="vectors per scan work item")
     ap.add_argument("--scan-order", type=int, default=1, help="1 list-major work queue (default), 0 query-major")
     ap.add_argument("--gemm-variant", type=int, default=0, help="tcgen05 GEMM tile shape (0 auto; see absb_gemm_set_variant)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: all-gathers of the query path as NVLink peer-memory stores fused into our kernels "
                          "(default) or as NCCL calls")
-    ap.add_argument("--pipeline", type=int, default=0,
-                    help="1: software-pipeline consecutive batches on two streams (encode of batch i+1 on a high-priority "
-                         "stream overlaps the HBM-bound search of batch i); the timed region covers fill and drain")
+    ap.add_argument("--pipeline", type=int, default=1,
+                    help="1 (default): QueryPipeline — consecutive batches software-pipelined on two streams (the tensor-bound "
+                         "encode of batch i+1 overlaps the HBM-bound search of batch i; the scan runs as one small CTA per SM "
+                         "beside the GEMM CTAs); the timed region covers fill and drain.  0: encode then search, one stream")
+    ap.add_argument("--no-coresident", action="store_true",
+                    help="pipeline without the SM-sharing shapes (full-size scan CTAs, full GEMM shared memory): the streams "
+                         "then mostly serialise; for A/B measurements")
+    ap.add_argument("--scan-impl", type=int, default=1, help="fine scan of the serial path: 1 shared-memory ring (cp.async.bulk), 0 registers")
+    ap.add_argument("--ring", default="", help="ring geometry warps,depth,stage_vecs of --scan-impl 1 (default 4,3,1)")
     ap.add_argument("--two-stage", type=int, default=64,
                     help="two-stage fine scan: fp16 shadow codes (+50%% index memory) give a shortlist of this many "
                          "candidates (32/64/128), fp32 codes their exact scores; identical results (0 = single-pass scan)")
@@ -297,12 +303,19 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def apply_scan_impl(ix, args):
+    w, dpt, sv = (int(v) for v in (getattr(args, "ring", "") or "4,3,1").split(","))
+    ix.set_scan_impl(getattr(args, "scan_impl", 1), w, dpt, sv)
+    ix.set_tunables(scan_chunk=getattr(args, "scan_chunk", -1), scan_ctas_per_sm=max(0, getattr(args, "scan_ctas", -1)))
+
+
 def build_shard(P, torch, args, rank: int, world: int, dev: int, rows_per_gpu: int | None = None):
     d, nlist = 1024, args.nlist
     total = (rows_per_gpu or args.rows_per_gpu) * world
     ix = P.index_factory(d, f"IVF{nlist},Flat", P.METRIC_INNER_PRODUCT, device=dev)
     ix.set_tunables(scan_chunk=args.scan_chunk, coarse_impl=args.coarse_impl, scan_ctas_per_sm=args.scan_ctas)
     ix.set_scan_order(bool(args.scan_order))
+    apply_scan_impl(ix, args)
     if args.two_stage:
         ix.set_two_stage(args.two_stage)
     if world > 1:
@@ -659,51 +672,30 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         last["emb"] = e
         return ix.search(e, k)
 
-    # ---- optional two-stream software pipeline over consecutive batches ---------------------------
+    # ---- two-stream software pipeline over consecutive batches (the product's QueryPipeline) -----------
+    pipe = None
     if args.pipeline:
-        s_enc = torch.cuda.Stream(priority=-1)  # tensor-bound encoder first in line for SM slots
-        s_srch = torch.cuda.Stream(priority=0)
-        emb_ring = [torch.empty((nq, 1024), dtype=torch.float32, device=device) for _ in range(2)]
-        ev_enc = [torch.cuda.Event() for _ in range(2)]
-        ev_srch = [torch.cuda.Event() for _ in range(2)]
-        pipe_state = {"i": 0, "last": None}
+        pipe = P.QueryPipeline(enc, ix, k=k, nprobe=args.nprobe, batch=nq, tokens=S, sharded=sh, px_emb=px_emb,
+                               coresident=not args.no_coresident)
 
-        def pipe_encode(i):
-            with torch.cuda.stream(s_enc):
-                s_enc.wait_event(ev_srch[i & 1])  # the search that read this ring entry two batches ago is done
-                e = enc.encode_tokens(ids_d[lo:hi], mask_d[lo:hi], normalize_embeddings=True)
-                if world > 1:
-                    if px_emb is not None:
-                        emb_ring[i & 1].copy_(px_emb.allgather(e).view(nq, 1024))
-                    else:
-                        dist.all_gather_into_tensor(emb_ring[i & 1], e)
-                else:
-                    emb_ring[i & 1].copy_(e)
-                ev_enc[i & 1].record(s_enc)
-
-        def pipe_search(j):
-            with torch.cuda.stream(s_srch):
-                s_srch.wait_event(ev_enc[j & 1])
-                out = sh.search(emb_ring[j & 1], k) if world > 1 else ix.search(emb_ring[j & 1], k)
-                ev_srch[j & 1].record(s_srch)
-            return out
-
-        def run_pipelined(steps):
-            """`steps` batches end to end: steps + 1 iterations, encode(i) || search(i - 1)."""
+        def run_pipelined(steps, host=False):
+            """`steps` batches end to end; encode(i + 1) is in flight with search(i).  host=True: pinned host
+            token ids in, numpy (D, I) out, the copies issued inside the pipeline."""
             out = None
-            cur = torch.cuda.current_stream()
-            s_enc.wait_stream(cur)
-            s_srch.wait_stream(cur)
-            for i in range(steps + 1):
-                if i < steps:
-                    pipe_encode(i)
-                if i > 0:
-                    out = pipe_search(i - 1)
-            cur.wait_stream(s_enc)
-            cur.wait_stream(s_srch)
+            pipe.start()
+            a, b = (ids_h[lo:hi], mask_h[lo:hi]) if host else (ids_d[lo:hi], mask_d[lo:hi])
+            for _ in range(steps):
+                t = pipe.submit(a, b)
+                if t is not None:
+                    out = pipe.result(t)
+            for t in pipe.flush():
+                out = pipe.result(t)
+            pipe.join()
             return out
 
     def step_e2e():
+        if pipe is not None:
+            return run_pipelined(1, host=True)
         e = enc.encode_tokens(ids_np[lo:hi], mask_np[lo:hi], normalize_embeddings=True)  # host in, host out
         if world > 1:
             e_d = torch.from_numpy(e).to(device, non_blocking=True)
@@ -766,7 +758,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ms_total = timed(args.steps, pipelined=bool(args.pipeline))
     kernel_events = not args.no_kernel_events
     enc_prof = ix_prof = None
-    ms_instrumented = None
+    ms_instrumented = ms_serial = None
+    if pipe is not None and pipe.coresident:
+        pipe.disable_coresidency()  # the per-kernel numbers below are those of each kernel ALONE on the GPU (serial step)
+        apply_scan_impl(ix, args)
+    if args.pipeline:
+        ms_serial = timed(args.steps) / args.steps  # the same K steps, encode then search on one stream
     if kernel_events:
         enc.set_profile(2)
         ix.set_profile(2)
@@ -778,8 +775,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     st = ix.last_stats()
     ms_per_step = ms_total / args.steps
     value = nq / (ms_per_step * 1e-3)
+    if pipe is not None and pipe.coresident:
+        pipe.enable_coresidency()
 
-    # ---- e2e: host buffers through the public numpy API ----------------------------------------
+    # ---- e2e: host buffers through the public API ------------------------------------------------
     e2e = None
     if not args.skip_e2e:
         for _ in range(2):
@@ -787,15 +786,24 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         assert np.array_equal(Ie, Iw), "host-API result differs from the device-API result"
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
+        if pipe is not None:
+            De, Ie = run_pipelined(args.steps, host=True)  # K batches: pinned host ids in, numpy (D, I) out, every batch
+            assert np.array_equal(Ie, Iw)
+        else:
+            for _ in range(args.steps):
+                step_e2e()
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
-        h2d = per * S * (8 + 4) + (nq * 1024 * 4 if world == 1 else per * 1024 * 4)
-        d2h = per * 1024 * 4 + nq * k * 12
+        if pipe is not None:
+            h2d, d2h = per * S * (8 + 4), nq * k * 12
+            api = ("QueryPipeline.submit(pinned host token ids) / .result() -> numpy (D, I): per batch H2D of the ids + mask on "
+                   "the encode stream, absb_enc_forward_dev, all-gather, absb_ivf_search[_push]_dev, D2H of (D, I) on the search stream")
+        else:
+            h2d = per * S * (8 + 4) + (nq * 1024 * 4 if world == 1 else per * 1024 * 4)
+            d2h = per * 1024 * 4 + nq * k * 12
+            api = "Encoder.encode_tokens(numpy) -> IndexIVFFlat.search(numpy): absb_enc_forward + absb_ivf_search"
         e2e = {"value": nq / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h),
-               "api": "Encoder.encode_tokens(numpy) -> IndexIVFFlat.search(numpy): absb_enc_forward + absb_ivf_search"}
+               "d2h_bytes_per_step": int(d2h), "api": api}
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     rooflines = {}
@@ -871,8 +879,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     cfg.update({"two_stage_shortlist": args.two_stage,
                 "two_stage_fallback_queries_total": (fallbacks if args.two_stage else None),
                 "two_stage_fallback_note": "summed over ranks, warm-up + timed + instrumented + e2e steps, %d queries each" % nq,
-                "pipeline": ("two streams: encode of batch i+1 overlaps search of batch i; K batches timed over K+1 iterations "
-                             "including fill and drain" if args.pipeline else "none: encode then search, one stream"),
+                "pipeline": (("QueryPipeline, two streams: encode of batch i+1 overlaps search of batch i; K batches timed end to end "
+                              "including fill and drain; " + ("scan as one 8-warp 64 KB CTA per SM beside the GEMM CTAs (161 KB)"
+                                                               if not args.no_coresident else "no SM-sharing shapes"))
+                             if args.pipeline else "none: encode then search, one stream"),
+                "ms_per_step_serial_same_run": ms_serial,
                 "exchange": exchange, "index_build_s": build_s, "distinct_probed_lists_per_step": distinct_lists,
                 "scan_work_items_per_step": st["items"], "ms_per_step_with_kernel_events": ms_instrumented, "coarse_impl": "tcgen05 split-bf16 (6 bf16 products, fp32-faithful)"
                 if args.coarse_impl == 1 else "fp32 FFMA", "kernel_events": "second timed pass of the same K steps" if kernel_events else "off"})

@@ -218,7 +218,10 @@ int absb_ivf_set_tunables(absb_ivf_t h, int scan_chunk, int coarse_impl, int sca
 /* Fine-scan kernel: impl 1 (default, d = 1024) = list vectors staged in shared memory by cp.async.bulk
  * into per-warp rings of `ring_depth` stages x `ring_stage_vecs` fp32 vectors (the fp16 pass stages twice
  * as many), `ring_warps` warps per CTA (ivf_scan_ring.cu); impl 0 = vectors held in registers
- * (ivf_scan.cu).  Results are bit-identical.  -1 / 0 keeps a field. */
+ * (ivf_scan.cu); impl 2 = the ring scan in its co-resident shape: ONE CTA of 8 warps x 2 stages x 4 KB per SM,
+ * capped at 96 registers, which fits on an SM next to a GEMM CTA of the encoder when the GEMMs run under
+ * absb_gemm_set_smem_budget(161 KB) — the list scan of batch i then overlaps the encode of batch i+1.
+ * Results are bit-identical.  -1 / 0 keeps a field. */
 int absb_ivf_set_scan_impl(absb_ivf_t h, int impl, int ring_warps, int ring_depth, int ring_stage_vecs);
 /* Order of the scan work queue: 1 (default) = list-major — the (query, probe) pairs are sorted by list
  * number, so probes of several queries into one list are scanned at the same time and the repeats hit
@@ -298,6 +301,9 @@ int absb_enc_get_profile(absb_enc_t e, double* gemm_ms, double* gemm_flops, doub
 
 /* Stand-alone GEMM entry used by tests and the micro-benchmark: C[M,N] (fp32) = A[M,K] * B[N,K]^T
  * with bf16 operands on tcgen05 (DEVICE pointers; K % 64 == 0). */
+/* Shared memory one GEMM CTA may take (bytes; 0 = all 227 KB): the operand ring gets as many stages as fit.
+ * 161 KB (4-5 stages instead of 5-7) leaves room for one co-resident scan CTA (absb_ivf_set_scan_impl 2). */
+int absb_gemm_set_smem_budget(int bytes);
 /* Test hook: force the tile shape of the tcgen05 GEMM (0 = automatic; 1 = one CTA, 128x256 tiles;
  * 2 = CTA pair (cta_group::2), 256x256 tiles; 3 = CTA pair, 256x192 tiles). Process-wide. */
 int absb_gemm_set_variant(int variant);

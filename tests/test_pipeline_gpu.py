@@ -79,3 +79,56 @@ def test_openalex_to_search_pipeline_matches_oracle_chain(gpu_pkg, tmp_path):
     clear = (cm > 1e-5) & (fm > 1e-5)
     assert clear.sum() >= len(pick) // 2, "too few unambiguous queries to compare"
     assert np.array_equal(I[clear], Io[clear]) and np.abs(D[clear] - Do[clear]).max() < 1e-5
+
+
+@pytest.mark.parametrize("coresident", [True, False])
+def test_query_pipeline_equals_serial_query_loop(gpu_pkg, coresident):
+    """QueryPipeline (encode of batch i+1 on one stream while batch i is searched on another; with
+    `coresident` the scan runs as one small register-capped ring CTA per SM next to GEMM CTAs that use a
+    smaller operand ring) returns, batch for batch, the bits the serial app.py-style loop returns:
+    device tensors in / out, and pinned host ids in / numpy out with the copies inside the pipeline."""
+    import torch
+
+    from oracle import synth as osynth
+
+    P = gpu_pkg
+    d, nlist, n, nq, S, k, nprobe, nb = 1024, 256, 40000, 64, 16, 10, 8, 5
+    enc = P.Encoder(config=P.STELLA_1_5B, random_init_seed=0)
+    ix = P.index_factory(d, f"IVF{nlist},Flat", P.METRIC_INNER_PRODUCT)
+    ix.set_two_stage(64)
+    ix.set_centroids(osynth.centroids(5, nlist, d))
+    ix.add(osynth.corpus_unit(5, 0, n, d, nlist))
+    ix.nprobe = nprobe
+    g = torch.Generator().manual_seed(3)
+    ids_h = torch.randint(0, P.STELLA_1_5B.vocab_size, (nb, nq, S), generator=g, dtype=torch.int64).pin_memory()
+    mask_h = torch.ones((nq, S), dtype=torch.int32)
+    mask_h[::3, S - 5:] = 0
+    mask_h = mask_h.pin_memory()
+    ids_d, mask_d = ids_h.cuda(), mask_h.cuda()
+    want = []
+    for b in range(nb):
+        e = enc.encode_tokens(ids_d[b], mask_d, normalize_embeddings=True)
+        D, I = ix.search(e, k)
+        want.append((D.cpu().numpy(), I.cpu().numpy()))
+    assert len({w[1].tobytes() for w in want}) == nb  # the batches really differ
+    try:
+        pipe = P.QueryPipeline(enc, ix, k=k, nprobe=nprobe, batch=nq, tokens=S, coresident=coresident)
+        got = [(D.cpu().numpy(), I.cpu().numpy()) for D, I in pipe.run((ids_d[b], mask_d) for b in range(nb))]
+        pipe.join()
+        assert len(got) == nb
+        for b in range(nb):
+            assert np.array_equal(got[b][1], want[b][1]) and np.array_equal(got[b][0], want[b][0]), b
+        got_h = list(pipe.run((ids_h[b], mask_h) for b in range(nb)))
+        for b in range(nb):
+            assert isinstance(got_h[b][1], np.ndarray)
+            assert np.array_equal(got_h[b][1], want[b][1]) and np.array_equal(got_h[b][0], want[b][0]), b
+    finally:
+        assert P.lib().absb_gemm_set_smem_budget(0) == 0  # process-wide setting: leave it as the other tests expect it
+    # the reduced GEMM operand ring alone changes no bit of the encoder output either
+    ref = enc.encode_tokens(ids_d[0], mask_d, normalize_embeddings=True).clone()
+    assert P.lib().absb_gemm_set_smem_budget(128 * 1024) == 0
+    try:
+        small = enc.encode_tokens(ids_d[0], mask_d, normalize_embeddings=True)
+        assert torch.equal(small, ref)
+    finally:
+        assert P.lib().absb_gemm_set_smem_budget(0) == 0
