@@ -253,10 +253,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int KVS>
-__global__ __launch_bounds__(kPThreads, 1) void attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                               const __grid_constant__ CUtensorMap tmKV,
-                                                                               const AttnParams p, int total_tiles,
-                                                                               int tiles_per_unit) {
+__device__ __forceinline__ void attention_tc_persistent_body(const CUtensorMap& tmQ, const CUtensorMap& tmKV,
+                                                             const AttnParams& p, int total_tiles, int tiles_per_unit) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int NK = p.NK;
@@ -557,6 +555,24 @@ __global__ __launch_bounds__(kPThreads, 1) void attention_tc_persistent_kernel(c
   }
 }
 
+template <int KVS>
+__global__ __launch_bounds__(kPThreads, 1) void attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                               const __grid_constant__ CUtensorMap tmKV,
+                                                                               const AttnParams p, int total_tiles,
+                                                                               int tiles_per_unit) {
+  attention_tc_persistent_body<KVS>(tmQ, tmKV, p, total_tiles, tiles_per_unit);
+}
+
+// Same kernel capped at 104 registers (a few hundred bytes of spills in the softmax warps): 384 x 104 leaves
+// room on the SM for the co-resident scan CTA of QueryPipeline (ivf_scan_ring.cu), as the GEMMs do.
+template <int KVS>
+__global__ __maxnreg__(104) void attention_tc_persistent_small_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                      const __grid_constant__ CUtensorMap tmKV,
+                                                                      const AttnParams p, int total_tiles,
+                                                                      int tiles_per_unit) {
+  attention_tc_persistent_body<KVS>(tmQ, tmKV, p, total_tiles, tiles_per_unit);
+}
+
 }  // namespace
 
 bool attention_tc_supported(int S) { return S >= 1 && S <= 256; }
@@ -600,13 +616,25 @@ void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, 
     if (!configured_p) {
       ABSB_CUDA(cudaFuncSetAttribute(attention_tc_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
       ABSB_CUDA(cudaFuncSetAttribute(attention_tc_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      ABSB_CUDA(cudaFuncSetAttribute(attention_tc_persistent_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      ABSB_CUDA(cudaFuncSetAttribute(attention_tc_persistent_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      prefer_max_shared(attention_tc_persistent_kernel<1>);
+      prefer_max_shared(attention_tc_persistent_kernel<2>);
+      prefer_max_shared(attention_tc_persistent_small_kernel<1>);
+      prefer_max_shared(attention_tc_persistent_small_kernel<2>);
       configured_p = true;
     }
     const int grid_p = std::max(1, std::min(total, sms));
-    if (kvs == 2)
-      attention_tc_persistent_kernel<2><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
-    else
-      attention_tc_persistent_kernel<1><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
+    // co-resident mode (the GEMMs run under a reduced shared-memory budget): register-capped twin, if its
+    // shared memory also fits beside the scan CTA
+    const bool small = gemm_coresident_mode() && smem_p <= 161 * 1024;
+    if (kvs == 2) {
+      if (small) attention_tc_persistent_small_kernel<2><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
+      else attention_tc_persistent_kernel<2><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
+    } else {
+      if (small) attention_tc_persistent_small_kernel<1><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
+      else attention_tc_persistent_kernel<1><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
+    }
     ABSB_CUDA(cudaGetLastError());
     return;
   }

@@ -128,6 +128,14 @@ struct HBuf {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Ask for the largest shared-memory carveout.  The L1 / shared split of an SM can only change while the SM is
+// idle, so kernels of two streams can share an SM only if whichever arrives first has already configured it
+// for the sum of both: every kernel that may run while a co-resident scan CTA is resident asks for the maximum.
+template <typename Kern>
+inline void prefer_max_shared(Kern kern) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 struct DeviceProps {
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;

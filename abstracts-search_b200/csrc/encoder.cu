@@ -430,6 +430,13 @@ struct Encoder {
     props = device_props(dev);
     DeviceGuard g(dev);
     ABSB_CUDA(cudaStreamCreate(&own_stream));
+    // every kernel of a forward may run while a co-resident scan CTA holds 64 KB of the SM (QueryPipeline)
+    prefer_max_shared(embed_kernel);
+    prefer_max_shared(rmsnorm_kernel<bf16>);
+    prefer_max_shared(rmsnorm_kernel<float>);
+    prefer_max_shared(pool_kernel);
+    prefer_max_shared(l2norm_kernel);
+    prefer_max_shared(attention_kernel);
     const int H = c.hidden_size, I = c.intermediate_size, QKV = qkv_dim();
     embed.alloc_exact((size_t)c.vocab_size * H);
     final_norm.alloc_exact(H);

@@ -506,6 +506,7 @@ void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const vo
   static bool configured = false;  // per instantiation
   if (!configured) {
     ABSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn(L::kMaxStages)));
+    prefer_max_shared(kern);
     configured = true;
   }
   p.stages = L::stages_for(gemm_smem_budget());
@@ -577,6 +578,7 @@ int g_gemm_variant = 0;  // 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3
 
 void gemm_set_variant(int v) { g_gemm_variant = v; }
 void gemm_set_smem_budget(int bytes) { g_gemm_smem_budget = bytes; }
+bool gemm_coresident_mode() { return g_gemm_smem_budget < 200 * 1024; }
 
 void gemm_bf16_tc_ex(int epi, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
                      int64_t ldc, const float* bias, const GemmSegs* segs, int sms, cudaStream_t st, const GemmRope* rope,

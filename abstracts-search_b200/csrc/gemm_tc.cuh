@@ -62,6 +62,10 @@ void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, 
 
 // test hook: 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3 = CTA pair x BN 192
 void gemm_set_variant(int v);
+// Shared memory a GEMM CTA may take (absb_gemm_set_smem_budget); a budget below the full 227 KB means the
+// encoder shares its SMs with a co-resident scan CTA.
+void gemm_set_smem_budget(int bytes);
+bool gemm_coresident_mode();
 
 // fp32 [rows,K] -> bf16 [rows, 3K] = [hi | mid | lo]
 void split3_bf16(int64_t rows, int K, const float* x, void* out, cudaStream_t st);

@@ -327,6 +327,7 @@ void launch_ring(Kern kern, const ScanRing& r, int sm_count, int ctas_per_sm, in
   const size_t smem = (size_t)warps * depth * stage_bytes + (size_t)warps * depth * 8 + (size_t)warps * kFifo * 4;
   ABSB_CHECK(smem <= 227 * 1024, ABSB_ERR_INVALID, "scan ring of %zu bytes exceeds the shared memory of an SM", smem);
   ABSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prefer_max_shared(kern);
   int per_sm = ctas_per_sm;
   if (per_sm <= 0) {
     ABSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));

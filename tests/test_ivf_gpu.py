@@ -842,25 +842,27 @@ def test_baseline_config2_ivf65536_ten_million_rows(gpu_pkg, corpus):
         if len(r):
             o.add(gen(seed, r, d, nlist), ids=r, list_ids=np.full(len(r), l))
     Do, Io = o.search_preassigned(qn, k, Ico, impl="c")
-    off, codes, _ = o._as_csr()
+    off, codes, ids_csr = o._as_csr()
     checked = 0
     for i in range(len(sel)):
         cs = np.sort(c64[:, i])[::-1]
         if cs[nprobe - 1] - cs[nprobe] <= 2e-5 or np.min(cs[:nprobe - 1] - cs[1:nprobe]) <= 2e-5:
             continue  # coarse near-tie: two correct fp32 coarse searches may order / cut differently
         assert np.array_equal(Ic[i], Ico[i]), i
-        sc = np.concatenate([codes[off[l]:off[l + 1]].astype(np.float64) @ qn[i].astype(np.float64) for l in Ico[i]])
-        top = np.sort(sc)[::-1][:k + 1]
         if not unit:
             assert np.array_equal(In[i], Io[i]) and np.array_equal(Dn[i], Do[i]), i  # exact arithmetic: bit for bit
         else:
             assert np.abs(Dn[i] - Do[i]).max() <= 2e-5, i
-            if np.min(top[:-1] - top[1:]) > 2e-5:
-                assert np.array_equal(In[i], Io[i]), i
-            else:
+            if not np.array_equal(In[i], Io[i]):
+                # only a near-tie may reorder ids between two correct fp32 scans: at every rank the two ids'
+                # fp64 scores must agree within the fp32 rounding of a 1024-term unit-vector product
+                sc = np.concatenate([codes[off[l]:off[l + 1]].astype(np.float64) @ qn[i].astype(np.float64) for l in Ico[i]])
+                idv = np.concatenate([ids_csr[off[l]:off[l + 1]] for l in Ico[i]])
+                s64 = dict(zip(idv.tolist(), sc.tolist()))
+                assert all(abs(s64[int(a)] - s64[int(b)]) <= 2e-6 for a, b in zip(In[i], Io[i])), i
                 continue
         checked += 1
-    assert checked >= 12, f"only {checked} of 16 sample queries were unambiguous"
+    assert checked >= 12, f"only {checked} of 16 sample queries came out id-identical"
     del ix, D1, I1, D2, I2, q
     gc.collect()
     t.cuda.empty_cache()
