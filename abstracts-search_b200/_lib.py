@@ -123,6 +123,8 @@ _SIGS = {
     "absb_ivf_set_profile": ([_H, c_int], c_int),
     "absb_ivf_get_profile": ([_H, _PD, _PD, _PD, _PI64], c_int),
     "absb_ivf_time_scan": ([_H, c_int, c_void_p, _PF], c_int),
+    "absb_ivf_profile_spans": ([_H, c_void_p, c_void_p, c_int64, _PI64], c_int),
+    "absb_enc_profile_spans": ([_H, c_void_p, c_void_p, c_int64, _PI64], c_int),
     # encoder
     "absb_enc_create": ([POINTER(EncConfig), c_int, POINTER(_H)], c_int),
     "absb_enc_destroy": ([_H], c_int),

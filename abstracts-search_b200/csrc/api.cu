@@ -815,6 +815,7 @@ int absb_ivf_set_scan_impl(absb_ivf_t h, int impl, int ring_warps, int ring_dept
   if (impl >= 0) {
     ix.scan_impl = impl;
     ix.ring.small = impl == 2;
+    ix.ring.l2_evict_first = impl == 2 && getenv("ABSB_SCAN_L2_DEFAULT") == nullptr;
     if (impl == 2) {  // the co-resident shape: ONE CTA of 8 warps x 2 stages x 4 KB per SM
       ix.ring.warps = 8;
       ix.ring.depth = 2;
@@ -914,6 +915,32 @@ int absb_ivf_get_profile(absb_ivf_t h, double* scan_ms, double* coarse_gemm_ms, 
   if (coarse_gemm_ms) *coarse_gemm_ms = ix.prof_ms[1];
   if (other_ms) *other_ms = ix.prof_ms[2];
   if (scan_launches) *scan_launches = ix.prof_scan_launches;
+  ABSB_API_END
+}
+
+// Timeline of the spans recorded since the profile was switched on (before they are folded into the totals):
+// out[i] = {kind, start_ms, stop_ms} relative to `base_event` (a cudaEvent_t recorded by the caller).
+static int64_t dump_spans(const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& pool, size_t used,
+                          const std::vector<int>& kinds, void* base_event, float* out, int64_t cap) {
+  ABSB_CUDA(cudaDeviceSynchronize());
+  int64_t n = 0;
+  for (size_t i = 0; i < used && n < cap; ++i) {
+    float t0 = 0.f, t1 = 0.f;
+    if (cudaEventElapsedTime(&t0, (cudaEvent_t)base_event, pool[i].first) != cudaSuccess) continue;
+    if (cudaEventElapsedTime(&t1, (cudaEvent_t)base_event, pool[i].second) != cudaSuccess) continue;
+    out[3 * n] = (float)kinds[i];
+    out[3 * n + 1] = t0;
+    out[3 * n + 2] = t1;
+    ++n;
+  }
+  return n;
+}
+
+int absb_ivf_profile_spans(absb_ivf_t h, void* base_event, float* out, int64_t cap, int64_t* n) {
+  ABSB_API_BEGIN
+  NEED(h); NEED(base_event); NEED(out); NEED(n);
+  DeviceGuard g(h->ix.device);
+  *n = dump_spans(h->ix.ev_pool, h->ix.ev_used, h->ix.ev_kind, base_event, out, cap);
   ABSB_API_END
 }
 

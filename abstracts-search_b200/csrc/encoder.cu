@@ -881,6 +881,26 @@ int absb_enc_set_profile(absb_enc_t e, int on) {
   ABSB_API_END
 }
 
+int absb_enc_profile_spans(absb_enc_t e, void* base_event, float* out, int64_t cap, int64_t* n) {
+  ABSB_API_BEGIN
+  NEED(e); NEED(base_event); NEED(out); NEED(n);
+  Encoder& enc = e->enc;
+  DeviceGuard g(enc.device);
+  ABSB_CUDA(cudaDeviceSynchronize());
+  int64_t m = 0;
+  for (size_t i = 0; i < enc.ev_used && m < cap; ++i) {
+    float t0 = 0.f, t1 = 0.f;
+    if (cudaEventElapsedTime(&t0, (cudaEvent_t)base_event, enc.ev_pool[i].first) != cudaSuccess) continue;
+    if (cudaEventElapsedTime(&t1, (cudaEvent_t)base_event, enc.ev_pool[i].second) != cudaSuccess) continue;
+    out[3 * m] = (float)enc.ev_kind[i];
+    out[3 * m + 1] = t0;
+    out[3 * m + 2] = t1;
+    ++m;
+  }
+  *n = m;
+  ABSB_API_END
+}
+
 int absb_enc_get_profile(absb_enc_t e, double* gemm_ms, double* gemm_flops, double* attention_ms, double* other_ms,
                          int64_t* forwards) {
   ABSB_API_BEGIN

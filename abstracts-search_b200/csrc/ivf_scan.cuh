@@ -57,6 +57,7 @@ struct ScanRing {
   int warps = 4;
   int depth = 4;
   int stage_vecs = 2;  // fp32 vectors per stage; the fp16 pass stages twice as many (same bytes)
+  bool l2_evict_first = false;  // stream the list codes through L2 with evict-first priority
   bool small = false;  // co-resident variant: 4 KB stages, <= 96 registers (fits beside a GEMM CTA of the encoder)
 };
 void launch_scan_ring(const ScanLaunch& a, const ScanRing& r, cudaStream_t st);

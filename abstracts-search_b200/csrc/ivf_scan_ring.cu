@@ -44,6 +44,17 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                : "memory");
 }
 
+// Same copy with an L2 eviction-priority hint (evict_first): list codes are streamed once per batch, so they
+// should not displace the encoder's weights and activations from L2 when the scan shares the GPU with it.
+__device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                               uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          tc::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(tc::smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 __device__ __forceinline__ float dot4r(const float4 a, const float4 b, float acc) {
   acc = fmaf(a.x, b.x, acc);
   acc = fmaf(a.y, b.y, acc);
@@ -136,7 +147,11 @@ __device__ __forceinline__ void ivf_scan_ring_body(const float* __restrict__ Q, 
                                                    const int* __restrict__ order, int k, float* __restrict__ part_s,
                                                    long long* __restrict__ part_id,
                                                    const unsigned short* const* __restrict__ half_slabs, int slab_shift,
-                                                   int P, int depth) {
+                                                   int P, int depth_and_hint) {
+  const int depth = depth_and_hint & 0xff;
+  const bool l2_evict_first = (depth_and_hint >> 8) & 1;
+  uint64_t l2_policy = 0;
+  if (l2_evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_policy));
   constexpr int VB = HALF ? kD * 2 : kD * 4;  // bytes per vector
   constexpr int SB = SV * VB;                 // bytes per stage
   extern __shared__ __align__(128) unsigned char ring_smem[];
@@ -188,7 +203,8 @@ __device__ __forceinline__ void ivf_scan_ring_body(const float* __restrict__ Q, 
     const int nv = p_left < SV ? p_left : SV;
     if (lane == 0) {
       tc::mbar_arrive_expect_tx(bars + s, (uint32_t)(nv * VB));
-      bulk_load(my_ring + (size_t)s * SB, p_src, (uint32_t)(nv * VB), bars + s);
+      if (l2_evict_first) bulk_load_hint(my_ring + (size_t)s * SB, p_src, (uint32_t)(nv * VB), bars + s, l2_policy);
+      else bulk_load(my_ring + (size_t)s * SB, p_src, (uint32_t)(nv * VB), bars + s);
     }
     p_src += (size_t)nv * VB;
     p_left -= nv;
@@ -206,8 +222,34 @@ __device__ __forceinline__ void ivf_scan_ring_body(const float* __restrict__ Q, 
   float4 qv[8];
   WarpTopK<SLOTS> tk;
   tk.init(k, lane);
+  // Software pipeline inside the warp: the per-lane partial sums of a stage are reduced (5-6 dependent
+  // shuffles) and offered to the top-k while the NEXT stage's shared-memory loads and FMA chains issue — one
+  // basic block holds both, so the shuffle latency hides behind FMA issue instead of adding to it.
+  float pend[SV];
+#pragma unroll
+  for (int u = 0; u < SV; ++u) pend[u] = 0.f;
+  int pend_nv = 0, pend_v = 0;
+  const int my_u = SV == 1 ? 0 : (SV == 2 ? lane >> 4 : lane >> 3);
+  // lane l holds the score of vector u(l) = l / (32 / SV) of the stage that started at vector v0 of the item;
+  // one ballot finds the (rare) candidates, offered in list order
+  auto offer = [&](float sc, int nv_, int v0) {
+    unsigned m = __ballot_sync(kFullMask, my_u < nv_ && tk.may_enter(sc));
+    while (m) {
+      const int src = __ffs(m) - 1;  // first lane of the lowest candidate vector: ascending u = list order
+      const int u = SV == 1 ? 0 : (SV == 2 ? src >> 4 : src >> 3);
+      m &= ~(SV == 1 ? 0xffffffffu : (SV == 2 ? 0xffffu << (u * 16) : 0xffu << (u * 8)));
+      const float cs = __shfl_sync(kFullMask, sc, src);
+      if (HALF) {
+        const long long g = cit.g0 + v0 + u;
+        if (tk.admits(cs, g)) tk.insert(cs, g);
+      } else if (tk.may_enter(cs)) {  // the threshold may have risen since the ballot
+        const long long id = __ldg(cit.ids + v0 + u);
+        if (tk.admits(cs, id)) tk.insert(cs, id);
+      }
+    }
+  };
   while (in_flight > 0) {
-    if (c_left == 0) {
+    if (c_left == 0) {  // (nothing is pending here: an item's last stage is finished before the next item starts)
       c_item = fifo[fifo_tail & (kFifo - 1)];
       ++fifo_tail;
       cit = load_ring_item<HALF>(items + c_item, half_slabs, slab_shift, P);
@@ -230,65 +272,46 @@ __device__ __forceinline__ void ivf_scan_ring_body(const float* __restrict__ Q, 
     tc::mbar_wait(bars + stage, parity);
     const unsigned char* sp = my_ring + (size_t)stage * SB;
     float acc[SV];
-    if (HALF) {
-      uint4 x[SV][4];
+    uint4 x[SV][HALF ? 4 : 8];
 #pragma unroll
-      for (int u = 0; u < SV; ++u)
+    for (int u = 0; u < SV; ++u)
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-          if (u < nv) x[u][jj] = *reinterpret_cast<const uint4*>(sp + (size_t)u * VB + (size_t)(jj * 32 + lane) * 16);
-#pragma unroll
-      for (int u = 0; u < SV; ++u) {
-        acc[u] = 0.f;
-        if (u < nv) {
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) acc[u] = dot8r(x[u][jj], qv[2 * jj], qv[2 * jj + 1], acc[u]);
-        }
-      }
-    } else {
-      float4 x[SV][8];
-#pragma unroll
-      for (int u = 0; u < SV; ++u)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (u < nv) x[u][j] = *reinterpret_cast<const float4*>(sp + (size_t)u * VB + (size_t)(j * 32 + lane) * 16);
-#pragma unroll
-      for (int u = 0; u < SV; ++u) {
-        acc[u] = 0.f;
-        if (u < nv) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[u] = dot4r(x[u][j], qv[j], acc[u]);
-        }
-      }
-    }
-    // the stage's bytes are in registers: hand it back to the bulk-copy engine before the (latency-bound)
-    // reduction and top-k update.  The refill is issued by lane 0 after the warp barrier, i.e. after every
-    // lane's shared-memory reads of this stage have been performed (same ordering the mbarrier-based
-    // consumer-release of a TMA pipeline relies on).
+      for (int j = 0; j < (HALF ? 4 : 8); ++j)
+        if (u < nv) x[u][j] = *reinterpret_cast<const uint4*>(sp + (size_t)u * VB + (size_t)(j * 32 + lane) * 16);
+    // the stage's bytes are on their way to registers: hand the buffer back to the bulk-copy engine.  The
+    // refill is issued by lane 0 after the warp barrier, i.e. after every lane's shared-memory reads of this
+    // stage have been performed (the ordering an mbarrier-based consumer release of a TMA pipeline relies on).
     __syncwarp();
     --in_flight;
     produce(stage);
     __syncwarp();
-    // lane l now gets the score of vector u(l) = l / (32 / SV); one ballot finds the (rare) candidates
-    const float sc = warp_sum_transposed<SV>(acc, lane);
-    const int my_u = SV == 1 ? 0 : (SV == 2 ? lane >> 4 : lane >> 3);
-    unsigned m = __ballot_sync(kFullMask, my_u < nv && tk.may_enter(sc));
-    while (m) {
-      const int src = __ffs(m) - 1;  // first lane of the lowest candidate vector: ascending u = list order
-      const int u = SV == 1 ? 0 : (SV == 2 ? src >> 4 : src >> 3);
-      m &= ~(SV == 1 ? 0xffffffffu : (SV == 2 ? 0xffffu << (u * 16) : 0xffu << (u * 8)));
-      const float cs = __shfl_sync(kFullMask, sc, src);
-      if (HALF) {
-        const long long g = cit.g0 + c_v + u;
-        if (tk.admits(cs, g)) tk.insert(cs, g);
-      } else if (tk.may_enter(cs)) {  // the threshold may have risen since the ballot
-        const long long id = __ldg(cit.ids + c_v + u);
-        if (tk.admits(cs, id)) tk.insert(cs, id);
+    // previous stage: reduction (shuffle chain) — independent of this stage's FMA chains below
+    const float sc_prev = warp_sum_transposed<SV>(pend, lane);
+#pragma unroll
+    for (int u = 0; u < SV; ++u) {
+      acc[u] = 0.f;
+      if (u < nv) {
+        if (HALF) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[u] = dot8r(x[u][jj], qv[2 * jj], qv[2 * jj + 1], acc[u]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[u] = dot4r(*reinterpret_cast<const float4*>(&x[u][j]), qv[j], acc[u]);
+        }
       }
     }
+    offer(sc_prev, pend_nv, pend_v);
+#pragma unroll
+    for (int u = 0; u < SV; ++u) pend[u] = acc[u];
+    pend_nv = nv;
+    pend_v = c_v;
     c_v += nv;
     c_left -= nv;
-    if (c_left == 0) tk.store(part_s + (size_t)c_item * k, part_id + (size_t)c_item * k);
+    if (c_left == 0) {  // the item ends with this stage: finish it now
+      offer(warp_sum_transposed<SV>(pend, lane), pend_nv, pend_v);
+      pend_nv = 0;
+      tk.store(part_s + (size_t)c_item * k, part_id + (size_t)c_item * k);
+    }
     if (++stage == depth) {
       stage = 0;
       parity ^= 1;
@@ -300,13 +323,13 @@ __device__ __forceinline__ void ivf_scan_ring_body(const float* __restrict__ Q, 
   const float *__restrict__ Q, const ScanItem *__restrict__ items, const int *__restrict__ n_items_ptr,           \
       int *__restrict__ queue_counter, const int *__restrict__ order, int k, float *__restrict__ part_s,          \
       long long *__restrict__ part_id, const unsigned short *const *__restrict__ half_slabs, int slab_shift, int P, \
-      int depth
+      int depth_and_hint
 
 // Full-size variant: whatever registers the compiler wants (120-165), several CTAs per SM when alone on the GPU.
 template <int SLOTS, bool HALF, int SV>
 __global__ void ivf_scan_ring_kernel(ABSB_RING_ARGS) {
   ivf_scan_ring_body<SLOTS, HALF, SV>(Q, items, n_items_ptr, queue_counter, order, k, part_s, part_id, half_slabs,
-                                      slab_shift, P, depth);
+                                      slab_shift, P, depth_and_hint);
 }
 
 // Co-resident variant: capped at 96 registers so that ONE CTA of 8 warps (24,576 registers, 64 KB of ring) fits
@@ -314,7 +337,7 @@ __global__ void ivf_scan_ring_kernel(ABSB_RING_ARGS) {
 template <int SLOTS, bool HALF, int SV>
 __global__ __maxnreg__(96) void ivf_scan_ring_small_kernel(ABSB_RING_ARGS) {
   ivf_scan_ring_body<SLOTS, HALF, SV>(Q, items, n_items_ptr, queue_counter, order, k, part_s, part_id, half_slabs,
-                                      slab_shift, P, depth);
+                                      slab_shift, P, depth_and_hint);
 }
 
 template <typename Kern>
@@ -334,7 +357,7 @@ void launch_ring(Kern kern, const ScanRing& r, int sm_count, int ctas_per_sm, in
     if (per_sm < 1) per_sm = 1;
   }
   kern<<<sm_count * per_sm, warps * 32, smem, st>>>(Q, items, n_items, queue_counter, order, k, part_s, part_id,
-                                                    half_slabs, slab_shift, P, depth);
+                                                    half_slabs, slab_shift, P, depth | (r.l2_evict_first ? 0x100 : 0));
   ABSB_CUDA(cudaGetLastError());
 }
 

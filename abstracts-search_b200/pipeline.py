@@ -4,11 +4,15 @@
     stream E (high priority)   encode(i+1)  [H2D ids] -> 28 Qwen2 layers -> pool/Dense/normalise -> all-gather
     stream S                   search(i)    coarse GEMM -> plan -> fine scan -> merge -> exchange [-> D2H]
 
-The encoder is tensor-bound and the fine scan HBM-bound, so running them at the same time hides the shorter
-one.  For that the two kernels have to share SMs: the scan runs in its co-resident shape (one 8-warp,
-64 KB, <= 96-register CTA per SM: `IndexIVFFlat.set_scan_impl(2)`) and the encoder's GEMM CTAs leave room
-for it (`absb_gemm_set_smem_budget`: 4-5 operand stages instead of 5-7, 104 registers).  Results are
-bit-identical to the serial path — same kernels, same arithmetic, only the schedule differs.
+With full-size kernels on both streams the overlap is what the block scheduler finds at kernel boundaries
+(the scan moves in as the GEMM CTAs of the other stream drain) plus the host<->device copies; measured gain
+3-6% of a step.  `coresident=True` makes the two kernels SHARE SMs for the whole scan: the scan runs in its
+co-resident shape (one 8-warp, 64 KB, <= 96-register CTA per SM: `IndexIVFFlat.set_scan_impl(2)`) and the
+encoder's GEMM / attention CTAs leave room for it (`absb_gemm_set_smem_budget`: 4-5 operand stages instead of
+5-7, 104 registers, max-shared carveout everywhere).  On B200 the kernels then do run concurrently
+(profiles/r02_overlap_timeline.md) but the small-M GEMMs are HBM-latency-bound themselves and slow down 1.6x
+under the scan's traffic while the 8-warp scan needs 4.2 ms instead of 1.8 ms: no net gain, hence off by
+default.  Results are bit-identical either way — same arithmetic, only the schedule differs.
 
 Inputs are token ids (the offline stand-in for tokenizer output): CUDA tensors for a device-resident
 pipeline, or pinned host tensors — then every batch's ids are copied host->device on stream E and its
@@ -23,7 +27,7 @@ COEXIST_GEMM_SMEM = 161 * 1024  # bytes one GEMM CTA may take next to a 64 KB sc
 
 class QueryPipeline:
     def __init__(self, encoder, index, k: int = 10, nprobe: int | None = None, batch: int = 512, tokens: int = 32,
-                 sharded=None, px_emb=None, coresident: bool = True, depth: int = 2):
+                 sharded=None, px_emb=None, coresident: bool = False, depth: int = 2):
         """`index`: this GPU's IndexIVFFlat; `sharded`: its ShardedIndexIVFFlat when the index is list-sharded over
         ranks (then `batch` is the WHOLE-JOB batch, this rank encodes batch / world of it and `px_emb` — a
         PeerExchange — or NCCL all-gathers the embeddings)."""

@@ -79,9 +79,10 @@ def parse_args():
                     help="1 (default): QueryPipeline — consecutive batches software-pipelined on two streams (the tensor-bound "
                          "encode of batch i+1 overlaps the HBM-bound search of batch i; the scan runs as one small CTA per SM "
                          "beside the GEMM CTAs); the timed region covers fill and drain.  0: encode then search, one stream")
-    ap.add_argument("--no-coresident", action="store_true",
-                    help="pipeline without the SM-sharing shapes (full-size scan CTAs, full GEMM shared memory): the streams "
-                         "then mostly serialise; for A/B measurements")
+    ap.add_argument("--coresident", action="store_true",
+                    help="pipeline with the SM-sharing shapes (one register-capped 8-warp scan CTA per SM beside GEMM CTAs with a "
+                         "smaller operand ring).  Measured on B200 (profiles/r02_overlap_timeline.md): the kernels do run at the "
+                         "same time, but each slows the other down by as much as the overlap saves, so it is off by default")
     ap.add_argument("--scan-impl", type=int, default=1, help="fine scan of the serial path: 1 shared-memory ring (cp.async.bulk), 0 registers")
     ap.add_argument("--ring", default="", help="ring geometry warps,depth,stage_vecs of --scan-impl 1 (default 4,3,1)")
     ap.add_argument("--two-stage", type=int, default=64,
@@ -676,7 +677,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     pipe = None
     if args.pipeline:
         pipe = P.QueryPipeline(enc, ix, k=k, nprobe=args.nprobe, batch=nq, tokens=S, sharded=sh, px_emb=px_emb,
-                               coresident=not args.no_coresident)
+                               coresident=args.coresident)
 
         def run_pipelined(steps, host=False):
             """`steps` batches end to end; encode(i + 1) is in flight with search(i).  host=True: pinned host
@@ -881,7 +882,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "two_stage_fallback_note": "summed over ranks, warm-up + timed + instrumented + e2e steps, %d queries each" % nq,
                 "pipeline": (("QueryPipeline, two streams: encode of batch i+1 overlaps search of batch i; K batches timed end to end "
                               "including fill and drain; " + ("scan as one 8-warp 64 KB CTA per SM beside the GEMM CTAs (161 KB)"
-                                                               if not args.no_coresident else "no SM-sharing shapes"))
+                                                               if args.coresident else "full-size kernels on both streams"))
                              if args.pipeline else "none: encode then search, one stream"),
                 "ms_per_step_serial_same_run": ms_serial,
                 "exchange": exchange, "index_build_s": build_s, "distinct_probed_lists_per_step": distinct_lists,

@@ -239,6 +239,12 @@ int absb_ivf_last_stats(absb_ivf_t h, int64_t* vectors_scanned, int64_t* bytes_s
 int absb_ivf_set_profile(absb_ivf_t h, int on);
 int absb_ivf_get_profile(absb_ivf_t h, double* scan_ms, double* coarse_gemm_ms, double* other_ms,
                          int64_t* scan_launches);
+/* Timeline of the kernel spans recorded since absb_*_set_profile(.., 1|2) (before absb_*_get_profile folds them):
+ * out[i] = {kind, start_ms, stop_ms} relative to base_event (a cudaEvent_t the caller recorded).  kinds: index 0
+ * fine scan, 1 coarse GEMM, 2 other; encoder 0 GEMM, 1 attention, 2 other.  Used to show which kernels of the
+ * two QueryPipeline streams run at the same time. */
+int absb_ivf_profile_spans(absb_ivf_t h, void* base_event, float* out, int64_t cap, int64_t* n);
+int absb_enc_profile_spans(absb_enc_t e, void* base_event, float* out, int64_t cap, int64_t* n);
 /* Replays ONLY the fine-scan kernel of the most recent *_dev search (same work items) `iters`
  * times on `stream` and returns the mean duration in ms measured with CUDA events on that
  * stream — used by bench.py for roofline.achieved. */
