@@ -123,6 +123,7 @@ _SIGS = {
     "absb_ivf_set_profile": ([_H, c_int], c_int),
     "absb_ivf_get_profile": ([_H, _PD, _PD, _PD, _PI64], c_int),
     "absb_ivf_time_scan": ([_H, c_int, c_void_p, _PF], c_int),
+    "absb_ivf_get_profile_scan16": ([_H, _PD, _PI64], c_int),
     "absb_ivf_profile_spans": ([_H, c_void_p, c_void_p, c_int64, _PI64], c_int),
     "absb_enc_profile_spans": ([_H, c_void_p, c_void_p, c_int64, _PI64], c_int),
     # encoder

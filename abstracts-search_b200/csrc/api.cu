@@ -78,6 +78,16 @@ struct absb_peer_s {
 
 #define NEED(p) ABSB_CHECK((p) != nullptr, ABSB_ERR_INVALID, "null argument: " #p)
 
+namespace absb {
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ABSB_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+}  // namespace absb
+
 extern "C" {
 
 // ------------------------------------------------------------------ library -----------------
@@ -897,8 +907,9 @@ int absb_ivf_set_profile(absb_ivf_t h, int on) {
   if (ix.profile) ix.fold_profile();
   ix.profile = on != 0;
   if (on == 2) {
-    ix.prof_ms[0] = ix.prof_ms[1] = ix.prof_ms[2] = 0;
+    ix.prof_ms[0] = ix.prof_ms[1] = ix.prof_ms[2] = ix.prof_ms[3] = 0;
     ix.prof_scan_launches = 0;
+    ix.prof_scan16_launches = 0;
   }
   ABSB_API_END
 }
@@ -941,6 +952,18 @@ int absb_ivf_profile_spans(absb_ivf_t h, void* base_event, float* out, int64_t c
   NEED(h); NEED(base_event); NEED(out); NEED(n);
   DeviceGuard g(h->ix.device);
   *n = dump_spans(h->ix.ev_pool, h->ix.ev_used, h->ix.ev_kind, base_event, out, cap);
+  ABSB_API_END
+}
+
+int absb_ivf_get_profile_scan16(absb_ivf_t h, double* scan16_ms, int64_t* scan16_launches) {
+  ABSB_API_BEGIN
+  NEED(h);
+  IvfIndex& ix = h->ix;
+  DeviceGuard g(ix.device);
+  ABSB_CUDA(cudaDeviceSynchronize());
+  ix.fold_profile();
+  if (scan16_ms) *scan16_ms = ix.prof_ms[3];
+  if (scan16_launches) *scan16_launches = ix.prof_scan16_launches;
   ABSB_API_END
 }
 

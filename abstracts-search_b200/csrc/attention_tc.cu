@@ -76,6 +76,7 @@ __global__ __launch_bounds__(kThreads) void attention_tc_kernel(const __grid_con
     nheads = min(p.heads_per_blk, group - h0);
   }
 
+  pdl_trigger();
   if (tid == 0) {
     tc::prefetch_tmap(&tmQ);
     tc::prefetch_tmap(&tmKV);
@@ -86,6 +87,7 @@ __global__ __launch_bounds__(kThreads) void attention_tc_kernel(const __grid_con
     tc::tmem_alloc<1>(tmem_slot, kTmemCols);
     tc::tmem_relinquish<1>();
   }
+  pdl_wait();  // global memory from here on
   // key bias: 0 for real tokens of this sequence, -inf for padding and for the rows past S
   for (int k = tid; k < NK; k += kThreads) sBias[k] = (k < S && p.mask[tok0 + k] != 0) ? 0.f : -INFINITY;
   tc::tcgen05_fence_before();
@@ -280,6 +282,7 @@ __device__ __forceinline__ void attention_tc_persistent_body(const CUtensorMap& 
   const int group = p.nh / p.nkv;
   const int S = p.S;
 
+  pdl_trigger();
   if (tid == 0) {
     tc::prefetch_tmap(&tmQ);
     tc::prefetch_tmap(&tmKV);
@@ -303,6 +306,7 @@ __device__ __forceinline__ void attention_tc_persistent_body(const CUtensorMap& 
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the set-up above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
     // ===================== producer =====================
@@ -628,14 +632,14 @@ void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, 
     // co-resident mode (the GEMMs run under a reduced shared-memory budget): register-capped twin, if its
     // shared memory also fits beside the scan CTA
     const bool small = gemm_coresident_mode() && smem_p <= 161 * 1024;
+    const dim3 g(grid_p), b(kPThreads);
     if (kvs == 2) {
-      if (small) attention_tc_persistent_small_kernel<2><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
-      else attention_tc_persistent_kernel<2><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
+      if (small) launch_pdl(attention_tc_persistent_small_kernel<2>, g, b, smem_p, st, tmQ, tmKV, p, total, tiles_per_unit);
+      else launch_pdl(attention_tc_persistent_kernel<2>, g, b, smem_p, st, tmQ, tmKV, p, total, tiles_per_unit);
     } else {
-      if (small) attention_tc_persistent_small_kernel<1><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
-      else attention_tc_persistent_kernel<1><<<grid_p, kPThreads, smem_p, st>>>(tmQ, tmKV, p, total, tiles_per_unit);
+      if (small) launch_pdl(attention_tc_persistent_small_kernel<1>, g, b, smem_p, st, tmQ, tmKV, p, total, tiles_per_unit);
+      else launch_pdl(attention_tc_persistent_kernel<1>, g, b, smem_p, st, tmQ, tmKV, p, total, tiles_per_unit);
     }
-    ABSB_CUDA(cudaGetLastError());
     return;
   }
   const size_t smem = 1024 + 2 * 128 * 128 + 4 * (size_t)p.NK * 128 + 256 * 4 + 4 * 8 + 16;
@@ -645,8 +649,7 @@ void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, 
     configured = true;
   }
   dim3 grid((unsigned)blocks, (unsigned)nkv, (unsigned)B);
-  attention_tc_kernel<<<grid, kThreads, smem, st>>>(tmQ, tmKV, p);
-  ABSB_CUDA(cudaGetLastError());
+  launch_pdl(attention_tc_kernel, grid, dim3(kThreads), smem, st, tmQ, tmKV, p);
 }
 
 }  // namespace absb

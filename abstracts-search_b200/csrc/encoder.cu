@@ -28,6 +28,8 @@ constexpr unsigned kFull = 0xffffffffu;
 // ------------------------------------------------------------------ small kernels -----------
 __global__ void embed_kernel(int64_t T, int H, int vocab, const long long* __restrict__ ids,
                              const bf16* __restrict__ table, float* __restrict__ h) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (w >= T) return;
@@ -72,6 +74,8 @@ __device__ __forceinline__ void rms_store(OUT* __restrict__ y, size_t t, int H, 
 template <typename OUT>
 __global__ void rmsnorm_kernel(int64_t T, int H, float eps, const float* __restrict__ x,
                                const float* __restrict__ w, OUT* __restrict__ y, float* __restrict__ rinv_out) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (t >= T) return;
@@ -120,6 +124,8 @@ __global__ void rmsnorm_kernel(int64_t T, int H, float eps, const float* __restr
 // h[b,s,j] * rinv[b,s] / max(sum_s m[b,s], 1e-9)   (sentence-transformers Pooling, mean mode).
 __global__ void pool_kernel(int S, int H, const float* __restrict__ h, const float* __restrict__ rinv,
                             const int* __restrict__ mask, const float* __restrict__ w, bf16* __restrict__ pooled) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= H) return;
@@ -136,6 +142,8 @@ __global__ void pool_kernel(int S, int H, const float* __restrict__ h, const flo
 
 // One warp per row: x /= max(||x||_2, 1e-12)   (torch.nn.functional.normalize)
 __global__ void l2norm_kernel(int64_t B, int E, float* __restrict__ x) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (r >= B) return;
@@ -177,6 +185,8 @@ __global__ __launch_bounds__(kAttnWarps * 32) void attention_kernel(const bf16* 
   __shared__ __align__(16) bf16 sK[kKT][kRowPad];
   __shared__ __align__(16) bf16 sV[kKT][kRowPad];
   __shared__ float sBias[kKT];
+  pdl_trigger();
+  pdl_wait();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -670,8 +680,7 @@ struct Encoder {
     last_launches = 0;
     {
       Span sp(this, st, 2);
-      embed_kernel<<<wblocks, 256, 0, st>>>(T, H, cfg.vocab_size, ids, embed.p, h.p);
-      ABSB_CUDA(cudaGetLastError());
+      launch_pdl(embed_kernel, dim3(wblocks), dim3(256), 0, st, T, H, cfg.vocab_size, ids, embed.p, h.p);
     }
     ++last_launches;
     const float scale_log2 = (1.0f / sqrtf((float)kHD)) * 1.4426950408889634f;
@@ -679,8 +688,7 @@ struct Encoder {
       Layer& L = layers[l];
       {
         Span sp(this, st, 2);
-        rmsnorm_kernel<bf16><<<wblocks, 256, 0, st>>>(T, H, cfg.rms_eps, h.p, L.ln1.p, xn.p, nullptr);
-        ABSB_CUDA(cudaGetLastError());
+        launch_pdl(rmsnorm_kernel<bf16>, dim3(wblocks), dim3(256), 0, st, T, H, cfg.rms_eps, h.p, L.ln1.p, xn.p, nullptr);
       }
       {
         // QKV projection with bias and RoPE (q and k heads) fused into the epilogue
@@ -700,16 +708,15 @@ struct Encoder {
         } else {
           const int units = (nh / nkv) * (int)ceil_div(S, 16);
           dim3 grid((unsigned)ceil_div(units, kAttnWarps), (unsigned)nkv, (unsigned)B);
-          attention_kernel<<<grid, kAttnWarps * 32, 0, st>>>(qkv.p, QKV, mask, ao.p, nh * kHD, S, nh, nkv, cfg.causal, scale_log2);
-          ABSB_CUDA(cudaGetLastError());
+          launch_pdl(attention_kernel, grid, dim3(kAttnWarps * 32), 0, st, qkv.p, QKV, mask, ao.p, nh * kHD, S, nh, nkv, cfg.causal,
+                     scale_log2);
         }
       }
       last_flops += 4.0 * (double)B * S * S * kHD * nh;
       gemm(EPI_F32_ADD, (int)T, H, nh * kHD, ao.p, L.wo.p, h.p, H, nullptr, st);
       {
         Span sp(this, st, 2);
-        rmsnorm_kernel<bf16><<<wblocks, 256, 0, st>>>(T, H, cfg.rms_eps, h.p, L.ln2.p, xn.p, nullptr);
-        ABSB_CUDA(cudaGetLastError());
+        launch_pdl(rmsnorm_kernel<bf16>, dim3(wblocks), dim3(256), 0, st, T, H, cfg.rms_eps, h.p, L.ln2.p, xn.p, nullptr);
       }
       gemm(EPI_SWIGLU_BF16, (int)T, 2 * I, H, xn.p, L.wgu.p, act.p, I, nullptr, st);
       gemm(EPI_F32_ADD, (int)T, H, I, act.p, L.wd.p, h.p, H, nullptr, st);
@@ -717,17 +724,14 @@ struct Encoder {
     }
     {
       Span sp(this, st, 2);
-      rmsnorm_kernel<bf16><<<wblocks, 256, 0, st>>>(T, H, cfg.rms_eps, h.p, final_norm.p, nullptr, rinv.p);
-      ABSB_CUDA(cudaGetLastError());
+      launch_pdl(rmsnorm_kernel<bf16>, dim3(wblocks), dim3(256), 0, st, T, H, cfg.rms_eps, h.p, final_norm.p, nullptr, rinv.p);
       dim3 pg((unsigned)ceil_div(H, 128), (unsigned)B);
-      pool_kernel<<<pg, 128, 0, st>>>(S, H, h.p, rinv.p, mask, final_norm.p, pooled.p);
-      ABSB_CUDA(cudaGetLastError());
+      launch_pdl(pool_kernel, pg, dim3(128), 0, st, S, H, h.p, rinv.p, mask, final_norm.p, pooled.p);
     }
     gemm(EPI_F32_BIAS, B, cfg.embed_dim, H, pooled.p, dense_w.p, out, cfg.embed_dim, dense_b.p, st);
     if (normalize) {
       Span sp(this, st, 2);
-      l2norm_kernel<<<(unsigned)ceil_div((int64_t)B * 32, 256), 256, 0, st>>>(B, cfg.embed_dim, out);
-      ABSB_CUDA(cudaGetLastError());
+      launch_pdl(l2norm_kernel, dim3((unsigned)ceil_div((int64_t)B * 32, 256)), dim3(256), 0, st, (int64_t)B, cfg.embed_dim, out);
       ++last_launches;
     }
     last_launches += 2;

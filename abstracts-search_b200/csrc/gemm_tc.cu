@@ -134,6 +134,7 @@ __global__ __maxnreg__(104) void gemm_bf16_tc_kernel(const __grid_constant__ CUt
   const int cta_rank = NCTA == 1 ? 0 : (int)tc::cluster_ctarank();
   const int worker = blockIdx.x / NCTA, num_workers = gridDim.x / NCTA;  // a worker = one CTA or one CTA pair
 
+  pdl_trigger();  // the next kernel of the stream may set itself up as soon as an SM has room for it
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
@@ -158,6 +159,9 @@ __global__ __maxnreg__(104) void gemm_bf16_tc_kernel(const __grid_constant__ CUt
   else tc::cluster_sync();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barriers, TMEM, tensor-map prefetch) overlapped the tail of the previous kernel; from
+  // here on global memory is touched
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own A rows and its share of B) ========
@@ -525,13 +529,15 @@ void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const vo
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = L::dyn(p.stages);
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NCTA;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   ABSB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
 }
 

@@ -372,8 +372,12 @@ IvfIndex::Span::Span(IvfIndex* ix_, cudaStream_t st_, int kind) : ix(ix_), st(st
 void IvfIndex::fold_profile() {
   for (size_t i = 0; i < ev_used; ++i) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ev_pool[i].first, ev_pool[i].second) == cudaSuccess) prof_ms[ev_kind[i]] += ms;
-    if (ev_kind[i] == 0) ++prof_scan_launches;
+    if (cudaEventElapsedTime(&ms, ev_pool[i].first, ev_pool[i].second) == cudaSuccess) {
+      prof_ms[ev_kind[i]] += ms;
+      if (ev_kind[i] == 3) prof_ms[0] += ms;  // the fp16 pass is part of the scan total
+    }
+    if (ev_kind[i] == 0 || ev_kind[i] == 3) ++prof_scan_launches;
+    if (ev_kind[i] == 3) ++prof_scan16_launches;
   }
   ev_used = 0;
   ev_kind.clear();
@@ -1067,7 +1071,7 @@ void IvfIndex::search_preassigned_dev(int64_t nq, const float* q, int k, int npr
       s16.sm_count = props.sm_count;
       s16.ctas_per_sm = scan_ctas_per_sm;
       {
-        Span sp(this, st, 0);
+        Span sp(this, st, 3);
         if (use_ring()) {
           ScanRing r16 = ring;
           r16.stage_vecs = ring.stage_vecs * 2;  // same stage bytes as the fp32 ring

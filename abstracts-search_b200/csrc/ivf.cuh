@@ -142,7 +142,8 @@ struct IvfIndex {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
   size_t ev_used = 0;
   std::vector<int> ev_kind;
-  double prof_ms[3] = {0, 0, 0};
+  double prof_ms[4] = {0, 0, 0, 0};  // [3] = the fp16 shortlist pass of the two-stage scan alone (also counted in [0])
+  int64_t prof_scan16_launches = 0;
   int64_t prof_scan_launches = 0;
   int64_t prof_vectors = 0;
   struct Span {

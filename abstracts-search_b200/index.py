@@ -427,7 +427,10 @@ class IndexIVFFlat:
 
         s, c, o, n = c_double(), c_double(), c_double(), c_int64()
         check(lib().absb_ivf_get_profile(self._h, byref(s), byref(c), byref(o), byref(n)))
-        return {"scan_ms": s.value, "coarse_gemm_ms": c.value, "other_ms": o.value, "scan_launches": n.value}
+        s16, n16 = c_double(), c_int64()
+        check(lib().absb_ivf_get_profile_scan16(self._h, byref(s16), byref(n16)))
+        return {"scan_ms": s.value, "coarse_gemm_ms": c.value, "other_ms": o.value, "scan_launches": n.value,
+                "scan16_ms": s16.value, "scan16_launches": n16.value}
 
     def time_scan(self, iters: int = 10) -> float:
         ms = c_float()

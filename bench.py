@@ -75,10 +75,11 @@ def parse_args():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: all-gathers of the query path as NVLink peer-memory stores fused into our kernels "
                          "(default) or as NCCL calls")
-    ap.add_argument("--pipeline", type=int, default=1,
-                    help="1 (default): QueryPipeline — consecutive batches software-pipelined on two streams (the tensor-bound "
-                         "encode of batch i+1 overlaps the HBM-bound search of batch i; the scan runs as one small CTA per SM "
-                         "beside the GEMM CTAs); the timed region covers fill and drain.  0: encode then search, one stream")
+    ap.add_argument("--pipeline", type=int, default=0,
+                    help="1: QueryPipeline — consecutive batches software-pipelined on two streams (encode of batch i+1 in flight "
+                         "with the search of batch i); the timed region covers fill and drain.  0 (default): encode then search on "
+                         "one stream, every kernel of the forward chained by programmatic dependent launch — measured faster "
+                         "(7.94 vs 8.18 ms per step at the 8-GPU per-GPU load, profiles/r02_overlap_timeline.md)")
     ap.add_argument("--coresident", action="store_true",
                     help="pipeline with the SM-sharing shapes (one register-capped 8-warp scan CTA per SM beside GEMM CTAs with a "
                          "smaller operand ring).  Measured on B200 (profiles/r02_overlap_timeline.md): the kernels do run at the "
@@ -810,28 +811,55 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     rooflines = {}
     if kernel_events:
         scan_step_ms = ix_prof["scan_ms"] / args.steps
+        hbm_src = pk["source"] + " copy bandwidth"
+        scan_name = "ivf_scan_ring_kernel" if args.scan_impl >= 1 else "ivf_scan_kernel"
         if args.two_stage:
-            # two-stage scan: the bytes the kernels actually have to move are the fp16 shadow codes of every
-            # probed vector plus the fp32 codes (+ ids) of the shortlist; the time is that of all three scan
-            # launches of a step (fp16 pass, fp32 re-score, fallback), so `achieved` is conservative.  The
-            # IndexIVFFlat-equivalent rate (algorithmic bytes of a single-pass fp32 scan / the same time) is
-            # reported next to it.
-            moved = st["vectors"] * 2048 + nq * args.two_stage * (1024 * 4 + 8)
-            scan_gbs = moved / (scan_step_ms * 1e-3) / 1e9 if scan_step_ms > 0 else 0.0
-            rooflines["ivf_scan16_kernel"] = {
-                "bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": scan_gbs / pk["hbm_gbs"],
-                "traffic": None, "peak_source": pk["source"] + " copy bandwidth",
-                "ms_per_launch": scan_step_ms, "ms_per_step": scan_step_ms, "bytes_moved_per_step": moved,
-                "ivfflat_algorithmic_bytes_per_step": st["bytes"], "vectors_per_step": st["vectors"],
+            # the fp16 shortlist pass alone: its algorithmic bytes are the fp16 shadow codes of every probed vector
+            ms16 = ix_prof["scan16_ms"] / max(1, ix_prof["scan16_launches"])
+            b16 = st["vectors"] * 2048
+            g16 = b16 / (ms16 * 1e-3) / 1e9 if ms16 > 0 else 0.0
+            rooflines[scan_name + "<fp16 shadow codes>"] = {
+                "bound": "hbm", "achieved": g16, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": g16 / pk["hbm_gbs"], "traffic": None,
+                "peak_source": hbm_src, "ms_per_launch": ms16, "ms_per_step": ms16 * ix_prof["scan16_launches"] / args.steps,
+                "algorithmic_bytes_per_launch": b16, "vectors_per_step": st["vectors"],
+                "note": "stage 1 of the two-stage scan: 2,048 B per probed vector; repeated probes of a list within a batch hit L2 "
+                        "(list-major queue), so DRAM traffic is below the algorithmic bytes and frac can exceed 1"}
+            # all three scan launches of a step together against the IndexIVFFlat algorithmic bytes (4,104 B per vector)
+            moved = b16 + nq * args.two_stage * (1024 * 4 + 8)
+            rooflines["two_stage_scan (fp16 pass + fp32 re-score + fallback)"] = {
+                "bound": "hbm", "achieved": moved / (scan_step_ms * 1e-3) / 1e9 if scan_step_ms > 0 else 0.0, "peak": pk["hbm_gbs"],
+                "unit": "GB/s", "frac": moved / (scan_step_ms * 1e-3) / 1e9 / pk["hbm_gbs"] if scan_step_ms > 0 else 0.0,
+                "traffic": None, "peak_source": hbm_src, "ms_per_launch": scan_step_ms, "ms_per_step": scan_step_ms,
+                "bytes_moved_per_step": moved, "ivfflat_algorithmic_bytes_per_step": st["bytes"],
                 "ivfflat_equivalent_gbs": st["bytes"] / (scan_step_ms * 1e-3) / 1e9 if scan_step_ms > 0 else 0.0,
-                "launches_per_step": ix_prof["scan_launches"] // max(1, args.steps),
-                "note": "fp16 shortlist pass + exact fp32 re-score + fallback launch timed together"}
+                "launches_per_step": ix_prof["scan_launches"] // max(1, args.steps)}
+            # the single-pass fp32 scan (IndexIVFFlat's own bytes) over the same work items, measured in the same run
+            ix.set_two_stage(0)
+            q_sp = last["emb"]
+            srch = (lambda: sh.search(q_sp, k)) if world > 1 else (lambda: ix.search(q_sp, k))
+            for _ in range(2):
+                srch()
+            ix.set_profile(2)
+            for _ in range(5):
+                srch()
+            sp_prof = ix.get_profile()
+            ix.set_profile(0)
+            st_sp = ix.last_stats()
+            ix.set_two_stage(args.two_stage)
+            ms_sp = sp_prof["scan_ms"] / max(1, sp_prof["scan_launches"])
+            g_sp = st_sp["bytes"] / (ms_sp * 1e-3) / 1e9 if ms_sp > 0 else 0.0
+            rooflines[scan_name + "<fp32 codes, single pass>"] = {
+                "bound": "hbm", "achieved": g_sp, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": g_sp / pk["hbm_gbs"], "traffic": None,
+                "peak_source": hbm_src, "ms_per_launch": ms_sp, "ms_per_step": 0.0, "algorithmic_bytes_per_launch": st_sp["bytes"],
+                "vectors_per_launch": st_sp["vectors"],
+                "note": "not part of the timed step (the step uses the two-stage scan): 5 single-pass searches of the step's own "
+                        "queries after the timed region; algorithmic bytes = probed vectors x (4 x 1024 + 8) (SURVEY 8d)"}
         else:
             scan_ms = ix_prof["scan_ms"] / max(1, ix_prof["scan_launches"])
             scan_gbs = st["bytes"] / max(1, ix_prof["scan_launches"] // args.steps) / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-            rooflines["ivf_scan_kernel"] = {
+            rooflines[scan_name + "<fp32 codes, single pass>"] = {
                 "bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": scan_gbs / pk["hbm_gbs"],
-                "traffic": None, "peak_source": pk["source"] + " copy bandwidth",
+                "traffic": None, "peak_source": hbm_src,
                 "ms_per_launch": scan_ms, "ms_per_step": scan_step_ms,
                 "algorithmic_bytes_per_step": st["bytes"], "vectors_per_step": st["vectors"]}
         gemm_tf = enc_prof["gemm_flops"] / (enc_prof["gemm_ms"] * 1e-3) / 1e12 if enc_prof["gemm_ms"] > 0 else 0.0

@@ -245,6 +245,9 @@ int absb_ivf_get_profile(absb_ivf_t h, double* scan_ms, double* coarse_gemm_ms, 
  * two QueryPipeline streams run at the same time. */
 int absb_ivf_profile_spans(absb_ivf_t h, void* base_event, float* out, int64_t cap, int64_t* n);
 int absb_enc_profile_spans(absb_enc_t e, void* base_event, float* out, int64_t cap, int64_t* n);
+/* Time and launch count of the fp16 shortlist pass of the two-stage scan alone (it is also part of scan_ms of
+ * absb_ivf_get_profile, which adds the fp32 re-score and the fallback launch). */
+int absb_ivf_get_profile_scan16(absb_ivf_t h, double* scan16_ms, int64_t* scan16_launches);
 /* Replays ONLY the fine-scan kernel of the most recent *_dev search (same work items) `iters`
  * times on `stream` and returns the mean duration in ms measured with CUDA events on that
  * stream — used by bench.py for roofline.achieved. */
