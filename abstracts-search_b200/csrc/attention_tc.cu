@@ -519,7 +519,7 @@ __device__ __forceinline__ void attention_tc_persistent_body(const CUtensorMap& 
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(p_ready + grp);
+      if (lane == 0) tc::mbar_arrive_relaxed(p_ready + grp);  // tcgen05.st waited for + fenced above
       // epilogue: two 64-column halves, both TMEM loads of a half in flight together
       tc::mbar_wait(o_full + grp, ph);
       tc::tcgen05_fence_after();
@@ -547,7 +547,7 @@ __device__ __forceinline__ void attention_tc_persistent_body(const CUtensorMap& 
       }
       tc::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(slot_free + grp);
+      if (lane == 0) tc::mbar_arrive_relaxed(slot_free + grp);  // TMEM reads only: do not wait for the output stores
     }
   }
 

@@ -110,11 +110,17 @@ __device__ __forceinline__ void tile_coords(const KernelParams& p, int tile, int
   }
 }
 
-// Register cap: 104 per thread (384 x 112 allocated = 43,008 of the SM's 65,536), so that one small CTA of the
-// shared-memory ring scan (ivf_scan_ring.cu: 8 warps x 80 registers) fits on the same SM while a GEMM of the
-// encoder is resident — the HBM-bound list scan of batch i runs under the tensor-bound encode of batch i+1.
+// ABSB_GEMM_MAXNREG (e.g. -DABSB_GEMM_MAXNREG=104): register cap for the SM-sharing experiment of
+// QueryPipeline(coresident=True) — 384 x 104 leaves room for the 8-warp scan CTA of ivf_scan_ring.cu on the
+// same SM (profiles/r02_overlap_timeline.md: measured, no net gain, so the default build keeps the
+// compiler's own allocation and the epilogues their prefetch registers).
+#ifdef ABSB_GEMM_MAXNREG
+#define ABSB_GEMM_BOUNDS __maxnreg__(ABSB_GEMM_MAXNREG)
+#else
+#define ABSB_GEMM_BOUNDS __launch_bounds__(kThreads, 1)
+#endif
 template <int BN, int EPI, int NCTA>
-__global__ __maxnreg__(104) void gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmC,
                                                                    const KernelParams p) {
@@ -310,45 +316,57 @@ __global__ __maxnreg__(104) void gemm_bf16_tc_kernel(const __grid_constant__ CUt
         const bool rotate = hc < p.rope_cols;
         // pair-major table: consecutive lanes (= consecutive positions) read consecutive float2
         const float2* cs = p.rope_cs + (row_ok ? row % p.rope_S : 0);
+        // 16 rotate-half pairs per step: the TMEM loads are issued first, then the global loads of this step's
+        // bias and (cos, sin) entries — all in flight together — and only then the wait; before, the table and
+        // bias loads started after the TMEM wait and their L2 latency was paid once per 8 columns.
 #pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t v1[32], v2[32];
-          tc::tmem_ld_32x32(t_base + chalf * 128 + c, v1);
-          tc::tmem_ld_32x32(t_base + chalf * 128 + 64 + c, v2);
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t v1[16], v2[16];
+          tc::tmem_ld_32x16(t_base + chalf * 128 + c, v1);
+          tc::tmem_ld_32x16(t_base + chalf * 128 + 64 + c, v2);
+          float ba[16], bb[16];
+          float2 t[16];
+          const bool live = row_ok && hc < p.N;
+          if (live && p.bias) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 x = __ldg(reinterpret_cast<const float4*>(p.bias + hc + c + e));
+              const float4 y = __ldg(reinterpret_cast<const float4*>(p.bias + hc + 64 + c + e));
+              ba[e] = x.x; ba[e + 1] = x.y; ba[e + 2] = x.z; ba[e + 3] = x.w;
+              bb[e] = y.x; bb[e + 1] = y.y; bb[e + 2] = y.z; bb[e + 3] = y.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) ba[e] = bb[e] = 0.f;
+          }
+          if (live && rotate) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) t[e] = __ldg(cs + (size_t)(c + e) * p.rope_ld);  // (cos, sin) of pair c + e
+          }
           tc::tmem_ld_wait();
-          if (row_ok && hc < p.N) {
+          if (live) {
+            float a[16], b[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              a[e] = __uint_as_float(v1[e]) + ba[e];
+              b[e] = __uint_as_float(v2[e]) + bb[e];
+            }
+            if (rotate) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float x0 = a[e], y0 = b[e];
+                a[e] = x0 * t[e].x - y0 * t[e].y;
+                b[e] = y0 * t[e].x + x0 * t[e].y;
+              }
+            }
             uint4* dst1 = reinterpret_cast<uint4*>(out + (size_t)row * p.ldc + hc + c);
             uint4* dst2 = reinterpret_cast<uint4*>(out + (size_t)row * p.ldc + hc + 64 + c);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float a[8], b[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                a[e] = __uint_as_float(v1[j * 8 + e]);
-                b[e] = __uint_as_float(v2[j * 8 + e]);
-              }
-              if (p.bias) {
-#pragma unroll
-                for (int e = 0; e < 8; e += 4) {
-                  const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + hc + c + j * 8 + e));
-                  const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + hc + 64 + c + j * 8 + e));
-                  a[e] += ba.x; a[e + 1] += ba.y; a[e + 2] += ba.z; a[e + 3] += ba.w;
-                  b[e] += bb.x; b[e + 1] += bb.y; b[e + 2] += bb.z; b[e + 3] += bb.w;
-                }
-              }
-              if (rotate) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float2 t = __ldg(cs + (size_t)(c + j * 8 + e) * p.rope_ld);  // (cos, sin) of pair c+j*8+e
-                  const float x0 = a[e], y0 = b[e];
-                  a[e] = x0 * t.x - y0 * t.y;
-                  b[e] = y0 * t.x + x0 * t.y;
-                }
-              }
-              dst1[j] = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]),
-                                   pack_bf16x2(a[6], a[7]));
-              dst2[j] = make_uint4(pack_bf16x2(b[0], b[1]), pack_bf16x2(b[2], b[3]), pack_bf16x2(b[4], b[5]),
-                                   pack_bf16x2(b[6], b[7]));
+            for (int j = 0; j < 2; ++j) {
+              dst1[j] = make_uint4(pack_bf16x2(a[j * 8], a[j * 8 + 1]), pack_bf16x2(a[j * 8 + 2], a[j * 8 + 3]),
+                                   pack_bf16x2(a[j * 8 + 4], a[j * 8 + 5]), pack_bf16x2(a[j * 8 + 6], a[j * 8 + 7]));
+              dst2[j] = make_uint4(pack_bf16x2(b[j * 8], b[j * 8 + 1]), pack_bf16x2(b[j * 8 + 2], b[j * 8 + 3]),
+                                   pack_bf16x2(b[j * 8 + 4], b[j * 8 + 5]), pack_bf16x2(b[j * 8 + 6], b[j * 8 + 7]));
             }
           }
         }
@@ -429,8 +447,9 @@ __global__ __maxnreg__(104) void gemm_bf16_tc_kernel(const __grid_constant__ CUt
       tc::tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (NCTA == 1 || cta_rank == 0) tc::mbar_arrive(tmem_empty + acc);
-        else tc::mbar_arrive_cluster(tmem_empty_addr0 + (uint32_t)(acc * 8));
+        // relaxed: only TMEM reads (already waited for and fenced) are handed over, not the tile's global stores
+        if (NCTA == 1 || cta_rank == 0) tc::mbar_arrive_relaxed(tmem_empty + acc);
+        else tc::mbar_arrive_cluster_relaxed(tmem_empty_addr0 + (uint32_t)(acc * 8));
       }
       if (++acc == 2) {
         acc = 0;
@@ -657,7 +676,9 @@ void gemm_bf16_tc_ex(int epi, int M, int N, int K, const void* A, int64_t lda, c
         const int64_t tm = ceil_div(M, 2 * BM);
         const int64_t cost256 = ceil_div(tm * ceil_div(N, 256), workers) * 256;
         const int64_t cost192 = ceil_div(tm * ceil_div(N, 192), workers) * 192;
-        if (cost192 * 100 < cost256 * 85) variant = 3;
+        // long-K GEMMs (FFN-down, K = 8960) are MMA-bound and gain from the finer wave balance of 192-column
+        // tiles earlier than the epilogue-bound short-K ones (r02i micro-bench, M = 16384: 334 vs 356 us)
+        if (cost192 * 100 < cost256 * (K >= 4096 ? 90 : 85)) variant = 3;
       }
     }
   }
