@@ -1,7 +1,7 @@
 // attention_tc.cu — bidirectional GQA attention of the stella/Qwen2 encoder on the 5th-generation
-// tensor cores, for sequences of up to 256 tokens (the bulk-encode batches of
-// `sidecar-search build -b 32`, /root/reference/Makefile:65, and app.py's queries, README.md:28;
-// SURVEY §2c E5).  Longer sequences (up to max_seq_len 512) take the mma.sync kernel in encoder.cu.
+// tensor cores (the bulk-encode batches of `sidecar-search build -b 32`, /root/reference/Makefile:65, and
+// app.py's queries, README.md:28): sequences of up to 256 tokens in one key block (below),
+// 257-512 tokens (stella's max_seq_length) in two key blocks (attention_tc_long_kernel).
 //
 // One CTA = one 128-row tile of queries of one (sequence, kv head): the rows are 128 consecutive
 // positions of one q head (S >= 128) or the whole sequences of several q heads that share the kv
@@ -210,6 +210,204 @@ __global__ __launch_bounds__(kThreads) void attention_tc_kernel(const __grid_con
   }
 }
 
+
+// ================================================================================================
+// 256 < S <= 512 (stella's max_seq_length): the score tile of 512 keys would take all 512 TMEM columns and
+// K + V (256 KB) no longer fit shared memory, so the keys are processed as TWO blocks of <= 256:
+//
+//   block b:  S_b = Q K_b^T  -> TMEM cols [0, 256)         (tcgen05.mma SS)
+//             softmax over the block: (m_b, l_b) per row, P_b = exp2(S_b - m_b) back into cols [0, 128)
+//             O_b = P_b V_b  -> TMEM cols [256 + 128 b, 384 + 128 b)   (tcgen05.mma TS)
+//   epilogue: O = (a_0 O_0 + a_1 O_1) / (a_0 l_0 + a_1 l_1),  a_b = exp2(m_b - max(m_0, m_1))
+//
+// Each block keeps its OWN accumulator, so no accumulator is ever rescaled in TMEM (no tcgen05.ld / st
+// round trip of O as in an online-softmax kernel); the combination costs two TMEM reads in the epilogue.
+// K_1 is fetched while the softmax of block 0 runs (its buffer is free once S_0 is complete), V_1 after
+// O_0 = P_0 V_0.  One CTA = 128 consecutive positions of one q head; K / V of a (sequence, kv head) are
+// re-read from L2 by its 6 x 4 tiles.
+// ================================================================================================
+constexpr int kLongKB = 256;  // keys per block
+
+__global__ __launch_bounds__(kThreads) void attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                     const __grid_constant__ CUtensorMap tmKV,
+                                                                     const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr uint32_t kv_half = (uint32_t)kLongKB * 128u;  // bytes of one 64-column half of a K or V block
+  uint8_t* sQ = smem;                            // [2][128][128 B]
+  uint8_t* sK = sQ + 2 * 128 * 128;              // [2][256][128 B]
+  uint8_t* sV = sK + 2 * kv_half;                // [2][256][128 B]
+  float* sBias = reinterpret_cast<float*>(sV + 2 * kv_half);  // [512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 512);  // qk_full, v_full, s_done, o_done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int blk = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int group = p.nh / p.nkv;
+  const int S = p.S;
+  const int64_t tok0 = (int64_t)b * S;
+  const int h0 = blk / p.blks_per_head;
+  const int p0 = (blk % p.blks_per_head) * 128;
+  const int nk1 = ((S - kLongKB + 15) / 16) * 16;  // keys of block 1 that the MMAs touch (16 .. 256)
+
+  pdl_trigger();
+  if (tid == 0) {
+    tc::prefetch_tmap(&tmQ);
+    tc::prefetch_tmap(&tmKV);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(bars + i, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) {
+    tc::tmem_alloc<1>(tmem_slot, 512);
+    tc::tmem_relinquish<1>();
+  }
+  pdl_wait();  // global memory from here on
+  for (int k = tid; k < 2 * kLongKB; k += kThreads) sBias[k] = (k < S && p.mask[tok0 + k] != 0) ? 0.f : -INFINITY;
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int pos = p0 + tid;
+  const bool row_ok = pos < S;
+  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t idesc2 = tc::make_idesc_bf16_f32(128, kHD, 1);
+  const int k_col = (p.nh + kvh) * kHD, v_col = (p.nh + p.nkv + kvh) * kHD;
+
+  if (tid == 0) {
+    // Q + K_0 on one barrier, V_0 on another (rows past the end of the tensor are zero-filled by TMA, rows of
+    // the next sequence are finite numbers: both are masked out by sBias)
+    tc::mbar_arrive_expect_tx(bars + 0, 2u * 16384u + 2 * kv_half);
+    for (int half = 0; half < 2; ++half)
+      tc::tma_load_2d(sQ + half * 16384, &tmQ, bars + 0, (kvh * group + h0) * kHD + half * 64, (int)(tok0 + p0));
+    for (int half = 0; half < 2; ++half) tc::tma_load_2d(sK + half * kv_half, &tmKV, bars + 0, k_col + half * 64, (int)tok0);
+    tc::mbar_arrive_expect_tx(bars + 1, 2 * kv_half);
+    for (int half = 0; half < 2; ++half) tc::tma_load_2d(sV + half * kv_half, &tmKV, bars + 1, v_col + half * 64, (int)tok0);
+  }
+  float m_blk[2], l_blk[2];
+#pragma unroll 1
+  for (int kb = 0; kb < 2; ++kb) {
+    const int nk = kb == 0 ? kLongKB : nk1;
+    const int key0 = kb * kLongKB;
+    const uint32_t ph = (uint32_t)kb;
+    if (tid == 0) {
+      // ---- S_kb = Q K_kb^T ----
+      tc::mbar_wait(bars + 0, ph);
+      tc::tcgen05_fence_after();
+      const uint32_t idesc1 = tc::make_idesc_bf16_f32(128, nk);
+#pragma unroll
+      for (int j = 0; j < kHD / 16; ++j) {
+        const uint32_t off = (uint32_t)(j >> 2), within = (uint32_t)(j & 3) * 32u;
+        const uint64_t da = tc::make_kmajor_sw128_desc(tc::smem_u32(sQ) + off * 16384u + within);
+        const uint64_t db = tc::make_kmajor_sw128_desc(tc::smem_u32(sK) + off * kv_half + within);
+        tc::umma_bf16<1>(tmem_base, da, db, idesc1, j != 0 ? 1u : 0u);
+      }
+      tc::umma_commit<1>(bars + 2);
+    }
+    __syncwarp();
+    tc::mbar_wait(bars + 2, ph);
+    tc::tcgen05_fence_after();
+    if (tid == 0 && kb == 0) {
+      // S_0 is complete, so the K buffer is free: fetch K_1 under the softmax of block 0
+      tc::mbar_arrive_expect_tx(bars + 0, 2 * kv_half);
+      for (int half = 0; half < 2; ++half)
+        tc::tma_load_2d(sK + half * kv_half, &tmKV, bars + 0, k_col + half * 64, (int)tok0 + kLongKB);
+    }
+    __syncwarp();
+    // ---- softmax of the block: thread = tile row = TMEM lane ----
+    float m = -INFINITY;
+    for (int c = 0; c < nk; c += 32) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(t_row + c, v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float sc = __uint_as_float(v[j]) * p.scale_log2 + ((c + j < nk) ? sBias[key0 + c + j] : -INFINITY);
+        if (p.causal && key0 + c + j > pos) sc = -INFINITY;
+        m = fmaxf(m, sc);
+      }
+    }
+    const float m_safe = (m == -INFINITY || !(m == m)) ? 0.f : m;
+    float sum = 0.f;
+    for (int c = 0; c < nk; c += 32) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(t_row + c, v);
+      tc::tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float s0 = __uint_as_float(v[2 * j]) * p.scale_log2 + ((c + 2 * j < nk) ? sBias[key0 + c + 2 * j] : -INFINITY);
+        float s1 = __uint_as_float(v[2 * j + 1]) * p.scale_log2 + ((c + 2 * j + 1 < nk) ? sBias[key0 + c + 2 * j + 1] : -INFINITY);
+        if (p.causal) {
+          if (key0 + c + 2 * j > pos) s0 = -INFINITY;
+          if (key0 + c + 2 * j + 1 > pos) s1 = -INFINITY;
+        }
+        const float e0 = exp2f(s0 - m_safe), e1 = exp2f(s1 - m_safe);
+        sum += e0 + e1;
+        pk[j] = pack2(e0, e1);
+      }
+      tc::tmem_st_32x16(t_row + (c >> 1), pk);  // P over the consumed low columns of S
+    }
+    m_blk[kb] = m;
+    l_blk[kb] = sum;
+    tc::tmem_st_wait();
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      // ---- O_kb = P_kb V_kb into its own accumulator ----
+      tc::tcgen05_fence_after();
+      tc::mbar_wait(bars + 1, ph);
+      tc::tcgen05_fence_after();
+      const uint32_t o_col = 256u + (uint32_t)kb * 128u;
+      for (int j = 0; j < nk / 16; ++j) {
+        const uint64_t db = tc::make_mnmajor_sw128_desc(tc::smem_u32(sV) + (uint32_t)j * 2048u, kv_half);
+        tc::umma_bf16_ts(tmem_base + o_col, tmem_base + (uint32_t)(j * 8), db, idesc2, j != 0 ? 1u : 0u);
+      }
+      tc::umma_commit<1>(bars + 3);
+      if (kb == 0) {
+        // P_0 and V_0 are in use until that product is complete; then V_1 may land and S_1 may overwrite P_0
+        tc::mbar_wait(bars + 3, 0);
+        tc::tcgen05_fence_after();
+        tc::mbar_arrive_expect_tx(bars + 1, 2 * kv_half);
+        for (int half = 0; half < 2; ++half)
+          tc::tma_load_2d(sV + half * kv_half, &tmKV, bars + 1, v_col + half * 64, (int)tok0 + kLongKB);
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- epilogue: combine the two blocks ----
+  tc::mbar_wait(bars + 3, 1);
+  tc::tcgen05_fence_after();
+  const float mm = fmaxf(m_blk[0], m_blk[1]);
+  const float a0 = l_blk[0] > 0.f ? exp2f(m_blk[0] - mm) : 0.f;
+  const float a1 = l_blk[1] > 0.f ? exp2f(m_blk[1] - mm) : 0.f;
+  const float den = a0 * l_blk[0] + a1 * l_blk[1];
+  const float w0 = den > 0.f ? a0 / den : 0.f, w1 = den > 0.f ? a1 / den : 0.f;
+  __nv_bfloat16* orow = p.out + (size_t)(tok0 + pos) * p.ldo + (size_t)(kvh * group + h0) * kHD;
+#pragma unroll 1
+  for (int c = 0; c < kHD; c += 32) {
+    uint32_t v0[32], v1[32];
+    tc::tmem_ld_32x32(t_row + 256 + c, v0);
+    tc::tmem_ld_32x32(t_row + 384 + c, v1);
+    tc::tmem_ld_wait();
+    if (row_ok) {
+      uint4* dst = reinterpret_cast<uint4*>(orow + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v0[j * 8 + e]) * w0 + __uint_as_float(v1[j * 8 + e]) * w1;
+        dst[j] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+      }
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc::tcgen05_fence_after();
+    tc::tmem_dealloc<1>(tmem_base, 512);
+  }
+}
 
 // ================================================================================================
 // Persistent, warp-specialised version: one CTA per SM walks a contiguous range of tiles.
@@ -579,12 +777,12 @@ __global__ __maxnreg__(104) void attention_tc_persistent_small_kernel(const __gr
 
 }  // namespace
 
-bool attention_tc_supported(int S) { return S >= 1 && S <= 256; }
+bool attention_tc_supported(int S) { return S >= 1 && S <= 512; }
 
 // qkv: bf16 [B*S, ld] = [q heads | k heads | v heads] x 128; out: bf16 [B*S, ldo] = q heads x 128
 void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, int B, int S, int nh, int nkv,
                   int causal, float scale_log2, int sms, bool persistent, cudaStream_t st) {
-  ABSB_CHECK(attention_tc_supported(S), ABSB_ERR_INVALID, "attention_tc: S=%d outside [1,256]", S);
+  ABSB_CHECK(attention_tc_supported(S), ABSB_ERR_INVALID, "attention_tc: S=%d outside [1,512]", S);
   AttnParams p{};
   p.S = S;
   p.nh = nh;
@@ -609,6 +807,21 @@ void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, 
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   const int64_t T = (int64_t)B * S;
+  if (S > 256) {
+    // two key blocks of <= 256 per q tile (attention_tc_long_kernel)
+    const CUtensorMap tmQl = make_tmap_bf16(qkv, T, ld, ld, 128);
+    const CUtensorMap tmKVl = make_tmap_bf16(qkv, T, ld, ld, kLongKB);
+    const size_t smem_l = 1024 + 2 * 128 * 128 + 4 * (size_t)kLongKB * 128 + 512 * 4 + 4 * 8 + 16;
+    static bool configured_l = false;
+    if (!configured_l) {
+      ABSB_CUDA(cudaFuncSetAttribute(attention_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      prefer_max_shared(attention_tc_long_kernel);
+      configured_l = true;
+    }
+    dim3 grid((unsigned)blocks, (unsigned)nkv, (unsigned)B);
+    launch_pdl(attention_tc_long_kernel, grid, dim3(kThreads), smem_l, st, tmQl, tmKVl, p);
+    return;
+  }
   const CUtensorMap tmQ = make_tmap_bf16(qkv, T, ld, ld, p.RB);
   const CUtensorMap tmKV = make_tmap_bf16(qkv, T, ld, ld, p.NK);
   if (persistent) {

@@ -144,8 +144,31 @@ __global__ __launch_bounds__(kSelectWarps * 32) void select_rows_kernel(
     // score reaches the current k-th best (the common case once the threshold has settled).  The
     // container's total order (score desc, id asc) makes the result independent of the offer order.
     const int ngroups = ncols / 128;
-#pragma unroll 2
-    for (int g = warp; g < ngroups; g += kSelectWarps) {
+    // four 128-column groups per step: four independent 128-bit loads in flight per lane and ONE vote for all
+    // of them (once the threshold has settled almost every step is rejected by that vote)
+    int g = warp;
+    for (; g + 3 * kSelectWarps < ngroups; g += 4 * kSelectWarps) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(srow + (g + u * kSelectWarps) * 128 + lane * 4));
+      float mx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mx = fmaxf(mx, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+      if (__any_sync(kFullMask, tk.may_enter(mx))) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = (g + u * kSelectWarps) * 128 + lane * 4;
+          const float m1 = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+          if (__any_sync(kFullMask, tk.may_enter(m1))) {
+            tk.offer_lanes(v[u].x, id_offset + c, true);
+            tk.offer_lanes(v[u].y, id_offset + c + 1, true);
+            tk.offer_lanes(v[u].z, id_offset + c + 2, true);
+            tk.offer_lanes(v[u].w, id_offset + c + 3, true);
+          }
+        }
+      }
+    }
+    for (; g < ngroups; g += kSelectWarps) {
       const int c = g * 128 + lane * 4;
       const float4 v = __ldcs(reinterpret_cast<const float4*>(srow + c));
       const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));

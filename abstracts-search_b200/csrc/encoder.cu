@@ -408,8 +408,8 @@ struct Encoder {
   std::vector<Layer> layers;
   DBuf<float2> rope_cs;
   bool weights_ready = false;
-  int attention_impl = 1;  // 1 = persistent tcgen05 kernel for S <= 256 (mma.sync above that), 2 = one-tile-per-CTA
-                           // tcgen05 kernel, 0 = always mma.sync
+  int attention_impl = 1;  // 1 = tcgen05: persistent kernel for S <= 256, two-key-block kernel for 257-512;
+                           // 2 = one-tile-per-CTA tcgen05 kernel (same two-block kernel above 256); 0 = always mma.sync
 
   // activations (sized for cap_tokens)
   int64_t cap_tokens = 0, cap_batch = 0;

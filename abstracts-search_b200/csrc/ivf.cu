@@ -1214,7 +1214,7 @@ void FlatIndex::search_dev(int64_t nq, const float* q, int k, float* D, long lon
   const int64_t col_chunk = 65536;
   const int nchunks = (int)std::max<int64_t>(1, ceil_div(ntotal, col_chunk));
   const int64_t row_step = 1024;
-  ws_scores.reserve((size_t)row_step * std::min<int64_t>(col_chunk, std::max<int64_t>(ntotal, 1)));
+  ws_scores.reserve((size_t)row_step * std::min<int64_t>(col_chunk, std::max<int64_t>((ntotal + 31) & ~(int64_t)31, 1)));
   ws_part_s.reserve((size_t)row_step * nchunks * k);
   ws_part_id.reserve((size_t)row_step * nchunks * k);
   ws_q_begin.reserve(row_step + 1);
@@ -1232,12 +1232,32 @@ void FlatIndex::search_dev(int64_t nq, const float* q, int k, float* D, long lon
       merge_partials((int)nr, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, D + r0 * k, I + r0 * k, st);
       continue;
     }
+    // The all-pairs inner products run on tcgen05 as a split-bf16 GEMM (x = hi + mid + lo in bf16, six products
+    // accumulated in fp32: fp32-faithful scores, exact on the lattice corpus) whenever the shapes allow; the
+    // database chunk is split on the fly, so no second copy of the corpus is kept.  d % 64 != 0 falls back to
+    // the fp32 FFMA GEMM.
+    const bool tensor = d % 64 == 0;
+    if (tensor) {
+      ws_q3.reserve((size_t)row_step * 3 * d);
+      split3_bf16(nr, d, q + r0 * d, ws_q3.p, st);
+    }
     for (int c = 0; c < nchunks; ++c) {
       const int64_t c0 = (int64_t)c * col_chunk;
       const int nc = (int)std::min(col_chunk, ntotal - c0);
-      gemm_nt_f32((int)nr, nc, d, q + r0 * d, d, xb.p + (size_t)c0 * d, d, ws_scores.p, nc, st);
-      select_rows(ws_scores.p, nc, nr, nc, c0, k, ws_part_s.p + (size_t)c * k, ws_part_id.p + (size_t)c * k,
-                  (int64_t)nchunks * k, false, st);
+      if (tensor) {
+        const int ncp = (nc + 31) & ~31;  // the GEMM wants N % 32 == 0: zero rows pad the last chunk
+        ws_x3.reserve((size_t)std::min<int64_t>(col_chunk, (ntotal + 31) & ~(int64_t)31) * 3 * d);
+        split3_bf16(nc, d, xb.p + (size_t)c0 * d, ws_x3.p, st);
+        if (ncp > nc)
+          ABSB_CUDA(cudaMemsetAsync(ws_x3.p + (size_t)nc * 3 * d, 0, sizeof(uint16_t) * (size_t)(ncp - nc) * 3 * d, st));
+        gemm_split3_f32((int)nr, ncp, d, ws_q3.p, ws_x3.p, ws_scores.p, ncp, props.sm_count, st);
+        select_rows(ws_scores.p, ncp, nr, nc, c0, k, ws_part_s.p + (size_t)c * k, ws_part_id.p + (size_t)c * k,
+                    (int64_t)nchunks * k, false, st);
+      } else {
+        gemm_nt_f32((int)nr, nc, d, q + r0 * d, d, xb.p + (size_t)c0 * d, d, ws_scores.p, nc, st);
+        select_rows(ws_scores.p, nc, nr, nc, c0, k, ws_part_s.p + (size_t)c * k, ws_part_id.p + (size_t)c * k,
+                    (int64_t)nchunks * k, false, st);
+      }
     }
     merge_partials((int)nr, k, ws_q_begin.p, ws_part_s.p, ws_part_id.p, D + r0 * k, I + r0 * k, st);
   }

@@ -218,6 +218,7 @@ struct FlatIndex {
   DBuf<float> ws_scores, ws_part_s, ws_x, ws_D;
   DBuf<long long> ws_part_id, ws_I;
   DBuf<int> ws_q_begin;
+  DBuf<uint16_t> ws_q3, ws_x3;  // bf16 [rows, 3d] splits of the query block / the database chunk (tcgen05 path)
 
   FlatIndex(int d, int device);
   ~FlatIndex();

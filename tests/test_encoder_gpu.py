@@ -204,11 +204,13 @@ def test_baseline_config0_encode_full_size(gpu_pkg):
 
 
 @pytest.mark.parametrize("impl", [1, 2, 0])
-@pytest.mark.parametrize("S", [1, 7, 16, 33, 64, 100, 128, 129, 200, 256])
+@pytest.mark.parametrize("S", [1, 7, 16, 33, 64, 100, 128, 129, 200, 256, 257, 272, 300, 384, 400, 511, 512])
 def test_attention_kernels_all_lengths(gpu_pkg, S, impl):
-    """Both attention kernels (tcgen05 for S <= 256, mma.sync) over sequence lengths that exercise every
-    tile shape: several q heads packed into one 128-row tile (S < 128), row tiles past the sequence end,
-    key counts that are not a multiple of 32, ragged padding, GQA with 6 q heads per kv head, causal."""
+    """The attention kernels (tcgen05: one key block for S <= 256, two key blocks with separate accumulators
+    for 257-512 = stella's max_seq_length; mma.sync) over sequence lengths that exercise every tile shape:
+    several q heads packed into one 128-row tile (S < 128), row tiles past the sequence end, key counts that
+    are not a multiple of 32 (or leave 1 / 16 / 256 keys for the second block), ragged padding that empties the
+    second key block of a sequence, GQA with 6 q heads per kv head, causal."""
     P = gpu_pkg
     for causal in (False, True):
         base = TinyCfg(num_heads=6, num_kv_heads=1, hidden_size=256, intermediate_size=256, num_layers=1, causal=causal)

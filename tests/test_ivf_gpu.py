@@ -913,6 +913,72 @@ def test_parquet_fill_and_tune_on_gpu_index(gpu_pkg, tmp_path, lattice):
     assert choice["recall"] >= 0.9 and ix.nprobe == choice["nprobe"]
 
 
+def test_tune_recall_against_the_oracles_exact_search(gpu_pkg, tmp_path):
+    """`index tune` (/root/reference/Makefile:27-32): the recall@k the sweep reports must be the recall against
+    EXACT search as the oracle computes it (fp64 all-pairs scores over the same rows) — not merely against the
+    product's own flat index.  Real-valued unit-norm rows; the product's IndexFlatIP (tcgen05 split-bf16 GEMM)
+    must itself return the oracle's exact top-k wherever the fp64 margin is clear."""
+    P = gpu_pkg
+    d, nlist, n, nq, k = 1024, 64, 30000, 96, 10
+    x = osynth.corpus_unit(21, 0, n, d, nlist)
+    q = osynth.queries_unit(21, 0, nq, d, nlist, n)
+    s64 = q.astype(np.float64) @ x.astype(np.float64).T
+    order = np.argsort(-s64, axis=1, kind="stable")[:, :k + 1]
+    top = np.take_along_axis(s64, order, axis=1)
+    clear = (top[:, :-1] - top[:, 1:]).min(axis=1) > 2e-6
+    I_true = order[:, :k]
+    flat = P.IndexFlatIP(d)
+    flat.add(x)
+    Df, If = flat.search(q, k)
+    assert clear.sum() >= nq // 2
+    assert np.array_equal(If[clear], I_true[clear])
+    assert np.abs(Df - np.take_along_axis(s64, If, axis=1)).max() < 2e-6
+    ix = P.index_factory(d, f"IVF{nlist},Flat", P.METRIC_INNER_PRODUCT)
+    ix.set_centroids(osynth.centroids(21, nlist, d))
+    ix.add(x)
+    nprobes = [1, 2, 4, 8, nlist]
+    pts = P.tune.sweep(ix, q, k, nprobes=nprobes, ground_truth=flat, repeats=1)
+    o = oivf.IVFFlat(d, nlist)
+    o.set_centroids(osynth.centroids(21, nlist, d))
+    o.add(x)
+    for p_, pt in zip(nprobes, pts):
+        _, Io = o.search(q, k, nprobe=p_, impl="c")
+        want = np.mean([len(np.intersect1d(a, b)) / k for a, b in zip(Io[clear], I_true[clear])])
+        ix.nprobe = p_
+        _, Ig = ix.search(q, k)
+        got = np.mean([len(np.intersect1d(a, b)) / k for a, b in zip(Ig[clear], I_true[clear])])
+        assert abs(got - want) < 1e-9, (p_, got, want)          # product recall == oracle recall vs exact fp64 truth
+        assert abs(pt["recall"] - P.tune.recall_at_k(Ig, If)) < 1e-12  # and the sweep reports what it measured
+    assert pts[-1]["recall"] == 1.0 and pts[0]["recall"] < pts[-1]["recall"]
+    choice = P.tune.tune(ix, q, k, min_recall=0.95, nprobes=nprobes, ground_truth=flat, params_path=str(tmp_path / "params.json"))
+    assert choice["recall"] >= 0.95
+
+
+def test_flat_search_ragged_sizes_on_the_tensor_path(gpu_pkg):
+    """IndexFlatIP over row counts that are not multiples of the GEMM's 32-column granule or of the 65,536-row
+    chunk, lattice rows (every score exact): ids and scores bit-exact to the oracle, incremental adds."""
+    P = gpu_pkg
+    d = 1024
+    ix = P.IndexFlatIP(d)
+    o = oivf.FlatIP(d)
+    q = osynth.queries(3, 0, 37, d, 64, 70000)
+    done = 0
+    for n_add in (1, 30, 4097, 65536 - 4128 + 5, 1000):
+        x = osynth.corpus(3, done, n_add, d, 64)
+        ix.add(x)
+        o.add(x)
+        done += n_add
+        for k in (1, 10):
+            if k > done:
+                continue
+            D, I = ix.search(q, k)
+            Do, Io = o.search(q, k, impl="c")
+            assert np.array_equal(I, Io) and np.array_equal(D, Do), (done, k)
+    D, I = ix.search(q[:1], 100)
+    Do, Io = o.search(q[:1], 100, impl="c")
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+
+
 def test_baseline_config0_flat_10k(gpu_pkg):
     """BASELINE configs[0], index half: IndexFlatIP k=10 over 10k x 1024 (gaussian unit vectors, the
     reference's CPU-runnable case) against the oracle's sgemm + top-k.  ids exact where the fp64
