@@ -40,6 +40,12 @@ struct AttnParams {
   int ldo;
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -212,36 +218,42 @@ __global__ __launch_bounds__(kThreads) void attention_tc_kernel(const __grid_con
 
 
 // ================================================================================================
-// 256 < S <= 512 (stella's max_seq_length): the score tile of 512 keys would take all 512 TMEM columns and
-// K + V (256 KB) no longer fit shared memory, so the keys are processed as TWO blocks of <= 256:
+// 256 < S <= 512 (stella's max_seq_length).  The 512-key score tile takes all 512 TMEM columns and K + V
+// (256 KB) do not fit shared memory together, so the tile is laid out around that:
 //
-//   block b:  S_b = Q K_b^T  -> TMEM cols [0, 256)         (tcgen05.mma SS)
-//             softmax over the block: (m_b, l_b) per row, P_b = exp2(S_b - m_b) back into cols [0, 128)
-//             O_b = P_b V_b  -> TMEM cols [256 + 128 b, 384 + 128 b)   (tcgen05.mma TS)
-//   epilogue: O = (a_0 O_0 + a_1 O_1) / (a_0 l_0 + a_1 l_1),  a_b = exp2(m_b - max(m_0, m_1))
+//   TMA      Q [128 x 128], K_0 [256 x 128], K_1 [<= 256 x 128]                         (160 KB)
+//   MMA 1    S_0 = Q K_0^T -> TMEM cols [0, 256),  S_1 = Q K_1^T -> cols [256, 512)      (tcgen05.mma SS)
+//   TMA      V_0, V_1 into the K buffers as soon as both products are complete — under the softmax
+//   softmax  TWO warpgroups, one per key block, thread = row: row maximum of the block -> shared memory ->
+//            maximum over BOTH blocks, so every probability is exp2(s - m) with the same m and the two P V
+//            products accumulate into ONE accumulator without any rescaling; P_b goes back to TMEM as packed
+//            bf16 over the low half of S_b
+//   MMA 2    O = P_0 V_0 + P_1 V_1 -> TMEM cols [128, 256) (the consumed upper half of S_0)  (tcgen05.mma TS)
+//   epilogue both warpgroups, 64 columns each: tcgen05.ld O, * 1 / (l_0 + l_1), bf16, row-contiguous stores
 //
-// Each block keeps its OWN accumulator, so no accumulator is ever rescaled in TMEM (no tcgen05.ld / st
-// round trip of O as in an online-softmax kernel); the combination costs two TMEM reads in the epilogue.
-// K_1 is fetched while the softmax of block 0 runs (its buffer is free once S_0 is complete), V_1 after
-// O_0 = P_0 V_0.  One CTA = 128 consecutive positions of one q head; K / V of a (sequence, kv head) are
-// re-read from L2 by its 6 x 4 tiles.
+// One CTA = 128 consecutive positions of one q head; K / V of a (sequence, kv head) are re-read from L2 by
+// its 6 x 4 tiles.
 // ================================================================================================
-constexpr int kLongKB = 256;  // keys per block
+constexpr int kLongKB = 256;      // keys per block
+constexpr int kLongThreads = 256;  // two softmax warpgroups
 
-__global__ __launch_bounds__(kThreads) void attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                     const __grid_constant__ CUtensorMap tmKV,
-                                                                     const AttnParams p) {
+__global__ __launch_bounds__(kLongThreads) void attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                         const __grid_constant__ CUtensorMap tmKV,
+                                                                         const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr uint32_t kv_half = (uint32_t)kLongKB * 128u;  // bytes of one 64-column half of a K or V block
-  uint8_t* sQ = smem;                            // [2][128][128 B]
-  uint8_t* sK = sQ + 2 * 128 * 128;              // [2][256][128 B]
-  uint8_t* sV = sK + 2 * kv_half;                // [2][256][128 B]
-  float* sBias = reinterpret_cast<float*>(sV + 2 * kv_half);  // [512]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 512);  // qk_full, v_full, s_done, o_done
+  constexpr uint32_t kv_blk = 2 * kv_half;                // one block of K (later V): 64 KB
+  uint8_t* sQ = smem;                                     // [2][128][128 B]
+  uint8_t* sKV = sQ + 2 * 128 * 128;                      // [2 blocks][2 halves][256][128 B]
+  float* sBias = reinterpret_cast<float*>(sKV + 2 * kv_blk);  // [512]
+  float* sMax = sBias + 512;                              // [2][128]
+  float* sSum = sMax + 256;                               // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 256);  // qk_full, s_done, v_full, o_done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int wg = tid >> 7, row = tid & 127;
   const int blk = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int group = p.nh / p.nkv;
   const int S = p.S;
@@ -262,143 +274,153 @@ __global__ __launch_bounds__(kThreads) void attention_tc_long_kernel(const __gri
     tc::tmem_relinquish<1>();
   }
   pdl_wait();  // global memory from here on
-  for (int k = tid; k < 2 * kLongKB; k += kThreads) sBias[k] = (k < S && p.mask[tok0 + k] != 0) ? 0.f : -INFINITY;
+  for (int k = tid; k < 2 * kLongKB; k += kLongThreads) sBias[k] = (k < S && p.mask[tok0 + k] != 0) ? 0.f : -INFINITY;
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int pos = p0 + tid;
+  const int pos = p0 + row;
   const bool row_ok = pos < S;
-  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const uint32_t idesc2 = tc::make_idesc_bf16_f32(128, kHD, 1);
+  const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const int k_col = (p.nh + kvh) * kHD, v_col = (p.nh + p.nkv + kvh) * kHD;
 
   if (tid == 0) {
-    // Q + K_0 on one barrier, V_0 on another (rows past the end of the tensor are zero-filled by TMA, rows of
-    // the next sequence are finite numbers: both are masked out by sBias)
-    tc::mbar_arrive_expect_tx(bars + 0, 2u * 16384u + 2 * kv_half);
+    // rows past the end of the tensor are zero-filled by TMA, rows of the next sequence are finite numbers: both
+    // are masked out by sBias
+    tc::mbar_arrive_expect_tx(bars + 0, 2u * 16384u + 2 * kv_blk);
     for (int half = 0; half < 2; ++half)
       tc::tma_load_2d(sQ + half * 16384, &tmQ, bars + 0, (kvh * group + h0) * kHD + half * 64, (int)(tok0 + p0));
-    for (int half = 0; half < 2; ++half) tc::tma_load_2d(sK + half * kv_half, &tmKV, bars + 0, k_col + half * 64, (int)tok0);
-    tc::mbar_arrive_expect_tx(bars + 1, 2 * kv_half);
-    for (int half = 0; half < 2; ++half) tc::tma_load_2d(sV + half * kv_half, &tmKV, bars + 1, v_col + half * 64, (int)tok0);
-  }
-  float m_blk[2], l_blk[2];
-#pragma unroll 1
-  for (int kb = 0; kb < 2; ++kb) {
-    const int nk = kb == 0 ? kLongKB : nk1;
-    const int key0 = kb * kLongKB;
-    const uint32_t ph = (uint32_t)kb;
-    if (tid == 0) {
-      // ---- S_kb = Q K_kb^T ----
-      tc::mbar_wait(bars + 0, ph);
-      tc::tcgen05_fence_after();
-      const uint32_t idesc1 = tc::make_idesc_bf16_f32(128, nk);
+    for (int kb = 0; kb < 2; ++kb)
+      for (int half = 0; half < 2; ++half)
+        tc::tma_load_2d(sKV + kb * kv_blk + half * kv_half, &tmKV, bars + 0, k_col + half * 64, (int)tok0 + kb * kLongKB);
+    // ---- S_0 = Q K_0^T, S_1 = Q K_1^T ----
+    tc::mbar_wait(bars + 0, 0);
+    tc::tcgen05_fence_after();
+    for (int kb = 0; kb < 2; ++kb) {
+      const uint32_t idesc1 = tc::make_idesc_bf16_f32(128, kb == 0 ? kLongKB : nk1);
 #pragma unroll
       for (int j = 0; j < kHD / 16; ++j) {
         const uint32_t off = (uint32_t)(j >> 2), within = (uint32_t)(j & 3) * 32u;
         const uint64_t da = tc::make_kmajor_sw128_desc(tc::smem_u32(sQ) + off * 16384u + within);
-        const uint64_t db = tc::make_kmajor_sw128_desc(tc::smem_u32(sK) + off * kv_half + within);
-        tc::umma_bf16<1>(tmem_base, da, db, idesc1, j != 0 ? 1u : 0u);
+        const uint64_t db = tc::make_kmajor_sw128_desc(tc::smem_u32(sKV) + kb * kv_blk + off * kv_half + within);
+        tc::umma_bf16<1>(tmem_base + (uint32_t)(kb * 256), da, db, idesc1, j != 0 ? 1u : 0u);
       }
-      tc::umma_commit<1>(bars + 2);
     }
-    __syncwarp();
-    tc::mbar_wait(bars + 2, ph);
-    tc::tcgen05_fence_after();
-    if (tid == 0 && kb == 0) {
-      // S_0 is complete, so the K buffer is free: fetch K_1 under the softmax of block 0
-      tc::mbar_arrive_expect_tx(bars + 0, 2 * kv_half);
+    tc::umma_commit<1>(bars + 1);
+    // both products complete -> the K buffers are free: V_0, V_1 land under the softmax
+    tc::mbar_wait(bars + 1, 0);
+    tc::mbar_arrive_expect_tx(bars + 2, 2 * kv_blk);
+    for (int kb = 0; kb < 2; ++kb)
       for (int half = 0; half < 2; ++half)
-        tc::tma_load_2d(sK + half * kv_half, &tmKV, bars + 0, k_col + half * 64, (int)tok0 + kLongKB);
-    }
-    __syncwarp();
-    // ---- softmax of the block: thread = tile row = TMEM lane ----
-    float m = -INFINITY;
-    for (int c = 0; c < nk; c += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(t_row + c, v);
+        tc::tma_load_2d(sKV + kb * kv_blk + half * kv_half, &tmKV, bars + 2, v_col + half * 64, (int)tok0 + kb * kLongKB);
+  }
+  __syncwarp();
+
+  // ---- softmax: warpgroup wg owns key block wg, thread = tile row = TMEM lane ----
+  const int nk = wg == 0 ? kLongKB : nk1;
+  const int key0 = wg * kLongKB;
+  const uint32_t t_blk = t_row + (uint32_t)(wg * 256);
+  tc::mbar_wait(bars + 1, 0);
+  tc::tcgen05_fence_after();
+  auto score = [&](uint32_t raw, int c) {  // c = key index inside the block
+    float sc = __uint_as_float(raw) * p.scale_log2 + ((c < nk) ? sBias[key0 + c] : -INFINITY);
+    if (p.causal && key0 + c > pos) sc = -INFINITY;
+    return sc;
+  };
+  float m = -INFINITY;
+  {
+    uint32_t va[32], vb[32];
+    tc::tmem_ld_32x32(t_blk, va);
+    for (int c = 0; c < nk; c += 64) {
       tc::tmem_ld_wait();
+      if (c + 32 < nk) tc::tmem_ld_32x32(t_blk + c + 32, vb);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float sc = __uint_as_float(v[j]) * p.scale_log2 + ((c + j < nk) ? sBias[key0 + c + j] : -INFINITY);
-        if (p.causal && key0 + c + j > pos) sc = -INFINITY;
-        m = fmaxf(m, sc);
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, score(va[j], c + j));
+      if (c + 32 < nk) {
+        tc::tmem_ld_wait();
+        if (c + 64 < nk) tc::tmem_ld_32x32(t_blk + c + 64, va);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, score(vb[j], c + 32 + j));
       }
     }
-    const float m_safe = (m == -INFINITY || !(m == m)) ? 0.f : m;
-    float sum = 0.f;
-    for (int c = 0; c < nk; c += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(t_row + c, v);
-      tc::tmem_ld_wait();
+  }
+  sMax[wg * 128 + row] = m;
+  __syncthreads();
+  m = fmaxf(sMax[row], sMax[128 + row]);
+  const float m_safe = (m == -INFINITY || !(m == m)) ? 0.f : m;
+  float sum = 0.f;
+  {
+    uint32_t va[32], vb[32];
+    auto probs = [&](const uint32_t (&v)[32], int c) {
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float s0 = __uint_as_float(v[2 * j]) * p.scale_log2 + ((c + 2 * j < nk) ? sBias[key0 + c + 2 * j] : -INFINITY);
-        float s1 = __uint_as_float(v[2 * j + 1]) * p.scale_log2 + ((c + 2 * j + 1 < nk) ? sBias[key0 + c + 2 * j + 1] : -INFINITY);
-        if (p.causal) {
-          if (key0 + c + 2 * j > pos) s0 = -INFINITY;
-          if (key0 + c + 2 * j + 1 > pos) s1 = -INFINITY;
-        }
-        const float e0 = exp2f(s0 - m_safe), e1 = exp2f(s1 - m_safe);
+        const float e0 = ex2_approx(score(v[2 * j], c + 2 * j) - m_safe);
+        const float e1 = ex2_approx(score(v[2 * j + 1], c + 2 * j + 1) - m_safe);
         sum += e0 + e1;
         pk[j] = pack2(e0, e1);
       }
-      tc::tmem_st_32x16(t_row + (c >> 1), pk);  // P over the consumed low columns of S
-    }
-    m_blk[kb] = m;
-    l_blk[kb] = sum;
-    tc::tmem_st_wait();
-    tc::tcgen05_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      // ---- O_kb = P_kb V_kb into its own accumulator ----
-      tc::tcgen05_fence_after();
-      tc::mbar_wait(bars + 1, ph);
-      tc::tcgen05_fence_after();
-      const uint32_t o_col = 256u + (uint32_t)kb * 128u;
-      for (int j = 0; j < nk / 16; ++j) {
-        const uint64_t db = tc::make_mnmajor_sw128_desc(tc::smem_u32(sV) + (uint32_t)j * 2048u, kv_half);
-        tc::umma_bf16_ts(tmem_base + o_col, tmem_base + (uint32_t)(j * 8), db, idesc2, j != 0 ? 1u : 0u);
-      }
-      tc::umma_commit<1>(bars + 3);
-      if (kb == 0) {
-        // P_0 and V_0 are in use until that product is complete; then V_1 may land and S_1 may overwrite P_0
-        tc::mbar_wait(bars + 3, 0);
-        tc::tcgen05_fence_after();
-        tc::mbar_arrive_expect_tx(bars + 1, 2 * kv_half);
-        for (int half = 0; half < 2; ++half)
-          tc::tma_load_2d(sV + half * kv_half, &tmKV, bars + 1, v_col + half * 64, (int)tok0 + kLongKB);
+      tc::tmem_st_32x16(t_blk + (c >> 1), pk);  // P over the consumed low columns of S_wg
+    };
+    tc::tmem_ld_32x32(t_blk, va);
+    for (int c = 0; c < nk; c += 64) {
+      tc::tmem_ld_wait();
+      if (c + 32 < nk) tc::tmem_ld_32x32(t_blk + c + 32, vb);
+      probs(va, c);
+      if (c + 32 < nk) {
+        tc::tmem_ld_wait();
+        if (c + 64 < nk) tc::tmem_ld_32x32(t_blk + c + 64, va);
+        probs(vb, c + 32);
       }
     }
-    __syncwarp();
   }
+  sSum[wg * 128 + row] = sum;
+  tc::tmem_st_wait();
+  tc::tcgen05_fence_before();
+  __syncthreads();
 
-  // ---- epilogue: combine the two blocks ----
-  tc::mbar_wait(bars + 3, 1);
+  if (tid == 0) {
+    // ---- O = P_0 V_0 + P_1 V_1, one accumulator (same row maximum in both blocks) ----
+    tc::tcgen05_fence_after();
+    tc::mbar_wait(bars + 2, 0);
+    tc::tcgen05_fence_after();
+    const uint32_t idesc2 = tc::make_idesc_bf16_f32(128, kHD, 1);
+    for (int kb = 0; kb < 2; ++kb) {
+      const int steps = (kb == 0 ? kLongKB : nk1) / 16;
+      for (int j = 0; j < steps; ++j) {
+        const uint64_t db = tc::make_mnmajor_sw128_desc(tc::smem_u32(sKV) + kb * kv_blk + (uint32_t)j * 2048u, kv_half);
+        tc::umma_bf16_ts(tmem_base + kOCol, tmem_base + (uint32_t)(kb * 256 + j * 8), db, idesc2, (kb | j) != 0 ? 1u : 0u);
+      }
+    }
+    tc::umma_commit<1>(bars + 3);
+  }
+  __syncwarp();
+
+  // ---- epilogue: 64 output columns per warpgroup ----
+  tc::mbar_wait(bars + 3, 0);
   tc::tcgen05_fence_after();
-  const float mm = fmaxf(m_blk[0], m_blk[1]);
-  const float a0 = l_blk[0] > 0.f ? exp2f(m_blk[0] - mm) : 0.f;
-  const float a1 = l_blk[1] > 0.f ? exp2f(m_blk[1] - mm) : 0.f;
-  const float den = a0 * l_blk[0] + a1 * l_blk[1];
-  const float w0 = den > 0.f ? a0 / den : 0.f, w1 = den > 0.f ? a1 / den : 0.f;
-  __nv_bfloat16* orow = p.out + (size_t)(tok0 + pos) * p.ldo + (size_t)(kvh * group + h0) * kHD;
-#pragma unroll 1
-  for (int c = 0; c < kHD; c += 32) {
+  const float l = sSum[row] + sSum[128 + row];
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  __nv_bfloat16* orow = p.out + (size_t)(tok0 + pos) * p.ldo + (size_t)(kvh * group + h0) * kHD + wg * 64;
+  {
     uint32_t v0[32], v1[32];
-    tc::tmem_ld_32x32(t_row + 256 + c, v0);
-    tc::tmem_ld_32x32(t_row + 384 + c, v1);
+    tc::tmem_ld_32x32(t_row + kOCol + wg * 64, v0);
+    tc::tmem_ld_32x32(t_row + kOCol + wg * 64 + 32, v1);
     tc::tmem_ld_wait();
     if (row_ok) {
-      uint4* dst = reinterpret_cast<uint4*>(orow + c);
+      uint4* dst = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float o[8];
+      for (int j = 0; j < 4; ++j)
+        dst[j] = make_uint4(pack2(__uint_as_float(v0[j * 8]) * inv, __uint_as_float(v0[j * 8 + 1]) * inv),
+                            pack2(__uint_as_float(v0[j * 8 + 2]) * inv, __uint_as_float(v0[j * 8 + 3]) * inv),
+                            pack2(__uint_as_float(v0[j * 8 + 4]) * inv, __uint_as_float(v0[j * 8 + 5]) * inv),
+                            pack2(__uint_as_float(v0[j * 8 + 6]) * inv, __uint_as_float(v0[j * 8 + 7]) * inv));
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v0[j * 8 + e]) * w0 + __uint_as_float(v1[j * 8 + e]) * w1;
-        dst[j] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
-      }
+      for (int j = 0; j < 4; ++j)
+        dst[4 + j] = make_uint4(pack2(__uint_as_float(v1[j * 8]) * inv, __uint_as_float(v1[j * 8 + 1]) * inv),
+                                pack2(__uint_as_float(v1[j * 8 + 2]) * inv, __uint_as_float(v1[j * 8 + 3]) * inv),
+                                pack2(__uint_as_float(v1[j * 8 + 4]) * inv, __uint_as_float(v1[j * 8 + 5]) * inv),
+                                pack2(__uint_as_float(v1[j * 8 + 6]) * inv, __uint_as_float(v1[j * 8 + 7]) * inv));
     }
   }
   tc::tcgen05_fence_before();
@@ -446,11 +468,6 @@ __device__ __forceinline__ TileInfo decode_tile(const AttnParams& p, int t, int 
   return ti;
 }
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 template <int KVS>
 __device__ __forceinline__ void attention_tc_persistent_body(const CUtensorMap& tmQ, const CUtensorMap& tmKV,
@@ -811,7 +828,7 @@ void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, 
     // two key blocks of <= 256 per q tile (attention_tc_long_kernel)
     const CUtensorMap tmQl = make_tmap_bf16(qkv, T, ld, ld, 128);
     const CUtensorMap tmKVl = make_tmap_bf16(qkv, T, ld, ld, kLongKB);
-    const size_t smem_l = 1024 + 2 * 128 * 128 + 4 * (size_t)kLongKB * 128 + 512 * 4 + 4 * 8 + 16;
+    const size_t smem_l = 1024 + 2 * 128 * 128 + 4 * (size_t)kLongKB * 128 + (512 + 512) * 4 + 4 * 8 + 16;
     static bool configured_l = false;
     if (!configured_l) {
       ABSB_CUDA(cudaFuncSetAttribute(attention_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -819,7 +836,7 @@ void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, 
       configured_l = true;
     }
     dim3 grid((unsigned)blocks, (unsigned)nkv, (unsigned)B);
-    launch_pdl(attention_tc_long_kernel, grid, dim3(kThreads), smem_l, st, tmQl, tmKVl, p);
+    launch_pdl(attention_tc_long_kernel, grid, dim3(kLongThreads), smem_l, st, tmQl, tmKVl, p);
     return;
   }
   const CUtensorMap tmQ = make_tmap_bf16(qkv, T, ld, ld, p.RB);
