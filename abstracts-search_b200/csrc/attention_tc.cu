@@ -246,8 +246,8 @@ __global__ __launch_bounds__(kLongThreads) void attention_tc_long_kernel(const _
   constexpr uint32_t kv_blk = 2 * kv_half;                // one block of K (later V): 64 KB
   uint8_t* sQ = smem;                                     // [2][128][128 B]
   uint8_t* sKV = sQ + 2 * 128 * 128;                      // [2 blocks][2 halves][256][128 B]
-  float* sBias = reinterpret_cast<float*>(sKV + 2 * kv_blk);  // [512]
-  float* sMax = sBias + 512;                              // [2][128]
+  uint32_t* kvalid = reinterpret_cast<uint32_t*>(sKV + 2 * kv_blk);  // [16] + pad: key-valid bits of the 512 keys
+  float* sMax = reinterpret_cast<float*>(kvalid + 512);   // [2][128]
   float* sSum = sMax + 256;                               // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 256);  // qk_full, s_done, v_full, o_done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
@@ -274,7 +274,12 @@ __global__ __launch_bounds__(kLongThreads) void attention_tc_long_kernel(const _
     tc::tmem_relinquish<1>();
   }
   pdl_wait();  // global memory from here on
-  for (int k = tid; k < 2 * kLongKB; k += kLongThreads) sBias[k] = (k < S && p.mask[tok0 + k] != 0) ? 0.f : -INFINITY;
+  // key-valid bits: real token of this sequence (padding, rows past S and the next sequence's rows are masked)
+  for (int w = warp; w < 2 * kLongKB / 32; w += kLongThreads / 32) {
+    const int k = w * 32 + (tid & 31);
+    const unsigned bits = __ballot_sync(0xffffffffu, k < S && p.mask[tok0 + k] != 0);
+    if ((tid & 31) == 0) kvalid[w] = bits;
+  }
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
@@ -286,7 +291,7 @@ __global__ __launch_bounds__(kLongThreads) void attention_tc_long_kernel(const _
 
   if (tid == 0) {
     // rows past the end of the tensor are zero-filled by TMA, rows of the next sequence are finite numbers: both
-    // are masked out by sBias
+    // are masked out by the key-valid bits
     tc::mbar_arrive_expect_tx(bars + 0, 2u * 16384u + 2 * kv_blk);
     for (int half = 0; half < 2; ++half)
       tc::tma_load_2d(sQ + half * 16384, &tmQ, bars + 0, (kvh * group + h0) * kHD + half * 64, (int)(tok0 + p0));
@@ -317,49 +322,88 @@ __global__ __launch_bounds__(kLongThreads) void attention_tc_long_kernel(const _
   __syncwarp();
 
   // ---- softmax: warpgroup wg owns key block wg, thread = tile row = TMEM lane ----
+  // Key validity is a bit mask per 32 keys (padding, keys past S, causal): a chunk whose 32 keys are all valid —
+  // the common case — costs one FMNMX per score in the max pass and FFMA + MUFU.EX2 + FADD in the exp pass.
   const int nk = wg == 0 ? kLongKB : nk1;
   const int key0 = wg * kLongKB;
   const uint32_t t_blk = t_row + (uint32_t)(wg * 256);
   tc::mbar_wait(bars + 1, 0);
   tc::tcgen05_fence_after();
-  auto score = [&](uint32_t raw, int c) {  // c = key index inside the block
-    float sc = __uint_as_float(raw) * p.scale_log2 + ((c < nk) ? sBias[key0 + c] : -INFINITY);
-    if (p.causal && key0 + c > pos) sc = -INFINITY;
-    return sc;
+  auto key_mask = [&](int c) -> unsigned {  // c: first key of the chunk inside the block
+    unsigned km = kvalid[(key0 + c) >> 5];
+    if (p.causal) {
+      const int kabs = key0 + c;
+      km &= pos < kabs ? 0u : (pos - kabs >= 31 ? 0xffffffffu : ((2u << (pos - kabs)) - 1u));
+    }
+    return km;
   };
-  float m = -INFINITY;
+  float m = -INFINITY;  // maximum of the RAW scores (the scale is positive)
   {
     uint32_t va[32], vb[32];
+    auto row_max = [&](const uint32_t (&v)[32], int c) {
+      const unsigned km = key_mask(c);
+      if (km == 0xffffffffu) {
+        float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          m0 = fmaxf(m0, __uint_as_float(v[j]));
+          m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+          m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+          m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+        }
+        m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if ((km >> j) & 1u) m = fmaxf(m, __uint_as_float(v[j]));
+      }
+    };
     tc::tmem_ld_32x32(t_blk, va);
     for (int c = 0; c < nk; c += 64) {
       tc::tmem_ld_wait();
       if (c + 32 < nk) tc::tmem_ld_32x32(t_blk + c + 32, vb);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) m = fmaxf(m, score(va[j], c + j));
+      row_max(va, c);
       if (c + 32 < nk) {
         tc::tmem_ld_wait();
         if (c + 64 < nk) tc::tmem_ld_32x32(t_blk + c + 64, va);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) m = fmaxf(m, score(vb[j], c + 32 + j));
+        row_max(vb, c + 32);
       }
     }
   }
   sMax[wg * 128 + row] = m;
   __syncthreads();
   m = fmaxf(sMax[row], sMax[128 + row]);
-  const float m_safe = (m == -INFINITY || !(m == m)) ? 0.f : m;
+  const float ms = (m == -INFINITY || !(m == m)) ? 0.f : m * p.scale_log2;
   float sum = 0.f;
   {
     uint32_t va[32], vb[32];
     auto probs = [&](const uint32_t (&v)[32], int c) {
+      const unsigned km = key_mask(c);
       uint32_t pk[16];
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      if (km == 0xffffffffu) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float e0 = ex2_approx(score(v[2 * j], c + 2 * j) - m_safe);
-        const float e1 = ex2_approx(score(v[2 * j + 1], c + 2 * j + 1) - m_safe);
-        sum += e0 + e1;
-        pk[j] = pack2(e0, e1);
+        for (int j = 0; j < 16; j += 2) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -ms));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -ms));
+          const float e2 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 2]), p.scale_log2, -ms));
+          const float e3 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 3]), p.scale_log2, -ms));
+          s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+          pk[j] = pack2(e0, e1);
+          pk[j + 1] = pack2(e2, e3);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -ms));
+          float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -ms));
+          if (!((km >> (2 * j)) & 1u)) e0 = 0.f;
+          if (!((km >> (2 * j + 1)) & 1u)) e1 = 0.f;
+          s0 += e0; s1 += e1;
+          pk[j] = pack2(e0, e1);
+        }
       }
+      sum += (s0 + s1) + (s2 + s3);
       tc::tmem_st_32x16(t_blk + (c >> 1), pk);  // P over the consumed low columns of S_wg
     };
     tc::tmem_ld_32x32(t_blk, va);
