@@ -23,6 +23,7 @@
 //            per 32 x 32 block), then release the accumulator (`tmem_empty`,
 //            remote arrive from the peer CTA) so the next tile's MMAs overlap.
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -489,8 +490,43 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Tensor maps are cached per (buffer, shape, box): a forward launches ~115 GEMMs on the same few dozen
+// (pointer, shape) pairs, and cuTensorMapEncodeTiled costs more host time than the launch itself.
+struct TmapKey {
+  const void* base;
+  int64_t rows, cols, ld;
+  int box_rows, kind;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && kind == o.kind;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (uint64_t)k.rows * 0xBF58476D1CE4E5B9ull + (uint64_t)k.cols * 0x94D049BB133111EBull + (uint64_t)k.ld * 31 + (uint64_t)k.box_rows * 7 + k.kind;
+    return (size_t)(h ^ (h >> 29));
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+
+template <typename Make>
+CUtensorMap cached_tmap(const TmapKey& key, Make make) {
+  std::lock_guard<std::mutex> lock(g_tmap_mu);
+  auto it = g_tmap_cache.find(key);
+  if (it != g_tmap_cache.end()) return it->second;
+  if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();  // descriptors are cheap to rebuild; keep the table bounded
+  const CUtensorMap m = make();
+  g_tmap_cache.emplace(key, m);
+  return m;
+}
+
+CUtensorMap make_tmap_uncached(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 // bf16 matrix [rows, cols] with row stride ld (elements); box = box_rows x 64 elements, 128B swizzle
 CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  return cached_tmap(TmapKey{base, rows, cols, ld, box_rows, 0}, [&] { return make_tmap_uncached(base, rows, cols, ld, box_rows); });
+}
+CUtensorMap make_tmap_uncached(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   ABSB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, ABSB_ERR_INVALID,
              "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (ld=%lld)", (long long)ld);
   CUtensorMap m;
@@ -505,8 +541,12 @@ CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, 
   return m;
 }
 
+CUtensorMap make_tmap_f32_box32_uncached(const void* base, int64_t rows, int64_t cols, int64_t ld);
 // fp32 matrix [rows, cols] with row pitch ld (elements): 32 x 32 boxes, SWIZZLE_128B (the residual stream)
 CUtensorMap make_tmap_f32_box32(const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  return cached_tmap(TmapKey{base, rows, cols, ld, 32, 1}, [&] { return make_tmap_f32_box32_uncached(base, rows, cols, ld); });
+}
+CUtensorMap make_tmap_f32_box32_uncached(const void* base, int64_t rows, int64_t cols, int64_t ld) {
   ABSB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 4) % 16 == 0, ABSB_ERR_INVALID,
              "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (ld=%lld)", (long long)ld);
   CUtensorMap m;
