@@ -155,6 +155,7 @@ _SIGS = {
     "absb_peer_wait_dev": ([_H, POINTER(c_void_p), c_void_p], c_int),
     "absb_peer_status": ([_H, POINTER(c_int)], c_int),
     "absb_ivf_search_push_dev": ([_H, _H, c_int64, c_void_p, c_int, c_int, c_void_p], c_int),
+    "absb_ivf_search_preassigned_push_dev": ([_H, _H, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
     "absb_peer_push_results_dev": ([_H, c_int64, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "absb_peer_merge_shards_dev": ([_H, c_int64, c_int, c_void_p, c_void_p, c_void_p], c_int),
     # OpenAlex JSON-lines front end (host only)

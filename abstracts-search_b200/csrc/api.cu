@@ -753,6 +753,35 @@ int absb_ivf_search_push_dev(absb_ivf_t h, absb_peer_t p, int64_t n, const float
   ABSB_API_END
 }
 
+int absb_ivf_search_preassigned_push_dev(absb_ivf_t h, absb_peer_t p, int64_t n, const float* q_dev, int k, int nprobe,
+                                         const int64_t* coarse_ids_dev, void* stream) {
+  ABSB_API_BEGIN
+  NEED(h);
+  NEED(p);
+  ABSB_CHECK(n >= 1 && q_dev && coarse_ids_dev, ABSB_ERR_INVALID, "bad search arguments");
+  ABSB_CHECK(k >= 1 && k <= ABSB_MAX_K, ABSB_ERR_INVALID, "k=%d outside [1,%d]", k, ABSB_MAX_K);
+  ABSB_CHECK(p->px.device == h->ix.device, ABSB_ERR_INVALID, "index and exchange live on different devices");
+  const size_t i_bytes = ((size_t)n * k * sizeof(long long) + 15) & ~(size_t)15;
+  ABSB_CHECK(i_bytes + (size_t)n * k * sizeof(float) <= p->px.slot_bytes, ABSB_ERR_INVALID,
+             "record of %lld x %d results does not fit the exchange slot (%zu bytes)", (long long)n, k, p->px.slot_bytes);
+  IvfIndex& ix = h->ix;
+  DeviceGuard g(ix.device);
+  ix.reset_stats();
+  SearchPush sp{p->px.begin_push(0, (long long)i_bytes), 0, n};
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t q0 = 0; q0 < n; q0 += kMaxPlanQueries) {
+    const int64_t nb = std::min<int64_t>(kMaxPlanQueries, n - q0);
+    SearchPush sub = sp;
+    sub.q_base = q0;
+    ix.search_preassigned_dev(nb, q_dev + q0 * ix.d, k, nprobe,
+                              reinterpret_cast<const long long*>(coarse_ids_dev) + q0 * nprobe, nullptr, nullptr, st, &sub);
+  }
+  p->px.commit();
+  p->px.rec_n = n;
+  p->px.rec_k = k;
+  ABSB_API_END
+}
+
 int absb_peer_push_results_dev(absb_peer_t p, int64_t n, int k, const float* D_dev, const int64_t* I_dev, void* stream) {
   ABSB_API_BEGIN
   NEED(p);

@@ -293,6 +293,65 @@ class ShardedIndexIVFFlat:
             check(lib().absb_peer_merge_shards_dev(px._h, n, k, ptr(Dm), ptr(Im), st))
         return Dm, Im
 
+    def search_spread(self, x_local, k: int, px_queries=None):
+        """Index.search for a query batch that is SPREAD over the ranks (rank r holds the r-th contiguous slice,
+        e.g. the queries it has just encoded; every rank the same number): each rank computes the coarse
+        top-nprobe of ITS slice only (1 / W of the coarse GEMM and of the centroid select — centroids are
+        replicated, so the result is the one every rank would compute), ONE all-gather moves the record
+        {embeddings | coarse ids} of every rank (`px_queries`: a PeerExchange with slots of
+        n_local * (4 d + 8 nprobe) bytes, else NCCL), then every rank scans its own lists for the whole batch and
+        the usual exchange + merge of the partial top-k follows.  Same (D, I) as `search` on the gathered batch."""
+        import torch
+        import torch.distributed as dist
+
+        self.local.nprobe = self.nprobe
+        n_loc, d, npb, W = x_local.shape[0], self.d, int(min(self.nprobe, self.nlist)), self.world
+        assert x_local.dtype == torch.float32 and x_local.is_contiguous() and x_local.shape[1] == d
+        on_gpu = x_local.is_cuda
+        Ic = self.local.coarse(x_local if on_gpu else x_local.numpy(), npb)[1]
+        Ic = torch.as_tensor(Ic).to(x_local.device).to(torch.int64).contiguous()
+        eb, cb = n_loc * d * 4, n_loc * npb * 8
+        rec = torch.empty(eb + cb, dtype=torch.uint8, device=x_local.device)
+        rec[:eb].view(torch.float32).copy_(x_local.reshape(-1))
+        rec[eb:].view(torch.int64).copy_(Ic.reshape(-1))
+        if px_queries is not None and W > 1:
+            g = px_queries.allgather(rec)
+        else:
+            g = torch.empty((W, eb + cb), dtype=torch.uint8, device=x_local.device)
+            if W > 1:
+                dist.all_gather_into_tensor(g.view(-1), rec, group=self.group)
+            else:
+                g[0].copy_(rec)
+        x_all = g[:, :eb].contiguous().view(torch.float32).view(W * n_loc, d)
+        Ic_all = g[:, eb:].contiguous().view(torch.int64).view(W * n_loc, npb)
+        self.last_queries = x_all  # the gathered batch (e.g. for a later exact re-check)
+        if on_gpu:
+            return self.search_preassigned(x_all, k, Ic_all)
+        return self.search_preassigned(x_all.numpy(), k, Ic_all.numpy())
+
+    def search_preassigned(self, x, k: int, Ic):
+        """`search` with the coarse result given for the whole batch (IndexIVF::search_preassigned on every shard)."""
+        import torch
+
+        from ._lib import check, current_stream_ptr, lib, ptr
+
+        n = x.shape[0]
+        if self._px is not None and self.world > 1 and hasattr(x, "is_cuda") and x.is_cuda:
+            px = self._px
+            if ((n * k * 8 + 15) & ~15) + n * k * 4 > px.slot_bytes:
+                raise ValueError(f"{n} x {k} results exceed the exchange slot ({px.slot_bytes} bytes)")
+            if px.status() != 0:
+                raise RuntimeError("peer exchange timed out waiting for another rank")
+            with torch.cuda.device(x.device):
+                st = current_stream_ptr()
+                check(lib().absb_ivf_search_preassigned_push_dev(self.local._h, px._h, n, ptr(x), k, Ic.shape[1], ptr(Ic), st))
+                Dm = torch.empty((n, k), dtype=torch.float32, device=x.device)
+                Im = torch.empty((n, k), dtype=torch.int64, device=x.device)
+                check(lib().absb_peer_merge_shards_dev(px._h, n, k, ptr(Dm), ptr(Im), st))
+            return Dm, Im
+        D, I = self.local.search_preassigned(x, k, Ic)
+        return self._exchange_and_merge(D, I, k)
+
     def search(self, x, k: int):
         """x: the full query batch on every rank.  Returns the merged (D, I) on every rank.
 
@@ -305,6 +364,12 @@ class ShardedIndexIVFFlat:
         if self._px is not None and self.world > 1 and hasattr(x, "is_cuda") and x.is_cuda:
             return self._search_peer(x, k)
         D, I = self.local.search(x, k)
+        return self._exchange_and_merge(D, I, k)
+
+    def _exchange_and_merge(self, D, I, k: int):
+        import torch
+        import torch.distributed as dist
+
         if self.world == 1:
             return D, I
         as_numpy = not hasattr(D, "is_cuda")

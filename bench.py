@@ -245,7 +245,8 @@ def workload_config(args, world: int):
         "corpus": ("unit: real-valued L2-normalised fp32 rows from the counter-based generator (oracle/synth.py regenerates "
                    "them bit for bit)" if args.corpus == "unit" else "lattice: integer/128 components, fp32 scores exact"),
         "queries_per_step": args.batch, "query_tokens": args.query_tokens,
-        "parallelism": f"encode dp{world}; index sharded by list x{world}; 1 all-gather of partial top-k",
+        "parallelism": (f"encode dp{world} + coarse quantiser dp{world} (each rank: its own queries); 1 all-gather of {{embeddings | "
+                        f"coarse ids}}; index sharded by list x{world}; 1 exchange of partial top-k"),
         "l2": "inputs larger than L2: >= 20 GB of list codes and 3.1 GB of weights stream per step (L2 = 126 MB)",
     }
 
@@ -647,7 +648,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         sh.nprobe = args.nprobe
         exchange = "nccl all-gather x2"
         if args.exchange == "peer" and sh.use_peer_exchange(max_results=args.batch * args.k, strict=False):
-            px_emb = P.PeerExchange.over_group(dev, (args.batch // world) * 1024 * 4, strict=False)
+            # slot = one rank's {embeddings | coarse ids} record of ShardedIndexIVFFlat.search_spread
+            px_emb = P.PeerExchange.over_group(dev, (args.batch // world) * (1024 * 4 + 8 * args.nprobe), strict=False)
             exchange = ("NVLink peer-memory stores fused into the merge kernels (no NCCL on the query path)"
                         if px_emb is not None else "peer-memory top-k exchange + nccl embedding all-gather")
 
@@ -665,12 +667,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     def step_dev():
         e = enc.encode_tokens(ids_d[lo:hi], mask_d[lo:hi], normalize_embeddings=True)
         if world > 1:
-            if px_emb is not None:
-                last["emb"] = px_emb.allgather(e).view(nq, 1024)
-                return sh.search(last["emb"], k)
-            dist.all_gather_into_tensor(emb_all, e)
-            last["emb"] = emb_all
-            return sh.search(emb_all, k)
+            # coarse top-nprobe of this rank's queries only; ONE all-gather of {embeddings | coarse ids}
+            out = sh.search_spread(e, k, px_queries=px_emb)
+            last["emb"] = sh.last_queries
+            return out
         last["emb"] = e
         return ix.search(e, k)
 
@@ -701,11 +701,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         e = enc.encode_tokens(ids_np[lo:hi], mask_np[lo:hi], normalize_embeddings=True)  # host in, host out
         if world > 1:
             e_d = torch.from_numpy(e).to(device, non_blocking=True)
-            if px_emb is not None:
-                D, I = sh.search(px_emb.allgather(e_d).view(nq, 1024), k)
-            else:
-                dist.all_gather_into_tensor(emb_all, e_d)
-                D, I = sh.search(emb_all, k)
+            D, I = sh.search_spread(e_d, k, px_queries=px_emb)
             return D.cpu().numpy(), I.cpu().numpy()
         return ix.search(e, k)  # numpy in, numpy out
 
@@ -730,9 +726,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     es = enc.last_stats()
     Iw = I.cpu().numpy()
     assert (Iw >= 0).all() and Iw.shape == (nq, k), "search returned missing results on a full index"
-    _, Ic = ix.coarse(emb_all if world > 1 else enc.encode_tokens(ids_d, mask_d, True), args.nprobe)
+    _, Ic = ix.coarse(last["emb"] if world > 1 else enc.encode_tokens(ids_d, mask_d, True), args.nprobe)
     distinct_lists = int(torch.unique(Ic).numel())
-    launches_per_step = int(es["launches"] + st["launches"] + ((3 if px_emb is not None else 1) if world > 1 else 0))
+    # + coarse of the local slice (split + GEMM + select), record pack copies, all-gather (peer: push + wait), unpack copies, shard merge
+    launches_per_step = int(es["launches"] + st["launches"] + ((3 + 2 + (2 if px_emb is not None else 1) + 2 + 1) if world > 1 else 0))
 
     # ---- timed region: value -------------------------------------------------------------------
     # Pass A (clean): K steps, CUDA events around the whole region on the launching stream -> value.

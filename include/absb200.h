@@ -358,6 +358,11 @@ int absb_peer_status(absb_peer_t p, int* status);
  * separate copy or collective).  Record = I [n,k] i64 then D [n,k] f32 (16-byte aligned). */
 int absb_ivf_search_push_dev(absb_ivf_t h, absb_peer_t p, int64_t n, const float* q_dev, int k,
                              int nprobe, void* stream);
+/* absb_ivf_search_push_dev with the coarse result given (IndexIVF::search_preassigned): for query batches whose
+ * coarse top-nprobe was computed where the query was encoded and travelled with the embedding in the all-gather,
+ * instead of being recomputed for the whole batch on every rank. */
+int absb_ivf_search_preassigned_push_dev(absb_ivf_t h, absb_peer_t p, int64_t n, const float* q_dev, int k, int nprobe,
+                                         const int64_t* coarse_ids_dev, void* stream);
 /* Same exchange for a result that already sits in local (D, I) [n,k] (e.g. from the two-stage scan):
  * packs the record and pushes it to every rank; absb_peer_merge_shards_dev consumes it. */
 int absb_peer_push_results_dev(absb_peer_t p, int64_t n, int k, const float* D_dev, const int64_t* I_dev,

@@ -93,8 +93,21 @@ def main():
     for _ in range(3):
         D2, I2 = sh2.search(qd, k)
         assert np.array_equal(I2.cpu().numpy(), Ir) and np.array_equal(D2.cpu().numpy(), Dr), f"rank {rank}: two-stage + peer"
+    # the batch SPREAD over the ranks: coarse computed where the slice lives, {queries | coarse ids} in ONE
+    # all-gather (NVLink peer stores, then NCCL), two-stage shards, fused push: same result
+    per = nq // world
+    qloc = qd[rank * per:(rank + 1) * per].contiguous()
+    pxq = P.PeerExchange.over_group(torch.cuda.current_device(), per * (d * 4 + 8 * nprobe))
+    for _ in range(3):
+        Ds, Is = sh2.search_spread(qloc, k, px_queries=pxq)
+        assert np.array_equal(Is.cpu().numpy(), Ir[: per * world]) and np.array_equal(Ds.cpu().numpy(), Dr[: per * world]), \
+            f"rank {rank}: search_spread + peer"
+        assert torch.equal(sh2.last_queries, qd[: per * world])
+    Ds, Is = sh.search_spread(qloc, k)  # NCCL all-gather of the record
+    assert np.array_equal(Is.cpu().numpy(), Ir[: per * world]) and np.array_equal(Ds.cpu().numpy(), Dr[: per * world]), \
+        f"rank {rank}: search_spread + nccl"
     torch.cuda.synchronize()
-    assert sh._px.status() == 0 and px.status() == 0 and sh2._px.status() == 0
+    assert sh._px.status() == 0 and px.status() == 0 and sh2._px.status() == 0 and pxq.status() == 0
     dist.barrier()
     if rank == 0:
         print(f"dist_build_check ok: world={world}, k-means matches, lists and search bit-exact, NVLink peer exchange bit-exact")

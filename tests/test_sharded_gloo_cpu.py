@@ -55,6 +55,12 @@ class OracleShard:
         _, Ic = self.ix.coarse(x, min(self.nprobe, self.nlist))
         return self.ix.search_preassigned(x, k, Ic)
 
+    def coarse(self, x, nprobe):
+        return self.ix.coarse(np.asarray(x), nprobe)
+
+    def search_preassigned(self, x, k, Ic):
+        return self.ix.search_preassigned(np.asarray(x), k, np.asarray(Ic))
+
 
 class OracleOps:
     """CPU stand-ins (oracle arithmetic) for DeviceOps, so that the distributed build's host logic —
@@ -130,7 +136,12 @@ def _worker(rank, world, port, out_dir):
     total = sh.ntotal
     q = osynth.queries(7, 0, nq, d, nlist, n)
     D, I = sh.search(q, k)
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), D=D, I=I, total=total, local=local.ntotal)
+    # the same batch SPREAD over the ranks: coarse where the slice lives, one all-gather of {queries | coarse ids}
+    import torch
+
+    q2 = osynth.queries(7, 100, 2 * 6, d, nlist, n)
+    Ds, Is = sh.search_spread(torch.from_numpy(np.ascontiguousarray(q2[rank * 6:(rank + 1) * 6])), k)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), D=D, I=I, total=total, local=local.ntotal, Ds=Ds, Is=Is)
     dist.destroy_process_group()
 
 
@@ -226,3 +237,6 @@ def test_sharded_search_world2_gloo(tmp_path):
         assert int(r["total"]) == n
         assert np.array_equal(r["I"], I) and np.array_equal(r["D"], D)
     assert sum(int(r["local"]) for r in res) == n and all(int(r["local"]) > 0 for r in res)
+    D2, I2 = ref.search(osynth.queries(7, 100, 12, d, nlist, n), k, nprobe=nprobe)
+    for r in res:
+        assert np.array_equal(r["Is"], I2) and np.array_equal(r["Ds"], D2), "search_spread differs from the single index"
