@@ -726,6 +726,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     es = enc.last_stats()
     Iw = I.cpu().numpy()
     assert (Iw >= 0).all() and Iw.shape == (nq, k), "search returned missing results on a full index"
+    if world > 1:
+        # the step's data-parallel coarse + gathered coarse ids against the replicated coarse on every rank
+        Dr_, Ir_ = sh.search(last["emb"].clone(), k)
+        assert np.array_equal(Ir_.cpu().numpy(), Iw) and np.array_equal(Dr_.cpu().numpy(), D.cpu().numpy()), \
+            "search_spread differs from the replicated-coarse search"
     _, Ic = ix.coarse(last["emb"] if world > 1 else enc.encode_tokens(ids_d, mask_d, True), args.nprobe)
     distinct_lists = int(torch.unique(Ic).numel())
     # + coarse of the local slice (split + GEMM + select), record pack copies, all-gather (peer: push + wait), unpack copies, shard merge
