@@ -120,7 +120,11 @@ __device__ __forceinline__ void tile_coords(const KernelParams& p, int tile, int
 #else
 #define ABSB_GEMM_BOUNDS __launch_bounds__(kThreads, 1)
 #endif
-template <int BN, int EPI, int NCTA>
+// CL = 2 ("quad"): a cluster of TWO CTA pairs stacked in M computes a 512 x BN super tile.  The pairs share the B
+// tile: every CTA fetches a QUARTER of it and multicasts the piece to its twin in the other pair, so the B operand
+// crosses L2 -> SM once per cluster instead of once per pair (-25% operand bytes per flop at BN = 256) — the big
+// GEMMs are bound by exactly that traffic (64 B per clock per SM at full tensor rate), most visibly at M = 2048.
+template <int BN, int EPI, int NCTA, int CL = 1>
 __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmC,
@@ -137,9 +141,12 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
-  const int cta_rank = NCTA == 1 ? 0 : (int)tc::cluster_ctarank();
-  const int worker = blockIdx.x / NCTA, num_workers = gridDim.x / NCTA;  // a worker = one CTA or one CTA pair
+  static_assert(CL == 1 || NCTA == 2, "a quad is two CTA pairs");
+  const int num_tiles = p.tiles_m * p.tiles_n;  // tiles_m counts rows of (128 * NCTA * CL)-row super tiles
+  const int crank = NCTA == 1 ? 0 : (int)tc::cluster_ctarank();
+  const int pair = CL == 1 ? 0 : (crank >> 1);  // which pair of the quad
+  const int cta_rank = crank & 1;               // rank inside the pair (0 = leader)
+  const int worker = blockIdx.x / (NCTA * CL), num_workers = gridDim.x / (NCTA * CL);  // a worker = CTA, pair or quad
 
   pdl_trigger();  // the next kernel of the stream may set itself up as soon as an SM has room for it
   if (warp == 0 && lane == 0) {
@@ -149,7 +156,7 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       tc::mbar_init(full_bar + i, 1);
-      tc::mbar_init(empty_bar + i, 1);
+      tc::mbar_init(empty_bar + i, CL);  // a quad's stage holds bytes issued by BOTH pairs: both MMAs must release it
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(tmem_full + i, 1);
@@ -178,6 +185,7 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         int tm, tn;
         tile_coords(p, tile, tm, tn);
+        tm = tm * CL + pair;
         const int row_a = (tm * NCTA + cta_rank) * BM;
         const int row_b = tn * BN + cta_rank * L::kBRows;
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -192,7 +200,15 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
             // both CTAs' bytes are credited to the leader's barrier; only the leader arrives on it
             if (cta_rank == 0) tc::mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes * NCTA);
             tc::tma_load_2d_2cta(sa, &tmA, full_bar + stage, p.a_off[seg] + within * BK, row_a);
-            tc::tma_load_2d_2cta(sa + L::kABytes, &tmB, full_bar + stage, p.b_off[seg] + within * BK, row_b);
+            if constexpr (CL == 1) {
+              tc::tma_load_2d_2cta(sa + L::kABytes, &tmB, full_bar + stage, p.b_off[seg] + within * BK, row_b);
+            } else {
+              // quarter `pair` of this CTA's half of B, delivered to this CTA and to its twin in the other pair
+              constexpr int kQRows = L::kBRows / 2;
+              tc::tma_load_2d_2cta_mc(sa + L::kABytes + pair * kQRows * 128, &tmB, full_bar + stage,
+                                      p.b_off[seg] + within * BK, row_b + pair * kQRows,
+                                      (uint16_t)((1u << cta_rank) | (1u << (2 + cta_rank))));
+            }
           }
           if (++stage == kStages) {
             stage = 0;
@@ -224,13 +240,15 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
             // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
             tc::umma_bf16<NCTA>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc::umma_commit<NCTA>(empty_bar + stage);
+          if constexpr (CL == 1) tc::umma_commit<NCTA>(empty_bar + stage);
+          else tc::umma_commit_2cta_mask(empty_bar + stage, 0xF);  // the stage is shared by the four CTAs
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc::umma_commit<NCTA>(tmem_full + acc);
+        if constexpr (CL == 1) tc::umma_commit<NCTA>(tmem_full + acc);
+        else tc::umma_commit_2cta_mask(tmem_full + acc, (uint16_t)(3u << (2 * pair)));
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -245,12 +263,13 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
     // so the result does not depend on timing).
     const int q = warp & 3;
     const int chalf = (warp - kEpiWarp0) >> 2;
-    const uint32_t tmem_empty_addr0 = NCTA == 1 ? 0u : tc::map_to_cta(tc::smem_u32(tmem_empty), 0);
+    const uint32_t tmem_empty_addr0 = NCTA == 1 ? 0u : tc::map_to_cta(tc::smem_u32(tmem_empty), (uint32_t)(2 * pair));
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int tm, tn;
       tile_coords(p, tile, tm, tn);
+      tm = tm * CL + pair;
       const int row = (tm * NCTA + cta_rank) * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
       tc::mbar_wait(tmem_full + acc, acc_phase);
@@ -561,36 +580,53 @@ CUtensorMap make_tmap_f32_box32_uncached(const void* base, int64_t rows, int64_t
   return m;
 }
 
-template <int BN, int EPI, int NCTA>
+template <int BN, int EPI, int NCTA, int CL = 1>
 void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const void* B, int64_t b_rows, int64_t b_cols,
             int64_t ldb, KernelParams p, int sms, cudaStream_t st) {
   using L = SmemLayout<BN, NCTA, EPI>;
-  auto kern = gemm_bf16_tc_kernel<BN, EPI, NCTA>;
+  auto kern = gemm_bf16_tc_kernel<BN, EPI, NCTA, CL>;
   static bool configured = false;  // per instantiation
+  static int max_clusters = 0;     // quads: clusters of 4 CTAs that fit the GPU at once (GPC layout dependent)
   if (!configured) {
     ABSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn(L::kMaxStages)));
     prefer_max_shared(kern);
     configured = true;
   }
   p.stages = L::stages_for(gemm_smem_budget());
-  p.tiles_m = (int)ceil_div(p.M, BM * NCTA);
+  p.tiles_m = (int)ceil_div(p.M, BM * NCTA * CL);
   p.tiles_n = (int)ceil_div(p.N, BN);
   // Few N tiles: walk N first so the CTAs running concurrently share A tiles (A is the big operand of the
   // down/O projections and would otherwise be re-read from HBM once per N tile).  Many N tiles: walk M first
   // so that they share the weight tile.
   p.n_fast = p.tiles_n <= 16 ? 1 : 0;
   const CUtensorMap tmA = make_tmap(A, a_rows, a_cols, lda, BM);
-  const CUtensorMap tmB = make_tmap(B, b_rows, b_cols, ldb, L::kBRows);
+  const CUtensorMap tmB = make_tmap(B, b_rows, b_cols, ldb, L::kBRows / CL);  // a quad fetches B in quarters
   const CUtensorMap tmC = EPI == EPI_F32_ADD ? make_tmap_f32_box32(p.out, p.M, p.N, p.ldc) : tmA;
-  const int workers = std::max(1, std::min(p.tiles_m * p.tiles_n, sms / NCTA));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(workers * NCTA));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = L::dyn(p.stages);
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.x = NCTA * CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  int slots = sms / (NCTA * CL);
+  if (CL > 1) {
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t q = cfg;
+      q.gridDim = dim3((unsigned)(sms / 4 * 4));
+      q.attrs = attr;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n < 1) n = sms / 4 - 1;
+      max_clusters = n;
+    }
+    slots = std::min(slots, max_clusters);
+  }
+  const int workers = std::max(1, std::min(p.tiles_m * p.tiles_n, slots));
+  cfg.gridDim = dim3((unsigned)(workers * NCTA * CL));
+  attr[0].val.clusterDim.x = NCTA * CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -600,28 +636,28 @@ void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const vo
   ABSB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
 }
 
-template <int BN, int NCTA>
+template <int BN, int NCTA, int CL = 1>
 void launch_epi(int epi, const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const void* B, int64_t b_rows,
                 int64_t b_cols, int64_t ldb, const KernelParams& p, int sms, cudaStream_t st) {
   switch (epi) {
-    case EPI_BF16_BIAS: launch<BN, EPI_BF16_BIAS, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st); break;
-    case EPI_F32_BIAS: launch<BN, EPI_F32_BIAS, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st); break;
-    case EPI_F32_ADD: launch<BN, EPI_F32_ADD, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st); break;
+    case EPI_BF16_BIAS: launch<BN, EPI_BF16_BIAS, NCTA, CL>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st); break;
+    case EPI_F32_BIAS: launch<BN, EPI_F32_BIAS, NCTA, CL>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st); break;
+    case EPI_F32_ADD: launch<BN, EPI_F32_ADD, NCTA, CL>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st); break;
     case EPI_SWIGLU_BF16:
       if constexpr (BN == 256) {
-        launch<BN, EPI_SWIGLU_BF16, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st);
+        launch<BN, EPI_SWIGLU_BF16, NCTA, CL>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st);
         break;
       }
       fail(ABSB_ERR_INVALID, "SwiGLU epilogue needs 256-column tiles");
     case EPI_ARGMAX:
       if constexpr (BN == 256) {
-        launch<BN, EPI_ARGMAX, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st);
+        launch<BN, EPI_ARGMAX, NCTA, CL>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st);
         break;
       }
       fail(ABSB_ERR_INVALID, "arg-max epilogue needs 256-column tiles");
     case EPI_BF16_BIAS_ROPE:
       if constexpr (BN == 256) {
-        launch<BN, EPI_BF16_BIAS_ROPE, NCTA>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st);
+        launch<BN, EPI_BF16_BIAS_ROPE, NCTA, CL>(A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, p, sms, st);
         break;
       }
       fail(ABSB_ERR_INVALID, "RoPE epilogue needs 256-column tiles");
@@ -637,7 +673,8 @@ CUtensorMap make_tmap_bf16(const void* base, int64_t rows, int64_t cols, int64_t
 
 namespace {
 
-int g_gemm_variant = 0;  // 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3 = CTA pair x BN 192
+int g_gemm_variant = 0;  // 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3 = CTA pair x BN 192;
+                         // 4 = quad (two pairs sharing B by multicast) x BN 256; 5 = quad x BN 192
 
 }  // namespace
 
@@ -723,10 +760,13 @@ void gemm_bf16_tc_ex(int epi, int M, int N, int K, const void* A, int64_t lda, c
     }
   }
   if (variant == 3 && needs256) variant = 2;
+  if (variant == 5 && needs256) variant = 4;
   switch (variant) {
     case 1: launch_epi<256, 1>(epi, A, M, a_cols, lda, B, N, b_cols, ldb, p, sms, st); break;
     case 2: launch_epi<256, 2>(epi, A, M, a_cols, lda, B, N, b_cols, ldb, p, sms, st); break;
     case 3: launch_epi<192, 2>(epi, A, M, a_cols, lda, B, N, b_cols, ldb, p, sms, st); break;
+    case 4: launch_epi<256, 2, 2>(epi, A, M, a_cols, lda, B, N, b_cols, ldb, p, sms, st); break;
+    case 5: launch_epi<192, 2, 2>(epi, A, M, a_cols, lda, B, N, b_cols, ldb, p, sms, st); break;
     default: fail(ABSB_ERR_INVALID, "unknown GEMM variant %d", variant);
   }
 }
@@ -836,7 +876,7 @@ void gemm_split3_argmax(int M, int N, int K, const void* A3, const void* B3, flo
 
 extern "C" int absb_gemm_set_variant(int variant) {
   ABSB_API_BEGIN
-  ABSB_CHECK(variant >= 0 && variant <= 3, ABSB_ERR_INVALID, "GEMM variant %d outside [0,3]", variant);
+  ABSB_CHECK(variant >= 0 && variant <= 5, ABSB_ERR_INVALID, "GEMM variant %d outside [0,5]", variant);
   absb::gemm_set_variant(variant);
   ABSB_API_END
 }

@@ -112,6 +112,18 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
       : "memory");
 }
 
+// CTA-pair load that is ALSO multicast to the same shared-memory offset of every CTA in `cta_mask` (cluster ranks);
+// each destination pair's LEADER barrier (peer bit cleared) is credited with the bytes that landed in that pair.
+__device__ __forceinline__ void tma_load_2d_2cta_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                    uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "h"(cta_mask),
+      "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // Bulk tensor reduction smem -> global (element-wise add; the element type comes from the tensor map).
 // Issued by ONE thread for a whole box; completion is tracked by the thread's bulk async-group.
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
@@ -215,6 +227,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
             smem_u32(bar)),
         "h"((uint16_t)3)
         : "memory");
+}
+
+// cta_group::2 commit whose arrive is multicast to the barrier at the same offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_2cta_mask(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t).

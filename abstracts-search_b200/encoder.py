@@ -341,7 +341,8 @@ SentenceTransformer = Encoder
 
 
 def gemm_set_variant(variant: int = 0):
-    """Test hook: 0 auto, 1 = one CTA 128x256 tiles, 2 = CTA pair 256x256, 3 = CTA pair 256x192."""
+    """Test hook: 0 auto, 1 = one CTA 128x256 tiles, 2 = CTA pair 256x256, 3 = CTA pair 256x192, 4 / 5 = quad (two
+    pairs sharing the B tile by TMA multicast) with 256- / 192-column tiles."""
     check(lib().absb_gemm_set_variant(int(variant)))
 
 

@@ -314,7 +314,8 @@ int absb_enc_get_profile(absb_enc_t e, double* gemm_ms, double* gemm_flops, doub
  * 161 KB (4-5 stages instead of 5-7) leaves room for one co-resident scan CTA (absb_ivf_set_scan_impl 2). */
 int absb_gemm_set_smem_budget(int bytes);
 /* Test hook: force the tile shape of the tcgen05 GEMM (0 = automatic; 1 = one CTA, 128x256 tiles;
- * 2 = CTA pair (cta_group::2), 256x256 tiles; 3 = CTA pair, 256x192 tiles). Process-wide. */
+ * 2 = CTA pair (cta_group::2), 256x256 tiles; 3 = CTA pair, 256x192 tiles; 4 / 5 = "quad": a cluster of two CTA
+ * pairs stacked in M that share the B tile through TMA multicast, 512x256 / 512x192 super tiles). Process-wide. */
 int absb_gemm_set_variant(int variant);
 /* Same GEMM with one of the fused epilogues (gemm_tc.cuh): 0 = bf16 out (+bias), 1 = f32 out (+bias),
  * 2 = f32 out += acc (residual stream), 3 = bf16 SwiGLU (B rows interleaved per 256-row tile, out

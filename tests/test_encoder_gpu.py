@@ -27,7 +27,7 @@ def _loaded(P, base, sd):
     return enc
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1, 32, 64), (300, 512, 192), (129, 1536, 1536),
                                     (1000, 2048, 1536), (2048, 1536, 8960), (77, 96, 72), (4096, 768, 512),
                                     (257, 192, 128), (40000, 384, 256)])
@@ -289,6 +289,17 @@ def test_gemm_fused_epilogues(gpu_pkg):
         enc.gemm_bf16_epi(A, B, 2, out=h2)
         enc.gemm_bf16_epi(A, B, 2, out=h2)  # twice: += really accumulates
         assert (h2 - (h + 2 * ref)).abs().max().item() < 4e-3 * max(1.0, K / 256)
+        # the quad variants (two CTA pairs sharing the B tile by TMA multicast): same numbers as the pair variants
+        for v in (4, 5):
+            enc.gemm_set_variant(v)
+            try:
+                h3 = h.clone()
+                enc.gemm_bf16_epi(A, B, 2, out=h3)
+                enc.gemm_bf16_epi(A, B, 2, out=h3)
+                o1q = enc.gemm_bf16_epi(A, B, 1, bias=bias)
+            finally:
+                enc.gemm_set_variant(0)
+            assert torch.equal(h3, h2) and torch.equal(o1q, o1), (M, N, K, v)
     # SwiGLU: B rows interleaved per 256-row tile [128 gate | 128 up]
     M, I, K = 260, 512, 256
     A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)

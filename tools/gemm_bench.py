@@ -33,7 +33,7 @@ def main():
         fl = 2.0 * M * N * K
         ms = timeit(lambda: torch.matmul(A, B.T))
         row = [f"{name:9s} M={M} N={N} K={K}  cuBLAS {ms*1e3:7.1f} us {fl/ms/1e9:7.0f} TF"]
-        for v in (1, 2, 3):
+        for v in (1, 2, 3, 4, 5):
             enc.gemm_set_variant(v)
             try:
                 ms = timeit(lambda: enc.gemm_bf16(A, B))
@@ -54,8 +54,8 @@ def epilogues():
         out = torch.zeros((T, N // 2 if epi == 3 else N), dtype=torch.bfloat16 if epi in (0, 3) else torch.float32, device="cuda")
         ms = timeit(lambda: enc.gemm_bf16_epi(A, B, epi, out=out))
         row = f"epi {name:11s} M={T} N={N} K={K}: auto {ms*1e3:7.1f} us {2.0*T*N*K/ms/1e9:7.0f} TF"
-        if epi == 2:  # the residual-add GEMMs may take 256- or 192-column tiles
-            for v in (2, 3):
+        if True:  # every epilogue under the pair (2, 3) and quad (4, 5) variants; 192-column tiles only where allowed
+            for v in ((2, 3, 4, 5) if epi == 2 else (2, 4)):
                 enc.gemm_set_variant(v)
                 ms = timeit(lambda: enc.gemm_bf16_epi(A, B, epi, out=out))
                 row += f" | v{v} {ms*1e3:7.1f} us {2.0*T*N*K/ms/1e9:7.0f} TF"
