@@ -535,7 +535,7 @@ def secondary_metrics(args, P, torch, dist, enc, rank, world, dev):
                      "collective": "1 all-reduce of [nlist, d] sums + counts per iteration (NCCL)" if world > 1 else "none"}
     del xt, cent
     ix.set_centroids(P.synth.centroids(SEED, nlist, d, device=dev))  # the generating centres: known assignment
-    steps_add, warm_add = 3, 1
+    steps_add, warm_add = 4, 1
     xb = [P.synth.corpus(SEED, (s_ * world + rank) * n_add, n_add, d, nlist, device=dev, unit=unit) for s_ in range(steps_add + warm_add)]
 
     def add_step(i):
@@ -544,7 +544,13 @@ def secondary_metrics(args, P, torch, dist, enc, rank, world, dev):
         else:
             ix.add(xb[i])
 
-    ms = timed(add_step, steps_add, warm_add)
+    # every add() is timed on its own: the first adds of a process also pay the driver's mapping of fresh device
+    # memory for the list slabs (4.3 GB per 1M-row add), which varies from box to box; the median is reported
+    torch.cuda.empty_cache()
+    per_step = []
+    for i in range(warm_add + steps_add):
+        per_step.append(timed(lambda _i, i=i: add_step(i), 1, 0))
+    ms = float(np.median(per_step[warm_add:]))
     sizes = torch.from_numpy(ix.list_sizes()).to(device)
     if world > 1:
         dist.all_reduce(sizes)
@@ -555,7 +561,8 @@ def secondary_metrics(args, P, torch, dist, enc, rank, world, dev):
         rows = np.arange(0, (steps_add + warm_add) * world * n_add, dtype=np.int64)
         want = np.bincount(osynth.cluster_of(SEED, rows, nlist), minlength=nlist)
         hist_ok = bool(np.array_equal(want, sizes.cpu().numpy()))
-    out["add"] = {"rows_per_s": n_add * world / (ms * 1e-3), "ms_per_step": ms, "rows_per_step_per_gpu": n_add,
+    out["add"] = {"rows_per_s": n_add * world / (ms * 1e-3), "ms_per_step": ms, "ms_per_step_each": [round(v, 1) for v in per_step],
+                  "rows_per_step_per_gpu": n_add,
                   "assign_tflops_per_gpu": n_add * 6 * 2.0 * nlist * d / (ms * 1e-3) / 1e12,
                   "list_sizes_equal_generator_histogram": hist_ok,
                   "collective": "1 all-to-all of (vector, id, list) to the list owners (NCCL)" if world > 1 else "none"}
