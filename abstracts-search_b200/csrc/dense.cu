@@ -220,6 +220,30 @@ __global__ __launch_bounds__(kSelectWarps * 32) void select_rows_kernel(
   }
 }
 
+// Offers the candidates [b, e) of a query to the warp's k-best in their stored order, 32 per vote; the loads of four
+// votes are issued together so the merge waits for memory once per 128 candidates instead of once per 32.
+template <int SLOTS>
+__device__ __forceinline__ void offer_span(WarpTopK<SLOTS>& tk, const float* __restrict__ part_s,
+                                           const long long* __restrict__ part_id, int64_t b, int64_t e, int lane) {
+  constexpr int U = 4;
+  for (int64_t c0 = b; c0 < e; c0 += 32 * U) {
+    float v[U];
+    long long id[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t c = c0 + 32 * u + lane;
+      const bool valid = c < e;
+      v[u] = valid ? part_s[c] : 0.f;
+      id[u] = valid ? part_id[c] : kIdSentinel;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c0 + 32 * u >= e) break;  // warp-uniform
+      tk.offer_lanes(v[u], id[u], id[u] != kIdSentinel);
+    }
+  }
+}
+
 // One warp per query merges `cnt` blocks of k candidates laid out contiguously.
 template <int SLOTS>
 __global__ __launch_bounds__(128) void merge_partials_kernel(
@@ -232,14 +256,7 @@ __global__ __launch_bounds__(128) void merge_partials_kernel(
   if (active != nullptr && active[q] == 0) return;
   WarpTopK<SLOTS> tk;
   tk.init(k, lane);
-  const int64_t b = (int64_t)q_begin[q] * k, e = (int64_t)q_begin[q + 1] * k;
-  for (int64_t c0 = b; c0 < e; c0 += 32) {
-    const int64_t c = c0 + lane;
-    const bool valid = c < e;
-    const float v = valid ? part_s[c] : 0.f;
-    const long long id = valid ? part_id[c] : 0;
-    tk.offer_lanes(v, id, valid && id != kIdSentinel);
-  }
+  offer_span(tk, part_s, part_id, (int64_t)q_begin[q] * k, (int64_t)q_begin[q + 1] * k, lane);
 #pragma unroll
   for (int i = 0; i < SLOTS; ++i) {
     const int r = lane * SLOTS + i;
@@ -270,14 +287,7 @@ __global__ __launch_bounds__(128) void merge_partials_push_kernel(
     tk.init(k, lane);
     const bool merge = active == nullptr || active[q] != 0;
     if (merge) {
-      const int64_t b = (int64_t)q_begin[q] * k, e = (int64_t)q_begin[q + 1] * k;
-      for (int64_t c0 = b; c0 < e; c0 += 32) {
-        const int64_t c = c0 + lane;
-        const bool valid = c < e;
-        const float v = valid ? part_s[c] : 0.f;
-        const long long id = valid ? part_id[c] : 0;
-        tk.offer_lanes(v, id, valid && id != kIdSentinel);
-      }
+      offer_span(tk, part_s, part_id, (int64_t)q_begin[q] * k, (int64_t)q_begin[q + 1] * k, lane);
     }
 #pragma unroll
     for (int i = 0; i < SLOTS; ++i) {

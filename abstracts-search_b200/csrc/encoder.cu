@@ -72,52 +72,68 @@ __device__ __forceinline__ void rms_store(OUT* __restrict__ y, size_t t, int H, 
 }
 
 template <typename OUT>
-__global__ void rmsnorm_kernel(int64_t T, int H, float eps, const float* __restrict__ x,
-                               const float* __restrict__ w, OUT* __restrict__ y, float* __restrict__ rinv_out) {
+__global__ __launch_bounds__(256, 2) void rmsnorm_kernel(int64_t T, int H, float eps, const float* __restrict__ x,
+                                                         const float* __restrict__ w, OUT* __restrict__ y,
+                                                         float* __restrict__ rinv_out) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  // grid-stride over rows (the launch caps the grid at two CTAs per SM): a warp has the loads of its NEXT row in
+  // flight while it reduces, scales and stores the current one, so the SM never drains between rows
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (t >= T) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)t * H);
   const float4* wr = reinterpret_cast<const float4*>(w);
   const int n4 = H / 4;
   if (n4 <= 32 * kRmsRegs) {
-    float4 v[kRmsRegs];
+    float4 v[kRmsRegs], nx[kRmsRegs];
+    auto load_row = [&](float4 (&r)[kRmsRegs], int64_t row) {
+      const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * H);
 #pragma unroll
-    for (int i = 0; i < kRmsRegs; ++i) {
-      const int j = lane + 32 * i;
-      v[i] = j < n4 ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    // same summation order as the streaming path below: per lane ascending j, then the warp tree
-    float ss = 0.f;
+      for (int i = 0; i < kRmsRegs; ++i) {
+        const int j = lane + 32 * i;
+        r[i] = j < n4 ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_row(v, t);
+    for (;;) {
+      const int64_t tn = t + nw;
+      const bool more = tn < T;
+      if (more) load_row(nx, tn);
+      // same summation order as the streaming path below: per lane ascending j, then the warp tree
+      float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < kRmsRegs; ++i) ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-    ss = warp_sum(ss);
-    const float rinv = rsqrtf(ss / (float)H + eps);
-    if (rinv_out) {
-      if (lane == 0) rinv_out[t] = rinv;
-      if (!y) return;
-    }
+      for (int i = 0; i < kRmsRegs; ++i) ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      ss = warp_sum(ss);
+      const float rinv = rsqrtf(ss / (float)H + eps);
+      if (rinv_out && lane == 0) rinv_out[t] = rinv;
+      if (y) {
 #pragma unroll
-    for (int i = 0; i < kRmsRegs; ++i) {
-      const int j = lane + 32 * i;
-      if (j < n4) rms_store(y, (size_t)t, H, j, v[i], rinv, __ldg(wr + j));
+        for (int i = 0; i < kRmsRegs; ++i) {
+          const int j = lane + 32 * i;
+          if (j < n4) rms_store(y, (size_t)t, H, j, v[i], rinv, __ldg(wr + j));
+        }
+      }
+      if (!more) break;
+#pragma unroll
+      for (int i = 0; i < kRmsRegs; ++i) v[i] = nx[i];
+      t = tn;
     }
     return;
   }
-  float ss = 0.f;
-  for (int j = lane; j < n4; j += 32) {
-    const float4 v = xr[j];
-    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  for (; t < T; t += nw) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)t * H);
+    float ss = 0.f;
+    for (int j = lane; j < n4; j += 32) {
+      const float4 v = xr[j];
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    const float rinv = rsqrtf(ss / (float)H + eps);
+    if (rinv_out && lane == 0) rinv_out[t] = rinv;
+    if (y)
+      for (int j = lane; j < n4; j += 32) rms_store(y, (size_t)t, H, j, xr[j], rinv, __ldg(wr + j));
   }
-  ss = warp_sum(ss);
-  const float rinv = rsqrtf(ss / (float)H + eps);
-  if (rinv_out) {
-    if (lane == 0) rinv_out[t] = rinv;
-    if (!y) return;
-  }
-  for (int j = lane; j < n4; j += 32) rms_store(y, (size_t)t, H, j, xr[j], rinv, __ldg(wr + j));
 }
 
 // Masked mean pool of the final-normed hidden states: pooled[b, j] = w[j] * sum_s m[b,s] *
@@ -674,6 +690,7 @@ struct Encoder {
     const int H = cfg.hidden_size, I = cfg.intermediate_size, nh = cfg.num_heads, nkv = cfg.num_kv_heads;
     const int QKV = qkv_dim();
     const int wblocks = (int)ceil_div(T * 32, 256);
+    const int rblocks = std::min(wblocks, 2 * props.sm_count);  // rmsnorm: grid-stride, two CTAs per SM
     last_B = B;
     last_S = S;
     last_flops = 0;
@@ -688,7 +705,7 @@ struct Encoder {
       Layer& L = layers[l];
       {
         Span sp(this, st, 2);
-        launch_pdl(rmsnorm_kernel<bf16>, dim3(wblocks), dim3(256), 0, st, T, H, cfg.rms_eps, h.p, L.ln1.p, xn.p, nullptr);
+        launch_pdl(rmsnorm_kernel<bf16>, dim3(rblocks), dim3(256), 0, st, T, H, cfg.rms_eps, h.p, L.ln1.p, xn.p, nullptr);
       }
       {
         // QKV projection with bias and RoPE (q and k heads) fused into the epilogue
@@ -716,7 +733,7 @@ struct Encoder {
       gemm(EPI_F32_ADD, (int)T, H, nh * kHD, ao.p, L.wo.p, h.p, H, nullptr, st);
       {
         Span sp(this, st, 2);
-        launch_pdl(rmsnorm_kernel<bf16>, dim3(wblocks), dim3(256), 0, st, T, H, cfg.rms_eps, h.p, L.ln2.p, xn.p, nullptr);
+        launch_pdl(rmsnorm_kernel<bf16>, dim3(rblocks), dim3(256), 0, st, T, H, cfg.rms_eps, h.p, L.ln2.p, xn.p, nullptr);
       }
       gemm(EPI_SWIGLU_BF16, (int)T, 2 * I, H, xn.p, L.wgu.p, act.p, I, nullptr, st);
       gemm(EPI_F32_ADD, (int)T, H, I, act.p, L.wd.p, h.p, H, nullptr, st);
@@ -724,7 +741,7 @@ struct Encoder {
     }
     {
       Span sp(this, st, 2);
-      launch_pdl(rmsnorm_kernel<bf16>, dim3(wblocks), dim3(256), 0, st, T, H, cfg.rms_eps, h.p, final_norm.p, nullptr, rinv.p);
+      launch_pdl(rmsnorm_kernel<bf16>, dim3(rblocks), dim3(256), 0, st, T, H, cfg.rms_eps, h.p, final_norm.p, nullptr, rinv.p);
       dim3 pg((unsigned)ceil_div(H, 128), (unsigned)B);
       launch_pdl(pool_kernel, pg, dim3(128), 0, st, S, H, h.p, rinv.p, mask, final_norm.p, pooled.p);
     }
