@@ -140,6 +140,7 @@ _SIGS = {
     "absb_enc_set_profile": ([_H, c_int], c_int),
     "absb_enc_get_profile": ([_H, _PD, _PD, _PD, _PD, _PI64], c_int),
     "absb_gemm_set_variant": ([c_int], c_int),
+    "absb_gemm_set_ksplit": ([c_int], c_int),
     "absb_gemm_set_smem_budget": ([c_int], c_int),
     "absb_gemm_bf16_epi_dev": ([c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "absb_gemm_bf16_dev": ([c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p], c_int),

@@ -92,7 +92,33 @@ struct KernelParams {
   const float2* rope_cs;  // EPI_BF16_BIAS_ROPE only
   int rope_S, rope_cols, rope_ld;
   int* arg_idx;  // EPI_ARGMAX only: [M, ldc] next to out = float [M, ldc]
+  // Split K (residual-add epilogue only): a tile's k-blocks are cut into `ksplit` slices of `kb_per_slice`; the
+  // work unit of the persistent loop is (slice, tile), slice-major.  Every slice adds its partial sum into the
+  // output; `split_ctr` holds one turn counter per (tile, CTA, epilogue warp) so that the slices of a tile add
+  // in slice order — the result is a fixed sum, independent of timing.
+  int ksplit, kb_per_slice;
+  int* split_ctr;
 };
+
+struct WorkUnit {
+  int tile, slice, kb0, kb1;
+};
+__device__ __forceinline__ WorkUnit work_unit(const KernelParams& p, int u, int num_tiles) {
+  WorkUnit w;
+  w.slice = u / num_tiles;  // ksplit == 1: always 0
+  w.tile = u - w.slice * num_tiles;
+  w.kb0 = w.slice * p.kb_per_slice;
+  w.kb1 = min(p.num_kb, w.kb0 + p.kb_per_slice);
+  return w;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* ptr, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -147,6 +173,7 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
   const int pair = CL == 1 ? 0 : (crank >> 1);  // which pair of the quad
   const int cta_rank = crank & 1;               // rank inside the pair (0 = leader)
   const int worker = blockIdx.x / (NCTA * CL), num_workers = gridDim.x / (NCTA * CL);  // a worker = CTA, pair or quad
+  const int num_units = num_tiles * p.ksplit;
 
   pdl_trigger();  // the next kernel of the stream may set itself up as soon as an SM has room for it
   if (warp == 0 && lane == 0) {
@@ -182,13 +209,14 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      for (int u = worker; u < num_units; u += num_workers) {
+        const WorkUnit wu = work_unit(p, u, num_tiles);
         int tm, tn;
-        tile_coords(p, tile, tm, tn);
+        tile_coords(p, wu.tile, tm, tn);
         tm = tm * CL + pair;
         const int row_a = (tm * NCTA + cta_rank) * BM;
         const int row_b = tn * BN + cta_rank * L::kBRows;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = wu.kb0; kb < wu.kb1; ++kb) {
           const int seg = kb / p.seg_kb, within = kb - seg * p.seg_kb;
           tc::mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
@@ -225,11 +253,12 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      for (int u = worker; u < num_units; u += num_workers) {
+        const WorkUnit wu = work_unit(p, u, num_tiles);
         tc::mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         tc::tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = wu.kb0; kb < wu.kb1; ++kb) {
           tc::mbar_wait(full_bar + stage, phase);
           tc::tcgen05_fence_after();
           const uint32_t sa = tc::smem_u32(smem + stage * L::kStageBytes);
@@ -238,7 +267,8 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
-            tc::umma_bf16<NCTA>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            tc::umma_bf16<NCTA>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                (kb != wu.kb0 || k != 0) ? 1u : 0u);
           }
           if constexpr (CL == 1) tc::umma_commit<NCTA>(empty_bar + stage);
           else tc::umma_commit_2cta_mask(empty_bar + stage, 0xF);  // the stage is shared by the four CTAs
@@ -266,12 +296,26 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
     const uint32_t tmem_empty_addr0 = NCTA == 1 ? 0u : tc::map_to_cta(tc::smem_u32(tmem_empty), (uint32_t)(2 * pair));
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+    for (int u = worker; u < num_units; u += num_workers) {
+      const WorkUnit wu = work_unit(p, u, num_tiles);
       int tm, tn;
-      tile_coords(p, tile, tm, tn);
+      tile_coords(p, wu.tile, tm, tn);
       tm = tm * CL + pair;
       const int row = (tm * NCTA + cta_rank) * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
+      int* turn = nullptr;
+      if constexpr (EPI == EPI_F32_ADD && kTmaReduce) {
+        if (p.ksplit > 1) {
+          // split K: this warp's boxes of the tile are added in slice order.  The earlier slice belongs to a unit
+          // with a smaller index — running on another worker or finished — so the wait cannot deadlock.
+          turn = p.split_ctr + (((size_t)wu.tile * CL + pair) * NCTA + cta_rank) * 8 + (warp - kEpiWarp0);
+          if (lane == 0) {
+            while (ld_acquire_gpu(turn) != wu.slice) __nanosleep(40);
+            asm volatile("fence.proxy.async;" ::: "memory");  // the reductions below run in the async proxy
+          }
+          __syncwarp();
+        }
+      }
       tc::mbar_wait(tmem_full + acc, acc_phase);
       tc::tcgen05_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
@@ -471,6 +515,13 @@ __global__ ABSB_GEMM_BOUNDS void gemm_bf16_tc_kernel(const __grid_constant__ CUt
         if (NCTA == 1 || cta_rank == 0) tc::mbar_arrive_relaxed(tmem_empty + acc);
         else tc::mbar_arrive_cluster_relaxed(tmem_empty_addr0 + (uint32_t)(acc * 8));
       }
+      if constexpr (EPI == EPI_F32_ADD && kTmaReduce) {
+        if (turn != nullptr && lane == 0) {
+          tc::bulk_wait_all();  // this slice's reductions have been performed ...
+          __threadfence();
+          st_release_gpu(turn, wu.slice + 1 == p.ksplit ? 0 : wu.slice + 1);  // ... the next slice may add (last: reset)
+        }
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -580,6 +631,45 @@ CUtensorMap make_tmap_f32_box32_uncached(const void* base, int64_t rows, int64_t
   return m;
 }
 
+// ---- split K for the residual-add GEMMs -----------------------------------------------------------------------
+// FFN-down at M = 2048 (the per-GPU token count of the 8-GPU query step) is 64 tiles of 140 k-blocks on 74 CTA
+// pairs: one wave, 10 pairs idle, 140 k-block times.  Cut into 8 slices it is 512 units of 17.5 k-blocks = 6.9
+// waves = 122.5 k-block times.  The slices of a tile add into the fp32 residual in slice order (turn counters in
+// `split_ctr`), so the sum is fixed.  MEASURED on B200 (profiles/r02y_gemm_split_k.log): slower at every shape that
+// matters — FFN-down M = 2048: 47.5 us unsplit, 49.1 / 51.8 / 62.2 us with 2 / 4 / 8 slices — because the
+// residual-add epilogue of a 256 x 192 tile costs ~9 us (it is what bounds the O-proj, whose main loop is 5 us) and
+// every slice pays it, while an unsplit FFN-down hides it under 27 us of MMAs.  Hence: 0 (default) and 1 = never
+// split, n = force n slices (tests, micro-benchmark).
+int g_gemm_ksplit = 0;
+constexpr int kSplitCounters = 1 << 16;
+
+int choose_ksplit(int tiles, int slots, int num_kb, bool allowed) {
+  (void)tiles;
+  (void)slots;
+  if (!allowed || num_kb < 2 || g_gemm_ksplit <= 1) return 1;
+  int ks = std::min(g_gemm_ksplit, num_kb);
+  while (ks > 1 && (int64_t)(ks - 1) * ceil_div(num_kb, ks) >= num_kb) --ks;  // no empty slice
+  return ks;
+}
+
+// zero-initialised turn counters, one buffer per (device, stream): every split launch leaves them at zero
+int* split_counters(cudaStream_t st) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, int*> bufs;
+  int dev = 0;
+  ABSB_CUDA(cudaGetDevice(&dev));
+  const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(st) * 64u + (uint64_t)dev;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = bufs.find(key);
+  if (it != bufs.end()) return it->second;
+  int* ptr = nullptr;
+  ABSB_CUDA(cudaMalloc(&ptr, kSplitCounters * sizeof(int)));
+  ABSB_CUDA(cudaMemset(ptr, 0, kSplitCounters * sizeof(int)));
+  ABSB_CUDA(cudaDeviceSynchronize());
+  bufs.emplace(key, ptr);
+  return ptr;
+}
+
 template <int BN, int EPI, int NCTA, int CL = 1>
 void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const void* B, int64_t b_rows, int64_t b_cols,
             int64_t ldb, KernelParams p, int sms, cudaStream_t st) {
@@ -624,7 +714,19 @@ void launch(const void* A, int64_t a_rows, int64_t a_cols, int64_t lda, const vo
     }
     slots = std::min(slots, max_clusters);
   }
-  const int workers = std::max(1, std::min(p.tiles_m * p.tiles_n, slots));
+  const int tiles = p.tiles_m * p.tiles_n;
+  p.ksplit = 1;
+  p.kb_per_slice = p.num_kb;
+  p.split_ctr = nullptr;
+  if constexpr (EPI == EPI_F32_ADD && kTmaReduce) {
+    const int ks = choose_ksplit(tiles, slots, p.num_kb, p.seg_kb == p.num_kb && (int64_t)tiles * NCTA * CL * 8 <= kSplitCounters);
+    if (ks > 1) {
+      p.ksplit = ks;
+      p.kb_per_slice = (int)ceil_div(p.num_kb, ks);
+      p.split_ctr = split_counters(st);
+    }
+  }
+  const int workers = std::max(1, std::min(tiles * p.ksplit, slots));
   cfg.gridDim = dim3((unsigned)(workers * NCTA * CL));
   attr[0].val.clusterDim.x = NCTA * CL;
   attr[0].val.clusterDim.y = 1;
@@ -679,6 +781,7 @@ int g_gemm_variant = 0;  // 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3
 }  // namespace
 
 void gemm_set_variant(int v) { g_gemm_variant = v; }
+void gemm_set_ksplit(int n) { g_gemm_ksplit = n; }
 void gemm_set_smem_budget(int bytes) { g_gemm_smem_budget = bytes; }
 bool gemm_coresident_mode() { return g_gemm_smem_budget < 200 * 1024; }
 
@@ -878,6 +981,13 @@ extern "C" int absb_gemm_set_variant(int variant) {
   ABSB_API_BEGIN
   ABSB_CHECK(variant >= 0 && variant <= 5, ABSB_ERR_INVALID, "GEMM variant %d outside [0,5]", variant);
   absb::gemm_set_variant(variant);
+  ABSB_API_END
+}
+
+extern "C" int absb_gemm_set_ksplit(int slices) {
+  ABSB_API_BEGIN
+  ABSB_CHECK(slices >= 0 && slices <= 64, ABSB_ERR_INVALID, "GEMM k-slices %d outside [0,64]", slices);
+  absb::gemm_set_ksplit(slices);
   ABSB_API_END
 }
 

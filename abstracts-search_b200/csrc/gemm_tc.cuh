@@ -62,6 +62,7 @@ void attention_tc(const void* qkv, int ld, const int* mask, void* out, int ldo, 
 
 // test hook: 0 auto; 1 = 1 CTA x BN 256; 2 = CTA pair x BN 256; 3 = CTA pair x BN 192
 void gemm_set_variant(int v);
+void gemm_set_ksplit(int n);  // 0 auto, 1 off, n forced (residual-add epilogue only)
 // Shared memory a GEMM CTA may take (absb_gemm_set_smem_budget); a budget below the full 227 KB means the
 // encoder shares its SMs with a co-resident scan CTA.
 void gemm_set_smem_budget(int bytes);

@@ -346,6 +346,11 @@ def gemm_set_variant(variant: int = 0):
     check(lib().absb_gemm_set_variant(int(variant)))
 
 
+def gemm_set_ksplit(slices: int = 0):
+    """Split K of the residual-add GEMMs: 0 / 1 = never (default; measured slower on B200), n = n slices (test hook)."""
+    check(lib().absb_gemm_set_ksplit(int(slices)))
+
+
 def gemm_bf16_epi(A, B, epi: int, out=None, bias=None):
     """The tcgen05 GEMM with a fused epilogue (0 bf16, 1 f32, 2 f32 +=, 3 SwiGLU bf16) — test hook."""
     import torch

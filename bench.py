@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--scan-chunk", type=int, default=512, help="vectors per scan work item")
     ap.add_argument("--scan-order", type=int, default=1, help="1 list-major work queue (default), 0 query-major")
     ap.add_argument("--gemm-variant", type=int, default=0, help="tcgen05 GEMM tile shape (0 auto; see absb_gemm_set_variant)")
+    ap.add_argument("--gemm-ksplit", type=int, default=0,
+                    help="k-slices of the residual-add GEMMs: 0 / 1 = never split (default), n = forced (experiment)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: all-gathers of the query path as NVLink peer-memory stores fused into our kernels "
                          "(default) or as NCCL calls")
@@ -618,6 +620,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     if args.gemm_variant:
         importlib.import_module("abstracts-search_b200.encoder").gemm_set_variant(args.gemm_variant)
+    if args.gemm_ksplit:
+        importlib.import_module("abstracts-search_b200.encoder").gemm_set_ksplit(args.gemm_ksplit)
     enc = P.Encoder(config=P.STELLA_1_5B, device=device, random_init_seed=0)
     secondary = None
     if not args.skip_secondary:
@@ -987,6 +991,8 @@ def run_encode(args, rank: int, world: int, local_rank: int):
     B, S = args.encode_batch, args.seq_len
     if args.gemm_variant:
         importlib.import_module("abstracts-search_b200.encoder").gemm_set_variant(args.gemm_variant)
+    if args.gemm_ksplit:
+        importlib.import_module("abstracts-search_b200.encoder").gemm_set_ksplit(args.gemm_ksplit)
     enc = P.Encoder(config=P.STELLA_1_5B, device=device, random_init_seed=0)
     nbuf = 4
     g = torch.Generator().manual_seed(99 + rank)

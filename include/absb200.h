@@ -317,6 +317,10 @@ int absb_gemm_set_smem_budget(int bytes);
  * 2 = CTA pair (cta_group::2), 256x256 tiles; 3 = CTA pair, 256x192 tiles; 4 / 5 = "quad": a cluster of two CTA
  * pairs stacked in M that share the B tile through TMA multicast, 512x256 / 512x192 super tiles). Process-wide. */
 int absb_gemm_set_variant(int variant);
+/* Split K of the residual-add GEMMs (epilogue 2: O-proj, FFN-down): 0 / 1 = never (default: measured slower on
+ * B200 at every encoder shape), n = force n slices (test / micro-benchmark hook).  The slices
+ * of a tile add into the output in slice order: the result does not depend on timing.  Process-wide. */
+int absb_gemm_set_ksplit(int slices);
 /* Same GEMM with one of the fused epilogues (gemm_tc.cuh): 0 = bf16 out (+bias), 1 = f32 out (+bias),
  * 2 = f32 out += acc (residual stream), 3 = bf16 SwiGLU (B rows interleaved per 256-row tile, out
  * [M, N/2]).  Test / micro-benchmark hook. */

@@ -268,6 +268,53 @@ def test_attention_kernels_all_lengths(gpu_pkg, S, impl):
         assert (1 - oenc.cosine_rows(emb, ref)).max() < COS_TOL, (S, impl, causal)
 
 
+@pytest.mark.parametrize("M,N,K,slices", [(2048, 1536, 8960, 8), (4096, 1536, 8960, 4), (8192, 1536, 8960, 2),
+                                          (1000, 768, 4096, 3), (300, 1536, 2048, 5), (129, 512, 1024, 16),
+                                          (2048, 1536, 8960, 64), (2048, 1536, 8960, 0)])
+def test_gemm_split_k_residual_add(gpu_pkg, M, N, K, slices):
+    """Residual-add GEMM with K cut into slices (absb_gemm_set_ksplit; 0 = the per-launch choice, which never splits:
+    measured slower on B200): same sum as the unsplit kernel up to fp32 re-association, equal to the
+    fp32 reference within the unsplit tolerance, and — the slices of a tile add in slice order — the same bits on
+    every run."""
+    import torch
+    from importlib import import_module
+
+    enc = import_module("abstracts-search_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    B = (torch.randn((N, K), device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    h = torch.randn((M, N), device="cuda", generator=g)
+    ref = h.double() + A.double() @ B.double().T
+    try:
+        enc.gemm_set_ksplit(1)
+        unsplit = h.clone()
+        enc.gemm_bf16_epi(A, B, 2, out=unsplit)
+        enc.gemm_set_ksplit(slices)
+        runs = []
+        for _ in range(3):
+            o = h.clone()
+            enc.gemm_bf16_epi(A, B, 2, out=o)
+            runs.append(o)
+        # a different shape in between: the turn counters are back at zero after every launch
+        o_small = h[:130, :512].clone()
+        enc.gemm_bf16_epi(A[:130], B[:512], 2, out=o_small)
+        o = h.clone()
+        enc.gemm_bf16_epi(A, B, 2, out=o)
+        runs.append(o)
+    finally:
+        enc.gemm_set_ksplit(0)
+    tol = 4e-3 * max(1.0, K / 256)
+    assert (unsplit.double() - ref).abs().max().item() < tol
+    for o in runs:
+        assert torch.equal(o, runs[0])
+        assert (o.double() - ref).abs().max().item() < tol
+        assert (o - unsplit).abs().max().item() < 1e-4 * max(1.0, K / 256)
+    if slices == 0:
+        assert torch.equal(runs[0], unsplit), "the per-launch choice does not split"
+    elif K >= 4096:
+        assert not torch.equal(runs[0], unsplit), "a forced split re-associates the fp32 sum"
+
+
 def test_gemm_fused_epilogues(gpu_pkg):
     """bias / residual-add (bulk tensor reduction) / SwiGLU epilogues against torch, ragged M."""
     import torch

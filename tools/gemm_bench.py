@@ -63,7 +63,30 @@ def epilogues():
         print(row, flush=True)
 
 
+def split_k():
+    """Residual-add GEMMs with K cut into slices (absb_gemm_set_ksplit): auto choice against 1 / 2 / 4 / 8 slices."""
+    for T in (2048, 4096, 8192, 16384):
+        for name, N, K in [("o  f32+=", 1536, 1536), ("down f32+=", 1536, 8960)]:
+            A = torch.randn((T, K), device="cuda").to(torch.bfloat16)
+            B = (torch.randn((N, K), device="cuda") * 0.02).to(torch.bfloat16)
+            out = torch.zeros((T, N), dtype=torch.float32, device="cuda")
+            row = f"split-k {name:11s} M={T} N={N} K={K}:"
+            for v in (0, 2, 3):
+                enc.gemm_set_variant(v)
+                row += f" || v{v}"
+                for ks in (0, 1, 2, 4, 8, 16):
+                    enc.gemm_set_ksplit(ks)
+                    ms = timeit(lambda: enc.gemm_bf16_epi(A, B, 2, out=out))
+                    row += f" | {'auto' if ks == 0 else ks}: {ms*1e3:6.1f}"
+            enc.gemm_set_variant(0)
+            enc.gemm_set_ksplit(0)
+            print(row, flush=True)
+
+
 if __name__ == "__main__":
+    if "--split-k" in sys.argv:
+        split_k()
+        sys.exit(0)
     if "--epi-only" not in sys.argv:
         main()
     epilogues()
