@@ -258,7 +258,9 @@ def read_ivfflat(path: str, ondisk_dir: str | None = None) -> IVFFlatData:
         name = bytes(r.vector(np.uint8)).decode()
         totsize = r.take("<Q")
         data_path = os.path.join(ondisk_dir or os.path.dirname(os.path.abspath(path)), os.path.basename(name))
-        data = np.memmap(data_path, dtype=np.uint8, mode="r")
+        # an index without vectors has a zero-byte ondisk.ivfdata, which cannot be mapped
+        any_rows = bool((table[:, 0] > 0).any())
+        data = np.memmap(data_path, dtype=np.uint8, mode="r") if any_rows else None
         out.ondisk = {"filename": name, "lists": table, "totsize": totsize}
         for size, cap, off in table.astype(np.int64):
             size, cap, off = int(size), int(cap), int(off)

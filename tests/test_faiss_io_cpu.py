@@ -194,3 +194,59 @@ def test_writer_emits_the_hand_built_ondisk_layout(tmp_path):
         off = int(table[l, 2])
         assert raw[off:off + sizes[l] * 16] == codes[l].tobytes()
         assert raw[off + int(table[l, 1]) * 16: off + int(table[l, 1]) * 16 + sizes[l] * 8] == ids[l].tobytes()
+
+
+def test_roundtrip_fuzz_array_sparse_and_ondisk(tmp_path):
+    """hypothesis: random (d, nlist, list sizes incl. many empty lists, metric, nprobe) through every container —
+    `ilar` full / sparse (the writer picks by fill ratio, as faiss does) and `ilod` + ondisk.ivfdata — must read
+    back identically, and the three files of one index must agree with each other."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    fio = _fio()
+    counter = [0]
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(d=st.sampled_from([1, 3, 4, 16, 33]), nlist=st.integers(1, 40), fill=st.floats(0.0, 1.0),
+           max_len=st.integers(1, 9), metric=st.sampled_from([0, 1]), nprobe=st.integers(1, 64), seed=st.integers(0, 2**31))
+    def run(d, nlist, fill, max_len, metric, nprobe, seed):
+        rng = np.random.default_rng(seed)
+        codes, ids, nxt = [], [], 0
+        for _ in range(nlist):
+            n = int(rng.integers(1, max_len + 1)) if rng.random() < fill else 0
+            codes.append(rng.standard_normal((n, d)).astype(np.float32))
+            ids.append(rng.permutation(np.arange(nxt, nxt + n, dtype=np.int64)) + int(rng.integers(0, 1 << 40)))
+            nxt += n
+        cent = rng.standard_normal((nlist, d)).astype(np.float32)
+        ix = fio.IVFFlatData(d, nlist, nprobe, metric, True, cent, codes, ids)
+        counter[0] += 1
+        sub = tmp_path / f"case{counter[0]}"
+        sub.mkdir()
+        p_arr, p_od, dpath = str(sub / "array.faiss"), str(sub / "index.faiss"), str(sub / "ondisk.ivfdata")
+        fio.write_ivfflat(p_arr, ix)
+        fio.write_ivfflat(p_od, ix, ondisk_path=dpath)
+        for back in (fio.read_ivfflat(p_arr), fio.read_ivfflat(p_od)):
+            assert (back.d, back.nlist, back.nprobe, back.metric, back.is_trained) == (d, nlist, nprobe, metric, True)
+            assert back.ntotal == nxt and np.array_equal(back.centroids, cent)
+            for l in range(nlist):
+                assert back.codes[l].shape == (len(ids[l]), d)
+                assert np.array_equal(back.codes[l], codes[l]) and np.array_equal(back.ids[l], ids[l])
+        import os
+
+        assert os.path.getsize(dpath) == nxt * (4 * d + 8)
+
+    run()
+
+
+def test_ondisk_index_without_vectors(tmp_path):
+    """A trained index written with on-disk lists before any add(): ondisk.ivfdata is a zero-byte file (found by the
+    fuzz above: it cannot be memory-mapped) and every list reads back empty."""
+    fio = _fio()
+    cent = np.arange(12, dtype=np.float32).reshape(3, 4)
+    empty = [np.zeros((0, 4), np.float32)] * 3, [np.zeros(0, np.int64)] * 3
+    p, dpath = str(tmp_path / "index.faiss"), str(tmp_path / "ondisk.ivfdata")
+    fio.write_ivfflat(p, fio.IVFFlatData(4, 3, 1, 0, True, cent, *empty), ondisk_path=dpath)
+    import os
+
+    assert os.path.getsize(dpath) == 0
+    back = fio.read_ivfflat(p)
+    assert back.ntotal == 0 and [len(i) for i in back.ids] == [0, 0, 0] and np.array_equal(back.centroids, cent)
