@@ -183,6 +183,15 @@ def test_compaction_plan_permutes_pages_in_place(n, scratch, seed):
     src = rng.permutation(n).astype(np.int32)
     if seed % 2:  # a partly ordered table, as left by a few large add() calls
         src[: n // 2] = np.sort(src[: n // 2])
+    _check_plan(src, scratch)
+
+
+def _check_plan(src, scratch):
+    """Replays a plan on a pool whose page p holds 1000 + p: phases must be internally race-free and the pool must end
+    up as content_new[t] == content_old[src[t]]."""
+    import numpy as np
+
+    n = len(src)
     moves, phases = _plan(src, scratch)
     pool = np.arange(n, dtype=np.int64) + 1000  # page p holds content 1000 + p
     sc = np.full(scratch, -1, dtype=np.int64)
@@ -203,6 +212,37 @@ def test_compaction_plan_permutes_pages_in_place(n, scratch, seed):
     assert begin == len(moves)
     assert np.array_equal(pool, src.astype(np.int64) + 1000), "content_new[t] must equal content_old[src[t]]"
     assert len(moves) <= 3 * n
+
+
+def test_compaction_plan_fuzz():
+    """hypothesis: permutations built from the shapes real page tables have — long ordered runs (large add() calls),
+    rotations, swapped blocks, fixed points, plus uniformly random ones — under scratch sizes from 1 page to > n."""
+    import numpy as np
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(n=st.integers(1, 400), scratch=st.integers(1, 450), kind=st.integers(0, 4), seed=st.integers(0, 2**31))
+    def run(n, scratch, kind, seed):
+        rng = np.random.default_rng(seed)
+        if kind == 0:
+            src = rng.permutation(n)
+        elif kind == 1:  # rotation: one cycle through every page
+            src = np.roll(np.arange(n), int(rng.integers(0, n)))
+        elif kind == 2:  # interleave of a few ordered runs (lists appended to in turn)
+            runs = int(rng.integers(1, 6))
+            owner = rng.integers(0, runs, n)
+            src = np.argsort(owner, kind="stable")
+        elif kind == 3:  # mostly fixed points, a few transpositions
+            src = np.arange(n)
+            for _ in range(int(rng.integers(0, 5))):
+                i, j = rng.integers(0, n, 2)
+                src[[i, j]] = src[[j, i]]
+        else:  # two swapped blocks
+            cut = int(rng.integers(0, n + 1))
+            src = np.concatenate([np.arange(cut, n), np.arange(0, cut)])
+        _check_plan(src.astype(np.int32), scratch)
+
+    run()
 
 
 def test_compaction_plan_skips_an_ordered_table_and_rejects_garbage():

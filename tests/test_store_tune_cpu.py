@@ -97,3 +97,98 @@ def test_train_index_reads_only_the_drawn_row_groups(tmp_path, monkeypatch):
     want = np.concatenate([real(p, g, d, ("embedding",))[1] for p, g, _ in reads])
     assert np.array_equal(seen["x"], want)
     assert P.store.train_index(ix, str(tmp_path / "data"), max_rows=300, seed=7) == rows  # seeded: same draw
+
+
+def test_store_fuzz_ragged_shards_and_row_groups(tmp_path):
+    """hypothesis: stores with ragged shard and row-group sizes (1-row groups, a short last shard, one group holding
+    everything): the footer listing, the streaming iterator, fill_index (+ ids.parquet) and the seeded train draw
+    must agree with the arrays that were written."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    P = _pkg()
+    case = [0]
+
+    class _Sink:
+        def __init__(self, d):
+            self.d, self.nlist, self.rows, self.trained = d, 4, [], None
+            self.cp = P.ClusteringParameters()
+
+        def add(self, x):
+            assert x.dtype == np.float32 and x.shape[1] == self.d
+            self.rows.append(x.copy())
+
+        def train(self, x):
+            self.trained = x.copy()
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(n=st.integers(1, 400), d=st.sampled_from([4, 64]), shard=st.integers(1, 500), group=st.integers(1, 300),
+           cap=st.integers(1, 500), seed=st.integers(0, 2**31))
+    def run(n, d, shard, group, cap, seed):
+        rng = np.random.default_rng(seed)
+        x = (rng.integers(-127, 128, (n, d)) / 128.0).astype(np.float32)  # exact in float16
+        ids = [f"W{int(v)}" for v in rng.integers(0, 1 << 40, n)]
+        case[0] += 1
+        root = str(tmp_path / f"s{case[0]}")
+        paths = P.store.write_shards(root, ids, x, shard_size=shard, row_group_size=group)
+        assert len(paths) == -(-n // shard) and P.store.count_rows(root) == n
+        groups = P.store.list_row_groups(root)
+        assert sum(g[2] for g in groups) == n and all(0 < g[2] <= min(group, shard) for g in groups)
+        got_ids, got = [], []
+        for i, e in P.store.iter_row_groups(root, d):
+            got_ids += i
+            got.append(e)
+        assert got_ids == ids and np.array_equal(np.concatenate(got), x)
+        sink = _Sink(d)
+        assert P.store.fill_index(sink, root, ids_parquet=root + "/../ids%d.parquet" % case[0]) == n
+        assert np.array_equal(np.concatenate(sink.rows), x) and len(sink.rows) == len(groups)
+        assert P.faiss_io.read_ids_parquet(root + "/../ids%d.parquet" % case[0]) == ids
+        rows = P.store.train_index(sink, root, max_rows=cap, seed=seed % 1000)
+        assert rows == sink.trained.shape[0] and min(cap, n) <= rows <= n
+        # the sample consists of whole row groups of the store: every sampled row is a stored row
+        stored = {r.tobytes() for r in x}
+        assert all(r.tobytes() in stored for r in sink.trained)
+
+    run()
+
+
+def test_pareto_and_recall_properties():
+    """hypothesis: `pareto` keeps exactly the operating points no other point dominates (recall and qps both at least
+    as good, one strictly better) — one representative per duplicate — and `recall_at_k` is the intersection measure
+    with -1 padding ignored on both sides."""
+    from hypothesis import given, settings, strategies as st
+
+    P = _pkg()
+    pt = st.tuples(st.integers(0, 20), st.integers(0, 20))
+
+    @settings(max_examples=300, deadline=None)
+    @given(pts=st.lists(pt, min_size=1, max_size=25))
+    def run_pareto(pts):
+        points = [{"nprobe": i, "recall": r / 20.0, "qps": float(q)} for i, (r, q) in enumerate(pts)]
+        keep = P.tune.pareto(points)
+        kept = {(p["recall"], p["qps"]) for p in keep}
+        assert len(kept) == len(keep)
+        assert [p["recall"] for p in keep] == sorted(p["recall"] for p in keep)
+
+        def dominated(a, b):  # b dominates a
+            return b[0] >= a[0] and b[1] >= a[1] and b != a
+
+        allp = {(p["recall"], p["qps"]) for p in points}
+        want = {a for a in allp if not any(dominated(a, b) for b in allp)}
+        assert kept == want
+
+    run_pareto()
+
+    @settings(max_examples=200, deadline=None)
+    @given(seed=st.integers(0, 2**31), nq=st.integers(1, 6), k=st.integers(1, 8), universe=st.integers(8, 40))
+    def run_recall(seed, nq, k, universe):
+        rng = np.random.default_rng(seed)
+        I = np.stack([rng.permutation(universe)[:k] for _ in range(nq)]).astype(np.int64)
+        T = np.stack([rng.permutation(universe)[:k] for _ in range(nq)]).astype(np.int64)
+        pad = rng.random((nq, k)) < 0.2
+        I[pad] = -1
+        T[rng.random((nq, k)) < 0.2] = -1
+        hits = sum(len(set(a[a >= 0]) & set(b[b >= 0])) for a, b in zip(I, T))
+        assert P.tune.recall_at_k(I, T) == hits / max(1, int((T >= 0).sum()))
+        assert P.tune.recall_at_k(T, T) == (1.0 if (T >= 0).any() else 0.0)
+
+    run_recall()
