@@ -324,7 +324,7 @@ class Encoder:
         return {"flops": f.value, "launches": l.value}
 
     def set_attention_impl(self, impl: int):
-        """1 = tcgen05 attention for S <= 256 (default), 0 = always the mma.sync kernel."""
+        """1 = tcgen05 attention (default; every S <= 512), 0 = the mma.sync kernel (test hook)."""
         check(lib().absb_enc_set_attention_impl(self._h, int(impl)))
 
     def set_profile(self, on: int):

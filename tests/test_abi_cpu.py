@@ -259,3 +259,65 @@ def test_compaction_plan_skips_an_ordered_table_and_rejects_garbage():
     a, b = ctypes.c_int64(), ctypes.c_int64()
     assert L.absb_plan_page_compaction(3, bad.ctypes.data, 2, out.ctypes.data, 16, ph.ctypes.data, 16,
                                        ctypes.byref(a), ctypes.byref(b)) != 0
+
+
+def test_encode_host_logic_fuzz(P):
+    """hypothesis: `SentenceTransformer.encode` host logic — prompt prefix, sort by text length (descending, stable),
+    batches of `batch_size`, results restored to input order, str in -> vector out — with the device forward replaced
+    by a function of each row's own (unpadded) token ids."""
+    from importlib import import_module
+
+    from hypothesis import given, settings, strategies as st
+
+    E = import_module("abstracts-search_b200.encoder")
+    enc = E.Encoder.__new__(E.Encoder)  # no device handle: only the host side is exercised
+    enc.config = P.EncoderConfig()
+    enc.prompts = {"s2p_query": "Instruct: find. Query: ", "empty": ""}
+    enc.default_prompt_name = None
+    enc.max_seq_length = 12
+    enc.tokenizer = E.HashTokenizer(1000)
+    enc.device = "cuda:0"
+    enc._h = None
+    seen_batches = []
+
+    def row_embedding(ids):
+        v = np.zeros(enc.config.embed_dim, dtype=np.float32)
+        for j, t in enumerate(ids):
+            v[(int(t) * 31 + j) % v.size] += 1.0 + j
+        return v
+
+    def fake_forward(input_ids, attention_mask=None, normalize_embeddings=False):
+        seen_batches.append(input_ids.shape)
+        assert input_ids.shape[1] <= enc.max_seq_length and attention_mask.shape == input_ids.shape
+        # right padding only, never a fully padded column
+        assert (np.diff(attention_mask, axis=1) <= 0).all() and attention_mask[:, 0].all() and attention_mask.any(axis=0).all()
+        return np.stack([row_embedding(r[m == 1]) for r, m in zip(input_ids, attention_mask)])
+
+    enc.encode_tokens = fake_forward
+    words = st.text(alphabet="abc xyz,.", min_size=0, max_size=40)
+
+    @settings(max_examples=150, deadline=None)
+    @given(sentences=st.lists(words, min_size=0, max_size=20), batch_size=st.integers(1, 7),
+           prompt_name=st.sampled_from([None, "s2p_query", "empty"]))
+    def run(sentences, batch_size, prompt_name):
+        seen_batches.clear()
+        out = enc.encode(sentences, prompt_name=prompt_name, batch_size=batch_size)
+        assert out.shape == (len(sentences), enc.config.embed_dim)
+        prefix = enc.prompts[prompt_name] if prompt_name else ""
+        for s, got in zip(sentences, out):
+            want = row_embedding(enc.tokenizer.encode(prefix + s)[: enc.max_seq_length])
+            assert np.array_equal(got, want)
+        assert len(seen_batches) == -(-len(sentences) // batch_size)
+        assert all(b[0] <= batch_size for b in seen_batches)
+        if sentences:
+            # longest texts first: sequence lengths of the batches never increase by more than truncation allows
+            one = enc.encode(sentences[0], prompt_name=prompt_name)
+            assert one.shape == (enc.config.embed_dim,) and np.array_equal(one, out[0])
+
+    run()
+    import pytest
+
+    with pytest.raises(ValueError):
+        enc.encode(["a"], prompt_name="no_such_prompt")
+    with pytest.raises(ValueError):
+        enc.encode(["a"], precision="int8")
