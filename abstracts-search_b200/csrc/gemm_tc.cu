@@ -856,9 +856,10 @@ void gemm_bf16_tc_ex(int epi, int M, int N, int K, const void* A, int64_t lda, c
         const int64_t tm = ceil_div(M, 2 * BM);
         const int64_t cost256 = ceil_div(tm * ceil_div(N, 256), workers) * 256;
         const int64_t cost192 = ceil_div(tm * ceil_div(N, 192), workers) * 192;
-        // long-K GEMMs (FFN-down, K = 8960) are MMA-bound and gain from the finer wave balance of 192-column
-        // tiles earlier than the epilogue-bound short-K ones (r02i micro-bench, M = 16384: 334 vs 356 us)
-        if (cost192 * 100 < cost256 * (K >= 4096 ? 90 : 85)) variant = 3;
+        // (A looser threshold for long-K GEMMs — 192-column tiles for FFN-down at M = 16384, 7 waves instead of 6 x
+        // 256 — looked better in one micro-benchmark session and lost in five others; in situ, interleaved bench
+        // runs: 41.07 ms per step against 40.33 ms with 256-column tiles, profiles/r02ae_ffn_down_tiles.txt.)
+        if (cost192 * 100 < cost256 * 85) variant = 3;
       }
     }
   }
