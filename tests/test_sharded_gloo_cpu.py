@@ -139,10 +139,15 @@ def _worker(rank, world, port, out_dir):
     # the same batch SPREAD over the ranks: coarse where the slice lives, one all-gather of {queries | coarse ids}
     import torch
 
-    q2 = osynth.queries(7, 100, 2 * 6, d, nlist, n)
-    Ds, Is = sh.search_spread(torch.from_numpy(np.ascontiguousarray(q2[rank * 6:(rank + 1) * 6])), k)
+    q2 = osynth.queries(7, 100, 12, d, nlist, n)
+    per = 12 // world
+    Ds, Is = sh.search_spread(torch.from_numpy(np.ascontiguousarray(q2[rank * per:(rank + 1) * per])), k)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), D=D, I=I, total=total, local=local.ntotal, Ds=Ds, Is=Is)
     dist.destroy_process_group()
+
+
+def _cuts(world, n):
+    return [0, 1800, n] if world == 2 else [0, 1800, 3100, n]
 
 
 def _build_worker(rank, world, port, out_dir, spherical=False):
@@ -160,8 +165,8 @@ def _build_worker(rank, world, port, out_dir, spherical=False):
 
     d, nlist, n, nq, k, nprobe = 64, 16, 5000, 9, 6, 4
     x = osynth.corpus(11, 0, n, d, nlist)
-    # uneven contiguous slices: rank 0 holds [0, 1800), rank 1 the rest
-    cut = [0, 1800, n]
+    # uneven contiguous slices: rank 0 holds [0, 1800), the others share the rest
+    cut = _cuts(world, n)
     mine = x[cut[rank]:cut[rank + 1]]
     local = OracleShard(d, nlist, rank, world)
     local.cp = P.ClusteringParameters()
@@ -185,12 +190,11 @@ def _build_worker(rank, world, port, out_dir, spherical=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("spherical", [False, True])
-def test_distributed_train_and_add_world2_gloo(tmp_path, spherical):
+@pytest.mark.parametrize("spherical,world", [(False, 2), (True, 2), (True, 3)])
+def test_distributed_train_and_add_world2_gloo(tmp_path, spherical, world):
     """train_distributed == single-process k-means (exact on the lattice corpus, where fp32 sums do not
     depend on order), with and without ClusteringParameters.spherical; add_distributed routes every row
     to its list owner with global ids."""
-    world = 2
     mp.spawn(_build_worker, args=(world, _free_port(), str(tmp_path), spherical), nprocs=world, join=True)
     from oracle import ivf as oivf
     from oracle import synth as osynth
@@ -204,11 +208,11 @@ def test_distributed_train_and_add_world2_gloo(tmp_path, spherical):
     for r in res:
         assert np.array_equal(r["cent"], cent), "distributed k-means differs from the single-process oracle"
         assert int(r["total"]) == n
-    # the global batch order of the two add calls: [r0 first half, r1 first half, r0 second half, r1 second half]
-    cut = [0, 1800, n]
+    # the global batch order of the two add calls: [every rank's first half in rank order, then the second halves]
+    cut = _cuts(world, n)
     h = [int(r["h"]) for r in res]
-    order = np.concatenate([np.arange(cut[0], cut[0] + h[0]), np.arange(cut[1], cut[1] + h[1]),
-                            np.arange(cut[0] + h[0], cut[1]), np.arange(cut[1] + h[1], cut[2])])
+    order = np.concatenate([np.arange(cut[r], cut[r] + h[r]) for r in range(world)] +
+                           [np.arange(cut[r] + h[r], cut[r + 1]) for r in range(world)])
     ref = oivf.IVFFlat(d, nlist)
     ref.set_centroids(cent)
     ref.add(x[order])  # default ids = position in the global batch order
@@ -221,8 +225,9 @@ def test_distributed_train_and_add_world2_gloo(tmp_path, spherical):
         assert np.array_equal(r["I"], I) and np.array_equal(r["D"], D)
 
 
-def test_sharded_search_world2_gloo(tmp_path):
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_search_world2_gloo(tmp_path, world):
+    """world 3: 16 lists over 3 ranks (6 / 5 / 5), odd record sizes, a spread batch of 4 queries per rank."""
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     from oracle import ivf as oivf
     from oracle import synth as osynth
