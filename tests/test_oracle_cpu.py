@@ -187,3 +187,48 @@ def test_subsampling_uses_rand_perm():
     sub = x[perm[: k * 256]]
     perm2 = oivf.rand_perm(k * 256, 1235)
     assert np.array_equal(cent, sub[perm2[:k]])
+
+
+def test_numpy_and_c_restatements_agree_fuzz():
+    """hypothesis: the two independent restatements of the faiss search semantics (oracle/ivf.py in numpy,
+    oracle/ivf_oracle.c) on small lattice indexes — tiny integer components so that exact score ties are common,
+    empty lists, k larger than the probed vectors (-1 / -FLT_MAX padding), nprobe up to nlist, custom ids — must
+    return identical (D, I) for the flat search, the coarse quantiser and the IVF search."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=120, deadline=None)
+    @given(seed=st.integers(0, 2**31), d=st.sampled_from([2, 4, 8]), nlist=st.integers(1, 9), n=st.integers(0, 60),
+           nq=st.integers(1, 5), k=st.integers(1, 12), nprobe=st.integers(1, 9), amp=st.integers(1, 3))
+    def run(seed, d, nlist, n, nq, k, nprobe, amp):
+        rng = np.random.default_rng(seed)
+        nprobe = min(nprobe, nlist)
+        x = (rng.integers(-amp, amp + 1, (n, d)) / 4.0).astype(np.float32)
+        q = (rng.integers(-amp, amp + 1, (nq, d)) / 4.0).astype(np.float32)
+        cent = (rng.integers(-amp, amp + 1, (nlist, d)) / 4.0).astype(np.float32)
+        ids = rng.permutation(4 * n + 1)[:n].astype(np.int64)
+        flat = oivf.FlatIP(d)
+        flat.add(x)
+        Dn, In = flat.search(q, k, impl="numpy")
+        Dc, Ic = flat.search(q, k, impl="c")
+        assert np.array_equal(Dn, Dc) and np.array_equal(In, Ic)
+        ix = oivf.IVFFlat(d, nlist)
+        ix.set_centroids(cent)
+        ix.add(x, ids=ids)
+        assert int(ix.list_sizes().sum()) == n
+        dn, cn = ix.coarse(q, nprobe, impl="numpy")
+        dc, cc = ix.coarse(q, nprobe, impl="c")
+        assert np.array_equal(cn, cc) and np.array_equal(dn, dc)
+        Dn, In = ix.search(q, k, nprobe=nprobe, impl="numpy")
+        Dc, Ic = ix.search(q, k, nprobe=nprobe, impl="c")
+        assert np.array_equal(Dn, Dc) and np.array_equal(In, Ic)
+        # the result is the top-k by (score desc, id asc) of the probed lists' vectors, padded with (-FLT_MAX, -1)
+        s64 = q.astype(np.float64) @ x.T.astype(np.float64) if n else np.zeros((nq, 0))
+        lists = ix.assign(x) if n else np.zeros(0, np.int64)
+        for qi in range(nq):
+            probed = np.isin(lists, cn[qi])
+            cand = sorted((-s64[qi, j], int(ids[j])) for j in np.nonzero(probed)[0])[:k]
+            want = [c[1] for c in cand] + [-1] * (k - len(cand))
+            assert In[qi].tolist() == want
+            assert all(Dn[qi, len(cand):] == np.float32(-3.4028234663852886e38))
+
+    run()
