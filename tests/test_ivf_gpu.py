@@ -1029,3 +1029,51 @@ def test_large_query_batch_splits_internally(gpu_pkg):
     assert np.array_equal(Id.cpu().numpy(), Io) and np.array_equal(Dd.cpu().numpy(), Do)
     st = ix.last_stats()
     assert st["vectors"] == o.last_nscanned
+
+
+def test_small_index_fuzz_against_the_oracle(gpu_pkg):
+    """hypothesis: small indexes built from tiny integer components (exact arithmetic, exact score ties everywhere),
+    custom ids, empty lists, several add() calls, k beyond the probed vectors, nprobe up to nlist, zero rows — through
+    both fine-scan modes (fp32 ring / register scan; fp16 shortlist + re-score + fallback) and both dimensions' kernel
+    sets (d = 1024: shared-memory ring; d = 64: register scan).  (D, I) must equal the C oracle bit for bit."""
+    from hypothesis import given, settings, strategies as st
+
+    P = gpu_pkg
+
+    @settings(max_examples=60, deadline=None)
+    @given(seed=st.integers(0, 2**31), d=st.sampled_from([64, 1024]), nlist=st.integers(1, 12), n=st.integers(0, 200),
+           nq=st.integers(1, 6), k=st.integers(1, 40), nprobe=st.integers(1, 12), amp=st.integers(1, 2),
+           two_stage=st.sampled_from([0, 32, 64]), pieces=st.integers(1, 3))
+    def run(seed, d, nlist, n, nq, k, nprobe, amp, two_stage, pieces):
+        rng = np.random.default_rng(seed)
+        nprobe = min(nprobe, nlist)
+        # sparse rows keep the number of distinct scores small: ties between and within lists
+        def rows(m):
+            v = np.zeros((m, d), dtype=np.float32)
+            cols = rng.integers(0, d, (m, 3))
+            vals = rng.integers(-amp, amp + 1, (m, 3)).astype(np.float32) / 4.0
+            for j in range(3):
+                v[np.arange(m), cols[:, j]] += vals[:, j]
+            return v
+
+        x, q, c = rows(n), rows(nq), rows(nlist)
+        ids = rng.permutation(5 * n + 1)[:n].astype(np.int64)
+        ix = P.IndexIVFFlat(d, nlist)
+        if two_stage and d == 1024:
+            ix.set_two_stage(two_stage)
+        ix.set_centroids(c)
+        o = oivf.IVFFlat(d, nlist)
+        o.set_centroids(c)
+        cuts = np.linspace(0, n, pieces + 1).astype(int)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b > a:
+                ix.add_with_ids(x[a:b], ids[a:b])
+                o.add(x[a:b], ids=ids[a:b])
+        assert ix.ntotal == n and np.array_equal(ix.list_sizes(), o.list_sizes())
+        ix.nprobe = nprobe
+        D, I = ix.search(q, k)
+        Do, Io = o.search(q, k, nprobe=nprobe, impl="c")
+        assert np.array_equal(I, Io), (I, Io)
+        assert np.array_equal(D, Do)
+
+    run()
