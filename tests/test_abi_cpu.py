@@ -321,3 +321,53 @@ def test_encode_host_logic_fuzz(P):
         enc.encode(["a"], prompt_name="no_such_prompt")
     with pytest.raises(ValueError):
         enc.encode(["a"], precision="int8")
+
+
+def test_safetensors_reader_fuzz(tmp_path, P):
+    """hypothesis: files in the safetensors layout (u64 header length, JSON header padded with spaces as the real
+    writer does, tensors at arbitrary — also unaligned — offsets, F32 / BF16 / F16, scalars, empty tensors, unknown
+    dtypes skipped) read back exactly."""
+    import json
+    import struct
+    from importlib import import_module
+
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    enc = import_module("abstracts-search_b200.encoder")
+    case = [0]
+    shape = st.lists(st.integers(0, 5), min_size=0, max_size=3)
+    tensor = st.tuples(st.sampled_from(["F32", "BF16", "F16", "I64"]), shape)
+
+    @settings(max_examples=80, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(tensors=st.lists(tensor, min_size=0, max_size=6), pad=st.integers(0, 9), gap=st.integers(0, 3), seed=st.integers(0, 2**31))
+    def run(tensors, pad, gap, seed):
+        rng = np.random.default_rng(seed)
+        header, blobs, want, off = {"__metadata__": {"format": "pt"}}, [], {}, 0
+        for i, (dt, shp) in enumerate(tensors):
+            n = int(np.prod(shp)) if shp else 1
+            if dt == "F32":
+                a = rng.standard_normal(n).astype(np.float32)
+                want[f"t{i}"] = (a.reshape(shp), "F32")
+            elif dt == "BF16":
+                a = rng.integers(0, 1 << 16, n).astype(np.uint16)
+                want[f"t{i}"] = (a.reshape(shp), "BF16")
+            elif dt == "F16":
+                a = rng.standard_normal(n).astype(np.float16)
+                want[f"t{i}"] = (a.astype(np.float32).reshape(shp), "F32")
+            else:
+                a = rng.integers(0, 100, n).astype(np.int64)  # not a weight dtype: ignored by the reader
+            raw = a.tobytes() + b"\0" * gap  # gaps make the next tensor's offset unaligned
+            header[f"t{i}"] = {"dtype": dt, "shape": shp, "data_offsets": [off, off + a.nbytes]}
+            blobs.append(raw)
+            off += len(raw)
+        hj = json.dumps(header).encode() + b" " * pad
+        case[0] += 1
+        path = tmp_path / f"m{case[0]}.safetensors"
+        path.write_bytes(struct.pack("<Q", len(hj)) + hj + b"".join(blobs))
+        got = enc.read_safetensors(str(path))
+        assert set(got) == set(want)
+        for name, (arr, dt) in want.items():
+            assert got[name][1] == dt and got[name][0].shape == arr.shape
+            assert np.array_equal(np.asarray(got[name][0]), arr)
+
+    run()
