@@ -295,9 +295,9 @@ int absb_enc_forward_dev(absb_enc_t e, int B, int S, const int64_t* input_ids_de
 int absb_enc_last_hidden(absb_enc_t e, float* out, int64_t numel);
 /* FLOP count and kernel launches of the most recent forward. */
 int absb_enc_last_stats(absb_enc_t e, double* flops, int64_t* launches);
-/* Attention kernel: 1 (default) = persistent warp-specialised tcgen05 kernel for sequences of up to 256
- * tokens and the mma.sync kernel above that; 2 = the one-tile-per-CTA tcgen05 kernel; 0 = always the
- * mma.sync kernel (test hooks). */
+/* Attention kernel: 1 (default) = tcgen05 for every sequence length up to the model's 512 tokens (persistent
+ * warp-specialised kernel up to 256 tokens, two-key-block kernel for 257-512); 2 = the one-tile-per-CTA
+ * tcgen05 kernel up to 256 tokens; 0 = always the mma.sync kernel (test hooks). */
 int absb_enc_set_attention_impl(absb_enc_t e, int impl);
 /* Per-phase device timing with CUDA events recorded on the forward's own stream around every
  * kernel: on = 1 start, 0 stop, 2 start with counters reset.  get_profile synchronises and returns
