@@ -220,7 +220,7 @@ def test_compaction_plan_fuzz():
     import numpy as np
     from hypothesis import given, settings, strategies as st
 
-    @settings(max_examples=200, deadline=None)
+    @settings(max_examples=200, deadline=None, derandomize=True)
     @given(n=st.integers(1, 400), scratch=st.integers(1, 450), kind=st.integers(0, 4), seed=st.integers(0, 2**31))
     def run(n, scratch, kind, seed):
         rng = np.random.default_rng(seed)
@@ -296,7 +296,7 @@ def test_encode_host_logic_fuzz(P):
     enc.encode_tokens = fake_forward
     words = st.text(alphabet="abc xyz,.", min_size=0, max_size=40)
 
-    @settings(max_examples=150, deadline=None)
+    @settings(max_examples=150, deadline=None, derandomize=True)
     @given(sentences=st.lists(words, min_size=0, max_size=20), batch_size=st.integers(1, 7),
            prompt_name=st.sampled_from([None, "s2p_query", "empty"]))
     def run(sentences, batch_size, prompt_name):
@@ -338,7 +338,7 @@ def test_safetensors_reader_fuzz(tmp_path, P):
     shape = st.lists(st.integers(0, 5), min_size=0, max_size=3)
     tensor = st.tuples(st.sampled_from(["F32", "BF16", "F16", "I64"]), shape)
 
-    @settings(max_examples=80, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @settings(max_examples=80, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture])
     @given(tensors=st.lists(tensor, min_size=0, max_size=6), pad=st.integers(0, 9), gap=st.integers(0, 3), seed=st.integers(0, 2**31))
     def run(tensors, pad, gap, seed):
         rng = np.random.default_rng(seed)

@@ -205,7 +205,7 @@ def test_roundtrip_fuzz_array_sparse_and_ondisk(tmp_path):
     fio = _fio()
     counter = [0]
 
-    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @settings(max_examples=60, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture])
     @given(d=st.sampled_from([1, 3, 4, 16, 33]), nlist=st.integers(1, 40), fill=st.floats(0.0, 1.0),
            max_len=st.integers(1, 9), metric=st.sampled_from([0, 1]), nprobe=st.integers(1, 64), seed=st.integers(0, 2**31))
     def run(d, nlist, fill, max_len, metric, nprobe, seed):

@@ -1040,7 +1040,7 @@ def test_small_index_fuzz_against_the_oracle(gpu_pkg):
 
     P = gpu_pkg
 
-    @settings(max_examples=60, deadline=None)
+    @settings(max_examples=60, deadline=None, derandomize=True)
     @given(seed=st.integers(0, 2**31), d=st.sampled_from([64, 1024]), nlist=st.integers(1, 12), n=st.integers(0, 200),
            nq=st.integers(1, 6), k=st.integers(1, 40), nprobe=st.integers(1, 12), amp=st.integers(1, 2),
            two_stage=st.sampled_from([0, 32, 64]), pieces=st.integers(1, 3))

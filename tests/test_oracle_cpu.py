@@ -196,7 +196,7 @@ def test_numpy_and_c_restatements_agree_fuzz():
     return identical (D, I) for the flat search, the coarse quantiser and the IVF search."""
     from hypothesis import given, settings, strategies as st
 
-    @settings(max_examples=120, deadline=None)
+    @settings(max_examples=120, deadline=None, derandomize=True)
     @given(seed=st.integers(0, 2**31), d=st.sampled_from([2, 4, 8]), nlist=st.integers(1, 9), n=st.integers(0, 60),
            nq=st.integers(1, 5), k=st.integers(1, 12), nprobe=st.integers(1, 9), amp=st.integers(1, 3))
     def run(seed, d, nlist, n, nq, k, nprobe, amp):

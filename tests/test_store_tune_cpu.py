@@ -120,7 +120,7 @@ def test_store_fuzz_ragged_shards_and_row_groups(tmp_path):
         def train(self, x):
             self.trained = x.copy()
 
-    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture])
     @given(n=st.integers(1, 400), d=st.sampled_from([4, 64]), shard=st.integers(1, 500), group=st.integers(1, 300),
            cap=st.integers(1, 500), seed=st.integers(0, 2**31))
     def run(n, d, shard, group, cap, seed):
@@ -160,7 +160,7 @@ def test_pareto_and_recall_properties():
     P = _pkg()
     pt = st.tuples(st.integers(0, 20), st.integers(0, 20))
 
-    @settings(max_examples=300, deadline=None)
+    @settings(max_examples=300, deadline=None, derandomize=True)
     @given(pts=st.lists(pt, min_size=1, max_size=25))
     def run_pareto(pts):
         points = [{"nprobe": i, "recall": r / 20.0, "qps": float(q)} for i, (r, q) in enumerate(pts)]
@@ -178,7 +178,7 @@ def test_pareto_and_recall_properties():
 
     run_pareto()
 
-    @settings(max_examples=200, deadline=None)
+    @settings(max_examples=200, deadline=None, derandomize=True)
     @given(seed=st.integers(0, 2**31), nq=st.integers(1, 6), k=st.integers(1, 8), universe=st.integers(8, 40))
     def run_recall(seed, nq, k, universe):
         rng = np.random.default_rng(seed)
